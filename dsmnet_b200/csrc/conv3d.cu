@@ -1,0 +1,459 @@
+// op 3 — 3-D convolution block (k=3, pad=1) as a tcgen05/TMEM implicit GEMM, bf16 x bf16 -> fp32.
+// Replaces Conv3d / ConvTranspose3d + BatchNorm3d (+ReLU, +residual) of reference
+// models/psmnet/submodule.py:16-19, models/psmnet/stackhourglass.py:26-41,46-60,73-98,135-149,
+// models/util_conv.py:150-179 and models/gcnet.py:38-61.
+//
+// Data layout: activations are bf16 "padded NDHWC" [B][D+2][H+2][W+2][C] with a zero rim, so
+//   * the GEMM row of a voxel is its C contiguous channels (K-major operand, 64 or 128 bytes),
+//   * for stride-1 convolutions (and each output-parity class of a k3/s2 transposed conv) a
+//     filter tap is a CONSTANT row offset in the flattened voxel index, the zero rim supplies
+//     the padding, and an M tile is simply 128 consecutive voxels: one 2-D TMA box per tap;
+//   * stride-2 convolutions read 16x8 output patches through eight "parity sub-lattice" 5-D
+//     tensor maps (tap k along a dim -> parity k&1, half-index o+(k>>1)).
+// GEMM: M = 128 voxels (TMEM lanes), N = Cout (TMEM columns, fp32), K = taps * Cin walked in
+// (tap, 64- or 32-channel chunk) pipeline stages: TMA -> swizzled smem ring -> tcgen05.mma
+// issued by one thread -> tcgen05.commit frees the stage; the accumulator is read back with
+// tcgen05.ld and the epilogue applies the folded BatchNorm affine, residual add and ReLU and
+// writes bf16 NDHWC (or fp32 for the Cout=1 classifiers) straight from registers.
+// MODE_SHIFT loads one (kd,kh) row segment of 130 voxels and issues the three kw taps from it
+// with row-shifted matrix descriptors (3x less L2->smem traffic).
+//
+// Roofline: tensor pipe; algorithmic flops = 2*27*Cin*Cout*voxels (transposed: input voxels).
+#include "common.cuh"
+#include "ptx.cuh"
+#include <string.h>
+
+namespace {
+
+enum { MODE_FLAT = 0, MODE_SHIFT = 1, MODE_BOX = 2 };
+
+struct ConvMaps {
+    CUtensorMap a[8];    // FLAT/SHIFT use a[0]; BOX uses the 8 parity sub-lattices
+    CUtensorMap w;       // packed weights [27*CoutP][Cin]
+};
+
+struct ConvGeom {
+    int B, Di, Hi, Wi;       // input extent (unpadded)
+    int Do, Ho, Wo;          // output buffer extent (unpadded; may be a crop of the natural size)
+    int Cout;                // channels actually stored
+    int transposed, relu, y_f32;
+    int nchunks;             // Cin / KC
+    long long P;             // rows of the flattened padded input
+    int tiles_w, tiles_h;    // BOX tiling of the output plane (16 x 8 patches)
+    int desc_variant;        // 0: base_offset 0; 1: base_offset from address bits [7,10)
+    int cls_begin[9];
+    int a_off[27];           // FLAT/SHIFT: row offset of the tap; BOX: map | ow<<4 | oh<<5 | od<<6
+    int w_row[27];           // first row of the tap in the packed weights
+};
+
+__device__ int g_conv_timeouts = 0;
+
+__device__ __forceinline__ bool wait_bar(uint32_t bar, uint32_t parity) {
+    if (ptx::mbar_try_wait(bar, parity)) return true;
+    if (*reinterpret_cast<volatile int*>(&g_conv_timeouts)) return false;
+    const long long t0 = clock64();
+    while (!ptx::mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 1500000000LL || *reinterpret_cast<volatile int*>(&g_conv_timeouts)) {
+            atomicAdd(&g_conv_timeouts, 1);
+            return false;
+        }
+    }
+    return true;
+}
+
+template <int KC, int NP, int MODE>
+struct Cfg {
+    static constexpr int ROWB = KC * 2;
+    static constexpr int A_ROWS = (MODE == MODE_SHIFT) ? 130 : 128;
+    static constexpr int A_BYTES = ((A_ROWS * ROWB + 1023) / 1024) * 1024;
+    static constexpr int NB = (MODE == MODE_SHIFT) ? 3 : 1;
+    static constexpr int B_TILE = NP * ROWB;
+    static constexpr int B_BYTES = ((NB * B_TILE + 1023) / 1024) * 1024;
+    static constexpr int STAGE = A_BYTES + B_BYTES;
+    static constexpr int S_RAW = (96 * 1024) / STAGE;
+    static constexpr int STAGES = S_RAW > 6 ? 6 : (S_RAW < 2 ? 2 : S_RAW);
+    static constexpr int TX_BYTES = A_ROWS * ROWB + NB * B_TILE;
+    static constexpr int TMEM_COLS = NP < 32 ? 32 : NP;
+    static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * NP * 4;
+};
+
+template <int KC, int NP, int MODE>
+__global__ void __launch_bounds__(128)
+conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvGeom g,
+                    const float* __restrict__ scale, const float* __restrict__ shift,
+                    const void* __restrict__ residual, void* __restrict__ y) {
+    using C = Cfg<KC, NP, MODE>;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int Dp = g.Di + 2, Hp = g.Hi + 2, Wp = g.Wi + 2;
+    const long long plane = (long long)Hp * Wp, vol = plane * Dp;
+
+    // ---- which tile ---------------------------------------------------------------------
+    long long p0 = 0;
+    int cls = 0, bx_b = 0, bx_d = 0, bx_h = 0, bx_w = 0;
+    if (MODE == MODE_BOX) {
+        int t = blockIdx.x;
+        bx_w = t % g.tiles_w; t /= g.tiles_w;
+        bx_h = t % g.tiles_h; t /= g.tiles_h;
+        bx_d = t % g.Do;      bx_b = t / g.Do;
+    } else {
+        p0 = (long long)blockIdx.x * 128;
+        cls = blockIdx.y;
+        // tiles that lie completely inside a rim plane (d' = 0 or D+1) produce nothing
+        const long long pl = min(p0 + 127, g.P - 1);
+        const long long b0 = p0 / vol, b1 = pl / vol;
+        const int dp0 = (int)((p0 - b0 * vol) / plane), dp1 = (int)((pl - b1 * vol) / plane);
+        if (b0 == b1 && dp0 == dp1 && (dp0 == 0 || dp0 == Dp - 1)) return;
+    }
+
+    // ---- shared memory carve-up ---------------------------------------------------------
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = ptx::smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - raw);
+    const uint32_t bars = base + C::STAGES * C::STAGE;          // full[S], empty[S], accum, tmem slot
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + C::STAGES * C::STAGE + 8 * (2 * C::STAGES + 1));
+    float* s_scale = reinterpret_cast<float*>(base_ptr + C::STAGES * C::STAGE + 256);
+    float* s_shift = s_scale + NP;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
+    const uint32_t accum_bar = bars + 8u * (2 * C::STAGES);
+
+    if (tid < NP) {
+        s_scale[tid] = scale ? __ldg(scale + tid) : 1.f;
+        s_shift[tid] = shift ? __ldg(shift + tid) : 0.f;
+    }
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&maps.w);
+        ptx::prefetch_tensormap(&maps.a[0]);
+        for (int s = 0; s < C::STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+        ptx::mbar_init(accum_bar, 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), C::TMEM_COLS);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    const int tap0 = g.cls_begin[cls];
+    const int ntaps = g.cls_begin[cls + 1] - tap0;
+    const int ngroups = (MODE == MODE_SHIFT) ? ntaps / 3 : ntaps;
+    const int n_it = ngroups * g.nchunks;
+
+    if (warp == 0) {
+      if (lane == 0) {
+        // ================= TMA producer =================
+        for (int it = 0; it < n_it; ++it) {
+            const int s = it % C::STAGES;
+            const uint32_t ph = (uint32_t)(it / C::STAGES) & 1u;
+            wait_bar(empty_bar(s), ph ^ 1u);
+            const int grp = it / g.nchunks, kc = it - grp * g.nchunks;
+            const int t = tap0 + ((MODE == MODE_SHIFT) ? 3 * grp : grp);
+            const uint32_t sa = base + s * C::STAGE, sb = sa + C::A_BYTES;
+            ptx::mbar_arrive_expect_tx(full_bar(s), C::TX_BYTES);
+            if (MODE == MODE_BOX) {
+                const int code = g.a_off[t];
+                ptx::tma_load_5d(sa, &maps.a[code & 7], full_bar(s), kc * KC,
+                                 bx_w * 16 + ((code >> 4) & 1), bx_h * 8 + ((code >> 5) & 1),
+                                 bx_d + ((code >> 6) & 1), bx_b);
+            } else {
+                ptx::tma_load_2d(sa, &maps.a[0], full_bar(s), kc * KC, (int)(p0 + g.a_off[t]));
+            }
+#pragma unroll
+            for (int j = 0; j < C::NB; ++j)
+                ptx::tma_load_2d(sb + j * C::B_TILE, &maps.w, full_bar(s), kc * KC, g.w_row[t + j]);
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        // ================= MMA issuer =================
+        constexpr uint32_t idesc = ptx::make_idesc_bf16(NP);
+        for (int it = 0; it < n_it; ++it) {
+            const int s = it % C::STAGES;
+            const uint32_t ph = (uint32_t)(it / C::STAGES) & 1u;
+            wait_bar(full_bar(s), ph);
+            ptx::tc_fence_after();
+            const uint32_t sa = base + s * C::STAGE, sb = sa + C::A_BYTES;
+#pragma unroll
+            for (int j = 0; j < C::NB; ++j) {
+#pragma unroll
+                for (int k = 0; k < KC / 16; ++k) {
+                    const uint32_t a_addr = sa + j * C::ROWB + k * 32;
+                    const uint32_t b_addr = sb + j * C::B_TILE + k * 32;
+                    const uint32_t abo = g.desc_variant ? ((a_addr >> 7) & 7u) : 0u;
+                    const uint64_t ad = ptx::make_kmajor_desc(a_addr, C::ROWB, abo);
+                    const uint64_t bd = ptx::make_kmajor_desc(b_addr, C::ROWB, 0u);
+                    ptx::umma_bf16(tmem, ad, bd, idesc, (it | j | k) ? 1u : 0u);
+                }
+            }
+            ptx::umma_commit(empty_bar(s));      // frees the stage when these MMAs retire
+        }
+        ptx::umma_commit(accum_bar);             // accumulator complete
+      }
+    }
+    __syncwarp();
+
+    // ================= epilogue (all 4 warps, one TMEM lane = one voxel per thread) =======
+    wait_bar(accum_bar, 0u);
+    __syncwarp();
+    ptx::tc_fence_after();
+
+    const int r = tid;                           // row of the tile == TMEM lane
+    bool valid = false;
+    int ob = 0, od = 0, oh = 0, ow = 0;
+    if (MODE == MODE_BOX) {
+        ob = bx_b; od = bx_d; oh = bx_h * 8 + (r >> 4); ow = bx_w * 16 + (r & 15);
+        valid = (oh < g.Ho) && (ow < g.Wo);
+    } else {
+        const long long p = p0 + r;
+        if (p < g.P) {
+            const long long b = p / vol, rem = p - b * vol;
+            const int dp = (int)(rem / plane);
+            const int rem2 = (int)(rem - (long long)dp * plane);
+            const int hp = rem2 / Wp, wp = rem2 - hp * Wp;
+            if (dp >= 1 && dp <= g.Di && hp >= 1 && hp <= g.Hi && wp >= 1 && wp <= g.Wi) {
+                ob = (int)b;
+                if (g.transposed) {
+                    od = 2 * (dp - 1) + ((cls >> 2) & 1); oh = 2 * (hp - 1) + ((cls >> 1) & 1); ow = 2 * (wp - 1) + (cls & 1);
+                } else { od = dp - 1; oh = hp - 1; ow = wp - 1; }
+                valid = (od < g.Do) && (oh < g.Ho) && (ow < g.Wo);
+            }
+        }
+    }
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+
+    if (g.y_f32) {
+        // single output channel (classifier / GC-Net l37): fp32, unpadded [B][Do][Ho][Wo]
+        uint32_t v[16];
+        ptx::tmem_ld16(taddr, v);
+        ptx::tc_wait_ld();
+        if (valid) {
+            const size_t o = (((size_t)ob * g.Do + od) * g.Ho + oh) * g.Wo + ow;
+            float a = fmaf(__uint_as_float(v[0]), s_scale[0], s_shift[0]);
+            if (residual) a += __ldg(reinterpret_cast<const float*>(residual) + o);
+            if (g.relu) a = fmaxf(a, 0.f);
+            reinterpret_cast<float*>(y)[o] = a;
+        }
+    } else {
+        constexpr int CH = NP >= 32 ? 32 : 16;
+        const size_t o = ((((size_t)ob * (g.Do + 2) + od + 1) * (g.Ho + 2) + oh + 1) * (g.Wo + 2) + ow + 1) * (size_t)g.Cout;
+        const uint4* res = residual ? reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(residual) + o) : nullptr;
+        uint4* out = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y) + o);
+#pragma unroll
+        for (int c0 = 0; c0 < NP; c0 += CH) {
+            uint32_t v[CH];
+            if (CH == 32) ptx::tmem_ld32(taddr + c0, v); else ptx::tmem_ld16(taddr + c0, v);
+            ptx::tc_wait_ld();
+            if (valid) {
+#pragma unroll
+                for (int q = 0; q < CH / 8; ++q) {
+                    float f[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        f[i] = fmaf(__uint_as_float(v[q * 8 + i]), s_scale[c0 + q * 8 + i], s_shift[c0 + q * 8 + i]);
+                    if (res) {
+                        const uint4 rv = __ldg(res + (c0 / 8) + q);
+                        f[0] += bf16_lo(rv.x); f[1] += bf16_hi(rv.x); f[2] += bf16_lo(rv.y); f[3] += bf16_hi(rv.y);
+                        f[4] += bf16_lo(rv.z); f[5] += bf16_hi(rv.z); f[6] += bf16_lo(rv.w); f[7] += bf16_hi(rv.w);
+                    }
+                    if (g.relu) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+                    }
+                    uint4 ov;
+                    ov.x = pack_bf16x2(f[0], f[1]); ov.y = pack_bf16x2(f[2], f[3]);
+                    ov.z = pack_bf16x2(f[4], f[5]); ov.w = pack_bf16x2(f[6], f[7]);
+                    out[(c0 / 8) + q] = ov;
+                }
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem, C::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_tiled() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+        if (q != cudaDriverEntryPointSuccess) return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+bool encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                const cuuint32_t* box, int row_bytes) {
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) return false;
+    cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+    const CUtensorMapSwizzle sw = (row_bytes == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
+                     box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <int KC, int NP, int MODE>
+int launch_cfg(const ConvMaps& maps, const ConvGeom& g, dim3 grid, const float* scale, const float* shift,
+               const void* residual, void* y, cudaStream_t st) {
+    using C = Cfg<KC, NP, MODE>;
+    auto kern = conv3d_igemm_kernel<KC, NP, MODE>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<grid, 128, C::SMEM, st>>>(maps, g, scale, shift, residual, y);
+    return dsm_launch_status();
+}
+
+template <int MODE>
+int launch_mode(int KC, int NP, const ConvMaps& maps, const ConvGeom& g, dim3 grid, const float* scale,
+                const float* shift, const void* residual, void* y, cudaStream_t st) {
+#define DSM_CASE(kc, np) if (KC == kc && NP == np) return launch_cfg<kc, np, MODE>(maps, g, grid, scale, shift, residual, y, st);
+    DSM_CASE(32, 16) DSM_CASE(32, 32) DSM_CASE(32, 64) DSM_CASE(32, 128)
+    DSM_CASE(64, 16) DSM_CASE(64, 32) DSM_CASE(64, 64) DSM_CASE(64, 128)
+#undef DSM_CASE
+    return DSM_EUNSUPPORTED;
+}
+
+int conv3d_dispatch(const void* x, const void* w, const float* scale, const float* shift, const void* residual, void* y,
+                    int B, int Cin, int Cout, int D, int H, int W, int stride, int transposed, int relu, int y_dtype,
+                    int Do, int Ho, int Wo, int variant, void* stream) {
+    if (!x || !w || !y || B <= 0 || Cin <= 0 || Cout <= 0 || D <= 0 || H <= 0 || W <= 0) return DSM_EINVAL;
+    if (stride != 1 && stride != 2) return DSM_EINVAL;
+    if (transposed && stride != 2) return DSM_EUNSUPPORTED;
+    if (y_dtype != DSM_BF16 && y_dtype != DSM_F32) return DSM_EINVAL;
+    if (Cin != 32 && Cin != 64 && Cin != 128) return DSM_EUNSUPPORTED;
+    const int KC = (Cin == 32) ? 32 : 64;
+    int NP;
+    if (y_dtype == DSM_F32) { if (Cout != 1) return DSM_EUNSUPPORTED; NP = 16; }
+    else { if (Cout != 16 && Cout != 32 && Cout != 64 && Cout != 128) return DSM_EUNSUPPORTED; NP = Cout; }
+    if (!dsm_aligned16(x) || !dsm_aligned16(w) || !dsm_aligned16(y) || (residual && !dsm_aligned16(residual))) return DSM_EALIGN;
+    // natural output extent
+    int nDo, nHo, nWo;
+    if (transposed) { nDo = 2 * D; nHo = 2 * H; nWo = 2 * W; }
+    else if (stride == 2) { nDo = (D - 1) / 2 + 1; nHo = (H - 1) / 2 + 1; nWo = (W - 1) / 2 + 1; }
+    else { nDo = D; nHo = H; nWo = W; }
+    if (Do <= 0) { Do = nDo; Ho = nHo; Wo = nWo; }
+    if (Do > nDo || Ho > nHo || Wo > nWo) return DSM_EINVAL;
+
+    const int Dp = D + 2, Hp = H + 2, Wp = W + 2;
+    const long long P = (long long)B * Dp * Hp * Wp;
+    if (P > 0x7fffff00LL) return DSM_EUNSUPPORTED;
+
+    ConvMaps maps;
+    ConvGeom g;
+    memset(&g, 0, sizeof(g));
+    g.B = B; g.Di = D; g.Hi = H; g.Wi = W; g.Do = Do; g.Ho = Ho; g.Wo = Wo;
+    g.Cout = Cout; g.transposed = transposed; g.relu = relu; g.y_f32 = (y_dtype == DSM_F32);
+    g.nchunks = Cin / KC; g.P = P; g.desc_variant = variant & 1;
+    const int row_bytes = KC * 2;
+    const int mode = (!transposed && stride == 2) ? MODE_BOX : ((variant & 2) && !transposed ? MODE_SHIFT : MODE_FLAT);
+
+    {   // weights: [27*NP][Cin]
+        cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)27 * NP};
+        cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
+        cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)NP};
+        if (!encode_map(&maps.w, w, 2, dims, strides, box, row_bytes)) return DSM_EDRIVER;
+    }
+    dim3 grid;
+    if (mode == MODE_BOX) {
+        for (int q = 0; q < 8; ++q) {
+            const int pd = (q >> 2) & 1, ph = (q >> 1) & 1, pw = q & 1;
+            const char* basep = reinterpret_cast<const char*>(x) + (((size_t)pd * Hp + ph) * Wp + pw) * (size_t)Cin * 2;
+            cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)((Wp - pw + 1) / 2), (cuuint64_t)((Hp - ph + 1) / 2),
+                                  (cuuint64_t)((Dp - pd + 1) / 2), (cuuint64_t)B};
+            cuuint64_t strides[4] = {(cuuint64_t)2 * Cin * 2, (cuuint64_t)2 * Wp * Cin * 2,
+                                     (cuuint64_t)2 * Hp * Wp * Cin * 2, (cuuint64_t)Dp * Hp * Wp * Cin * 2};
+            cuuint32_t box[5] = {(cuuint32_t)KC, 16, 8, 1, 1};
+            if (!encode_map(&maps.a[q], basep, 5, dims, strides, box, row_bytes)) return DSM_EDRIVER;
+        }
+        g.cls_begin[0] = 0; g.cls_begin[1] = 27;
+        for (int kd = 0; kd < 3; ++kd) for (int kh = 0; kh < 3; ++kh) for (int kw = 0; kw < 3; ++kw) {
+            const int t = (kd * 3 + kh) * 3 + kw;
+            const int q = ((kd & 1) << 2) | ((kh & 1) << 1) | (kw & 1);
+            g.a_off[t] = q | ((kw >> 1) << 4) | ((kh >> 1) << 5) | ((kd >> 1) << 6);
+            g.w_row[t] = t * NP;
+        }
+        g.tiles_w = dsm_ceil_div(Wo, 16); g.tiles_h = dsm_ceil_div(Ho, 8);
+        const long long nt = (long long)B * Do * g.tiles_h * g.tiles_w;
+        if (nt > 0x7fffffffLL) return DSM_EUNSUPPORTED;
+        grid = dim3((unsigned)nt, 1, 1);
+    } else {
+        cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)P};
+        cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
+        cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)(mode == MODE_SHIFT ? 130 : 128)};
+        if (!encode_map(&maps.a[0], x, 2, dims, strides, box, row_bytes)) return DSM_EDRIVER;
+        for (int q = 1; q < 8; ++q) maps.a[q] = maps.a[0];
+        int ncls = 1;
+        if (!transposed) {
+            g.cls_begin[0] = 0; g.cls_begin[1] = 27;
+            for (int kd = 0; kd < 3; ++kd) for (int kh = 0; kh < 3; ++kh) for (int kw = 0; kw < 3; ++kw) {
+                const int t = (kd * 3 + kh) * 3 + kw;
+                g.a_off[t] = ((kd - 1) * Hp + (kh - 1)) * Wp + (kw - 1);
+                g.w_row[t] = t * NP;
+            }
+        } else {
+            // out[2j+par] : par 0 <- (k=1, in j) ; par 1 <- (k=0, in j+1), (k=2, in j)
+            ncls = 8;
+            int n = 0;
+            const int kk[2][2] = {{1, -1}, {0, 2}}, off[2][2] = {{0, 0}, {1, 0}}, cnt[2] = {1, 2};
+            for (int q = 0; q < 8; ++q) {
+                const int pd = (q >> 2) & 1, ph = (q >> 1) & 1, pw = q & 1;
+                g.cls_begin[q] = n;
+                for (int a = 0; a < cnt[pd]; ++a) for (int b2 = 0; b2 < cnt[ph]; ++b2) for (int c = 0; c < cnt[pw]; ++c) {
+                    g.a_off[n] = (off[pd][a] * Hp + off[ph][b2]) * Wp + off[pw][c];
+                    g.w_row[n] = ((kk[pd][a] * 3 + kk[ph][b2]) * 3 + kk[pw][c]) * NP;
+                    ++n;
+                }
+            }
+            g.cls_begin[8] = n;   // 27
+        }
+        grid = dim3((unsigned)dsm_ceil_div_ll(P, 128), ncls, 1);
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == MODE_BOX)   return launch_mode<MODE_BOX>(KC, NP, maps, g, grid, scale, shift, residual, y, st);
+    if (mode == MODE_SHIFT) return launch_mode<MODE_SHIFT>(KC, NP, maps, g, grid, scale, shift, residual, y, st);
+    return launch_mode<MODE_FLAT>(KC, NP, maps, g, grid, scale, shift, residual, y, st);
+}
+
+}  // namespace
+
+extern "C" int dsm_conv3d_fwd(const void* x, const void* w_packed, const float* scale, const float* shift,
+                              const void* residual, void* y,
+                              int B, int Cin, int Cout, int D, int H, int W,
+                              int stride, int transposed, int relu, int y_dtype,
+                              void* ws, size_t ws_bytes, void* stream) {
+    (void)ws; (void)ws_bytes;
+    return conv3d_dispatch(x, w_packed, scale, shift, residual, y, B, Cin, Cout, D, H, W, stride, transposed, relu,
+                           y_dtype, 0, 0, 0, /*variant=*/0, stream);
+}
+
+// Extended form: (Do,Ho,Wo) is the extent of the y / residual buffers when it is a crop of the
+// natural output size (the reference's myadd_3d / myAdd3d crop-to-min semantics,
+// stackhourglass.py:10-20, util_fun.py:41-51); `variant` bit0 = descriptor base-offset mode,
+// bit1 = MODE_SHIFT (row-shifted descriptors) for stride-1 convolutions.
+extern "C" int dsm_conv3d_fwd_ex(const void* x, const void* w_packed, const float* scale, const float* shift,
+                                 const void* residual, void* y,
+                                 int B, int Cin, int Cout, int D, int H, int W,
+                                 int stride, int transposed, int relu, int y_dtype,
+                                 int Do, int Ho, int Wo, int variant, void* stream) {
+    return conv3d_dispatch(x, w_packed, scale, shift, residual, y, B, Cin, Cout, D, H, W, stride, transposed, relu,
+                           y_dtype, Do, Ho, Wo, variant, stream);
+}
+
+// number of pipeline waits that timed out since the library was loaded (0 in a healthy run)
+extern "C" int dsm_debug_conv_timeouts(void) {
+    int v = -1;
+    if (cudaMemcpyFromSymbol(&v, g_conv_timeouts, sizeof(int)) != cudaSuccess) return -1;
+    return v;
+}

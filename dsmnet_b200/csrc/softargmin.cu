@@ -1,0 +1,223 @@
+// op 4 — soft-argmin disparity regression.
+// Replaces F.softmax (legacy implicit dim -> 1) + disparityregression of reference
+// models/psmnet/submodule.py:56-63 as used at models/psmnet/stackhourglass.py:155-166, the
+// GC-Net head models/gcnet.py:104-111 (softmax of MINUS the cost), and — fused — the trilinear
+// upsample that precedes it at stackhourglass.py:152-153,163.
+//   disp[b,y,x] = sum_d d * softmax_d(sign * cost[b,:,y,x])
+// Streaming kernels: every thread owns 4 consecutive pixels (128-bit loads), walks D in chunks
+// of 8 planes with a chunked online softmax (one rescale per chunk), fp32 throughout.
+// Algorithmic HBM bytes: 4*B*H*W*(D+1).
+#include "common.cuh"
+
+namespace {
+
+constexpr int DCH = 8;
+
+struct Online {   // running max m, sum s = sum e^(v-m), t = sum d*e^(v-m)
+    float m, s, t;
+    __device__ __forceinline__ void init() { m = -INFINITY; s = 0.f; t = 0.f; }
+    __device__ __forceinline__ void chunk(const float* v, int n, int d0) {
+        float cm = v[0];
+#pragma unroll
+        for (int i = 1; i < DCH; ++i) if (i < n) cm = fmaxf(cm, v[i]);
+        const float nm = fmaxf(m, cm);
+        const float sc = __expf(m - nm);     // exp(-inf) = 0 on the first chunk
+        s *= sc; t *= sc;
+#pragma unroll
+        for (int i = 0; i < DCH; ++i) if (i < n) {
+            const float e = __expf(v[i] - nm);
+            s += e; t = fmaf((float)(d0 + i), e, t);
+        }
+        m = nm;
+    }
+};
+
+template <bool VEC>
+__global__ void __launch_bounds__(128)
+softargmin_fwd_kernel(const float* __restrict__ cost, float* __restrict__ disp,
+                      int D, long long HW, long long nq /*pixel groups per batch item*/, float sign) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const int b = blockIdx.y;
+    constexpr int PV = VEC ? 4 : 1;
+    const float* c = cost + (size_t)b * D * HW + q * PV;
+    Online o[PV];
+#pragma unroll
+    for (int p = 0; p < PV; ++p) o[p].init();
+    for (int d0 = 0; d0 < D; d0 += DCH) {
+        const int n = min(DCH, D - d0);
+        float v[PV][DCH];
+#pragma unroll
+        for (int i = 0; i < DCH; ++i) if (i < n) {
+            if (VEC) {
+                const float4 t = ld_stream_f4(reinterpret_cast<const float4*>(c + (size_t)(d0 + i) * HW));
+                v[0][i] = sign * t.x; v[1 % PV][i] = sign * t.y; v[2 % PV][i] = sign * t.z; v[3 % PV][i] = sign * t.w;
+            } else {
+                v[0][i] = sign * ld_stream_f1(c + (size_t)(d0 + i) * HW);
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < PV; ++p) o[p].chunk(v[p], n, d0);
+    }
+    float* out = disp + (size_t)b * HW + q * PV;
+    if (VEC) {
+        *reinterpret_cast<float4*>(out) = make_float4(o[0].t / o[0].s, o[1 % PV].t / o[1 % PV].s,
+                                                      o[2 % PV].t / o[2 % PV].s, o[3 % PV].t / o[3 % PV].s);
+    } else {
+        out[0] = o[0].t / o[0].s;
+    }
+}
+
+// backward: gcost[b,d,y,x] = sign * p_d * (d - disp) * gdisp,  p = softmax_d(sign*cost)
+// pass 1 recomputes (m, s); pass 2 writes.  One thread per pixel (scalar, coalesced along x).
+__global__ void __launch_bounds__(256)
+softargmin_bwd_kernel(const float* __restrict__ cost, const float* __restrict__ disp,
+                      const float* __restrict__ gdisp, float* __restrict__ gcost,
+                      int D, long long HW, float sign) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const int b = blockIdx.y;
+    const float* c = cost + (size_t)b * D * HW + p;
+    float* gc = gcost + (size_t)b * D * HW + p;
+    float m = -INFINITY;
+    for (int d = 0; d < D; ++d) m = fmaxf(m, sign * __ldg(c + (size_t)d * HW));
+    float s = 0.f;
+    for (int d = 0; d < D; ++d) s += __expf(sign * __ldg(c + (size_t)d * HW) - m);
+    const float out = disp[(size_t)b * HW + p];
+    const float g = gdisp[(size_t)b * HW + p] * sign / s;
+    for (int d = 0; d < D; ++d) {
+        const float e = __expf(sign * __ldg(c + (size_t)d * HW) - m);
+        gc[(size_t)d * HW] = g * e * ((float)d - out);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+dispreg_fwd_kernel(const float* __restrict__ prob, float* __restrict__ disp, int D, long long HW) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const int b = blockIdx.y;
+    const float* c = prob + (size_t)b * D * HW + p;
+    float t = 0.f;
+#pragma unroll 8
+    for (int d = 0; d < D; ++d) t = fmaf((float)d, ld_stream_f1(c + (size_t)d * HW), t);
+    disp[(size_t)b * HW + p] = t;
+}
+
+__global__ void __launch_bounds__(256)
+dispreg_bwd_kernel(const float* __restrict__ gdisp, float* __restrict__ gprob, int D, long long HW) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const int b = blockIdx.y;
+    const float g = gdisp[(size_t)b * HW + p];
+    float* o = gprob + (size_t)b * D * HW + p;
+    for (int d = 0; d < D; ++d) o[(size_t)d * HW] = (float)d * g;
+}
+
+// ---------------------------------------------------------------------------------------
+// Fused head: trilinear x-upsample of the low-res cost + softmax over D + regression.
+// The (h,w) interpolation weights do not depend on d, so each thread keeps the two bilinearly
+// interpolated low-res planes that bracket the current d and refreshes one of them whenever
+// the low-res index advances (warp-uniform: it depends on d only).  Reads 4*B*Dl*Hl*Wl bytes
+// (L1/L2 resident), writes 4*B*H*W; bound by the exp (SFU) rate, not HBM.
+// Index/weight arithmetic follows ATen's area_pixel_compute_source_index (fp32).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void src_index(int dst, float scale, int in_size, int align_corners, int& i0, int& i1, float& l1) {
+    float real;
+    if (align_corners) real = scale * (float)dst;
+    else { real = scale * ((float)dst + 0.5f) - 0.5f; if (real < 0.f) real = 0.f; }
+    i0 = min((int)floorf(real), in_size - 1);
+    l1 = fminf(fmaxf(real - (float)i0, 0.f), 1.f);
+    i1 = min(i0 + 1, in_size - 1);
+}
+
+__global__ void __launch_bounds__(128)
+upsample_softargmin_kernel(const float* __restrict__ cost, float* __restrict__ disp,
+                           int Dl, int Hl, int Wl, int D, int H, int W,
+                           float sd, float sh, float sw, int align_corners) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, b = blockIdx.z;
+    if (x >= W) return;
+    int h0, h1, w0, w1; float lh1, lw1;
+    src_index(y, sh, Hl, align_corners, h0, h1, lh1);
+    src_index(x, sw, Wl, align_corners, w0, w1, lw1);
+    const float lh0 = 1.f - lh1, lw0 = 1.f - lw1;
+    const float* base = cost + (size_t)b * Dl * Hl * Wl;
+    const size_t pl = (size_t)Hl * Wl;
+    const int o00 = h0 * Wl + w0, o01 = h0 * Wl + w1, o10 = h1 * Wl + w0, o11 = h1 * Wl + w1;
+    auto plane = [&](int dl) -> float {
+        const float* p = base + (size_t)dl * pl;
+        return lh0 * (lw0 * __ldg(p + o00) + lw1 * __ldg(p + o01)) + lh1 * (lw0 * __ldg(p + o10) + lw1 * __ldg(p + o11));
+    };
+    int cur0 = -1, cur1 = -1;
+    float c0 = 0.f, c1 = 0.f;
+    Online o; o.init();
+    for (int dd = 0; dd < D; dd += DCH) {
+        const int n = min(DCH, D - dd);
+        float v[DCH];
+#pragma unroll
+        for (int i = 0; i < DCH; ++i) if (i < n) {
+            int d0, d1; float ld1;
+            src_index(dd + i, sd, Dl, align_corners, d0, d1, ld1);
+            if (d0 != cur0) { if (d0 == cur1) c0 = c1; else c0 = plane(d0); cur0 = d0; }
+            if (d1 != cur1) { c1 = (d1 == cur0) ? c0 : plane(d1); cur1 = d1; }
+            v[i] = (1.f - ld1) * c0 + ld1 * c1;
+        }
+        o.chunk(v, n, dd);
+    }
+    disp[((size_t)b * H + y) * W + x] = o.t / o.s;
+}
+
+}  // namespace
+
+extern "C" int dsm_softargmin_fwd(const float* cost, float* disp, int B, int D, int H, int W, float sign, void* stream) {
+    if (!cost || !disp || B <= 0 || D <= 0 || H <= 0 || W <= 0) return DSM_EINVAL;
+    if (B > 65535) return DSM_EUNSUPPORTED;
+    const long long HW = (long long)H * W;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((HW & 3) == 0 && dsm_aligned16(cost) && dsm_aligned16(disp)) {
+        const long long nq = HW / 4;
+        softargmin_fwd_kernel<true><<<dim3((unsigned)dsm_ceil_div_ll(nq, 128), B), 128, 0, st>>>(cost, disp, D, HW, nq, sign);
+    } else {
+        softargmin_fwd_kernel<false><<<dim3((unsigned)dsm_ceil_div_ll(HW, 128), B), 128, 0, st>>>(cost, disp, D, HW, HW, sign);
+    }
+    return dsm_launch_status();
+}
+
+extern "C" int dsm_softargmin_bwd(const float* cost, const float* disp, const float* gdisp, float* gcost,
+                                  int B, int D, int H, int W, float sign, void* stream) {
+    if (!cost || !disp || !gdisp || !gcost || B <= 0 || D <= 0 || H <= 0 || W <= 0) return DSM_EINVAL;
+    if (B > 65535) return DSM_EUNSUPPORTED;
+    const long long HW = (long long)H * W;
+    softargmin_bwd_kernel<<<dim3((unsigned)dsm_ceil_div_ll(HW, 256), B), 256, 0, (cudaStream_t)stream>>>(cost, disp, gdisp, gcost, D, HW, sign);
+    return dsm_launch_status();
+}
+
+extern "C" int dsm_disparity_regression_fwd(const float* prob, float* disp, int B, int D, int H, int W, void* stream) {
+    if (!prob || !disp || B <= 0 || D <= 0 || H <= 0 || W <= 0) return DSM_EINVAL;
+    if (B > 65535) return DSM_EUNSUPPORTED;
+    const long long HW = (long long)H * W;
+    dispreg_fwd_kernel<<<dim3((unsigned)dsm_ceil_div_ll(HW, 256), B), 256, 0, (cudaStream_t)stream>>>(prob, disp, D, HW);
+    return dsm_launch_status();
+}
+
+extern "C" int dsm_disparity_regression_bwd(const float* gdisp, float* gprob, int B, int D, int H, int W, void* stream) {
+    if (!gdisp || !gprob || B <= 0 || D <= 0 || H <= 0 || W <= 0) return DSM_EINVAL;
+    if (B > 65535) return DSM_EUNSUPPORTED;
+    const long long HW = (long long)H * W;
+    dispreg_bwd_kernel<<<dim3((unsigned)dsm_ceil_div_ll(HW, 256), B), 256, 0, (cudaStream_t)stream>>>(gdisp, gprob, D, HW);
+    return dsm_launch_status();
+}
+
+extern "C" int dsm_upsample_softargmin_fwd(const float* cost_lr, float* disp, int B, int Dl, int Hl, int Wl,
+                                           int D, int H, int W, int align_corners, void* stream) {
+    if (!cost_lr || !disp || B <= 0 || Dl <= 0 || Hl <= 0 || Wl <= 0 || D <= 0 || H <= 0 || W <= 0) return DSM_EINVAL;
+    if (H > 65535 || B > 65535) return DSM_EUNSUPPORTED;
+    // ATen: align_corners -> (in-1)/(out-1) (0 when out==1); otherwise in/out; all in fp32
+    auto scale = [&](int in, int out) -> float {
+        if (align_corners) return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
+        return (float)in / (float)out;
+    };
+    upsample_softargmin_kernel<<<dim3(dsm_ceil_div(W, 128), H, B), 128, 0, (cudaStream_t)stream>>>(
+        cost_lr, disp, Dl, Hl, Wl, D, H, W, scale(Dl, D), scale(Hl, H), scale(Wl, W), align_corners);
+    return dsm_launch_status();
+}

@@ -1,0 +1,277 @@
+// op 2 — concatenation cost volume (PSMNet / GC-Net), plus the layout converters that sit at
+// the reference boundary of the 3-D stack.
+// Replaces the Python loops at reference models/psmnet/stackhourglass.py:124-133 (PSM),
+// models/gcnet.py:131-135 (GC) and models/gcnet.py:157-164 (GC right-reference volume):
+//   PSM      : vol[b,c,d,y,x]   = fL[b,c,y,x]   (x>=d else 0)   vol[b,C+c,d,y,x] = fR[b,c,y,x-d] (x>=d else 0)
+//   GC       : vol[b,c,d,y,x]   = fL[b,c,y,x]   (all x)         vol[b,C+c,d,y,x] = fR[b,c,y,x-d] (x>=d else 0)
+//   GC_RIGHT : vol[b,c,d,y,x]   = fR[b,c,y,x]   (all x)         vol[b,C+c,d,y,x] = fL[b,c,y,x+d] (x+d<W else 0)
+// Pure copies, so results are bit-exact (the bf16 variant is RNE of the same values).
+// HBM-write bound: algorithmic bytes = 4*B*H*W*2C (read) + e*B*2C*D*H*W (write), e = 4 or 2.
+#include "common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------
+// NCDHW fp32 (the reference's layout).  CTA = (y, channel ch of 2C, b): the source row is
+// staged once in shared memory, then D rows of W floats are streamed out with 128-bit stores.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+concat_ncdhw_kernel(const float* __restrict__ fL, const float* __restrict__ fR, float* __restrict__ out,
+                    int C, int D, int H, int W, int mode) {
+    extern __shared__ __align__(16) float row[];       // [W]
+    const int y = blockIdx.x, ch = blockIdx.y, b = blockIdx.z;
+    const bool second = ch >= C;
+    const int c = second ? ch - C : ch;
+    const float* src;
+    if (mode == DSM_VOL_GC_RIGHT) src = second ? fL : fR; else src = second ? fR : fL;
+    src += (((size_t)b * C + c) * H + y) * W;
+    for (int x = threadIdx.x; x < W; x += blockDim.x) row[x] = __ldg(src + x);
+    __syncthreads();
+
+    float* o = out + ((((size_t)b * 2 * C + ch) * D) * H + y) * W;
+    const size_t dstride = (size_t)H * W;
+    // shift of the source index and zero region per disparity
+    //   first half : PSM -> zero for x<d, no shift; GC/GC_RIGHT -> plain copy
+    //   second half: PSM/GC -> src[x-d], zero for x<d; GC_RIGHT -> src[x+d], zero for x+d>=W
+    const bool vec = ((W & 3) == 0);
+    for (int d = 0; d < D; ++d) {
+        int shift = 0, lo = 0, hi = W;                  // out[x] = row[x+shift] for lo<=x<hi else 0
+        if (!second) { if (mode == DSM_VOL_PSM) lo = d; }
+        else if (mode == DSM_VOL_GC_RIGHT) { shift = d; hi = W - d; }
+        else { shift = -d; lo = d; }
+        if (lo > W) lo = W;
+        if (hi < 0) hi = 0;
+        float* od = o + d * dstride;
+        if (vec) {
+            for (int xq = threadIdx.x; xq < (W >> 2); xq += blockDim.x) {
+                const int x = xq << 2;
+                float v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int xx = x + j;
+                    v[j] = (xx >= lo && xx < hi) ? row[xx + shift] : 0.f;
+                }
+                st_stream_f4(reinterpret_cast<float4*>(od + x), make_float4(v[0], v[1], v[2], v[3]));
+            }
+        } else {
+            for (int x = threadIdx.x; x < W; x += blockDim.x)
+                od[x] = (x >= lo && x < hi) ? row[x + shift] : 0.f;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Padded NDHWC bf16 (the 3-D stack's layout): [B][D+2][H+2][W+2][2C], zero rim included.
+// CTA = (padded row y', slab of d', b).  The two feature rows are transposed once into shared
+// memory as bf16 [x][C]; every voxel is then 2C*2 bytes = a run of 16-byte chunks, and a padded
+// row of the volume is one contiguous (W+2)*2C*2-byte stream written with 128-bit stores.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+concat_ndhwc_bf16_kernel(const float* __restrict__ fL, const float* __restrict__ fR, uint4* __restrict__ out,
+                         int C, int D, int H, int W, int mode, int dslab) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(smem_raw);          // first half source  [W][C]
+    __nv_bfloat16* sB = sA + (size_t)W * C;                                    // second half source [W][C]
+    const int yp = blockIdx.x, b = blockIdx.z;
+    const int dp0 = blockIdx.y * dslab;
+    const int dp1 = min(dp0 + dslab, D + 2);
+    const int Wp = W + 2, Hp = H + 2;
+    const int cpv = (2 * C) / 8;          // 16-byte chunks per voxel
+    const int half = cpv / 2;
+    const bool yrim = (yp == 0 || yp == H + 1);
+
+    if (!yrim) {
+        const int y = yp - 1;
+        const float* a = (mode == DSM_VOL_GC_RIGHT ? fR : fL) + ((size_t)b * C * H + y) * W;
+        const float* r = (mode == DSM_VOL_GC_RIGHT ? fL : fR) + ((size_t)b * C * H + y) * W;
+        const size_t plane = (size_t)H * W;
+        for (int i = threadIdx.x; i < C * W; i += blockDim.x) {
+            const int c = i / W, x = i - c * W;
+            sA[x * C + c] = __float2bfloat16_rn(__ldg(a + c * plane + x));
+            sB[x * C + c] = __float2bfloat16_rn(__ldg(r + c * plane + x));
+        }
+    }
+    __syncthreads();
+
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    const uint4* vA = reinterpret_cast<const uint4*>(sA);
+    const uint4* vB = reinterpret_cast<const uint4*>(sB);
+    const int row_chunks = Wp * cpv;
+    for (int dp = dp0; dp < dp1; ++dp) {
+        uint4* orow = out + (((size_t)b * (D + 2) + dp) * Hp + yp) * (size_t)row_chunks;
+        const bool rim = yrim || dp == 0 || dp == D + 1;
+        const int d = dp - 1;
+        for (int i = threadIdx.x; i < row_chunks; i += blockDim.x) {
+            uint4 v = zero;
+            if (!rim) {
+                const int xp = i / cpv, k = i - xp * cpv;
+                const int x = xp - 1;
+                if (xp >= 1 && xp <= W) {
+                    if (k < half) {
+                        if (mode != DSM_VOL_PSM || x >= d) v = vA[x * half + k];
+                    } else if (mode == DSM_VOL_GC_RIGHT) {
+                        if (x + d < W) v = vB[(x + d) * half + (k - half)];
+                    } else {
+                        if (x >= d) v = vB[(x - d) * half + (k - half)];
+                    }
+                }
+            }
+            st_stream_u4(orow + i, v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// backward, NCDHW fp32:  gA[b,c,y,x] = sum_d g[b,c,d,y,x] (PSM: only d<=x)
+//                        gB[b,c,y,x'] = sum_d g[b,C+c,d,y,x'+d] (GC_RIGHT: x'-d), where it exists
+// one thread per (b,c,y,x); reads are coalesced along x for every d.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+concat_bwd_ncdhw_kernel(const float* __restrict__ g, float* __restrict__ gL, float* __restrict__ gR,
+                        int B, int C, int D, int H, int W, int mode) {
+    const long long n = (long long)B * C * H * W;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int x = (int)(i % W);
+    long long t = i / W;
+    const int y = (int)(t % H); t /= H;
+    const int c = (int)(t % C);
+    const int b = (int)(t / C);
+    const size_t dstride = (size_t)H * W;
+    const float* g1 = g + ((((size_t)b * 2 * C + c) * D) * H + y) * W;
+    const float* g2 = g + ((((size_t)b * 2 * C + C + c) * D) * H + y) * W;
+    float s1 = 0.f, s2 = 0.f;
+    const int d1 = (mode == DSM_VOL_PSM) ? min(D, x + 1) : D;
+    for (int d = 0; d < d1; ++d) s1 += ld_stream_f1(g1 + d * dstride + x);
+    if (mode == DSM_VOL_GC_RIGHT) {
+        const int d2 = min(D, x + 1);                 // source index x' = x, taken at volume x'-d >= 0
+        for (int d = 0; d < d2; ++d) s2 += ld_stream_f1(g2 + d * dstride + x - d);
+    } else {
+        const int d2 = min(D, W - x);                 // volume position x+d < W
+        for (int d = 0; d < d2; ++d) s2 += ld_stream_f1(g2 + d * dstride + x + d);
+    }
+    // first half belongs to fL (fR for GC_RIGHT); second half to the other one
+    if (mode == DSM_VOL_GC_RIGHT) { gR[i] = s1; gL[i] = s2; }
+    else                          { gL[i] = s1; gR[i] = s2; }
+}
+
+// ---------------------------------------------------------------------------------------
+// NCDHW fp32 <-> padded NDHWC bf16.  CTA = (y', d', b); transposes a [C][W] slab through smem.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_ndhwc_kernel(const float* __restrict__ x, uint4* __restrict__ y, int C, int D, int H, int W) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __nv_bfloat16* s = reinterpret_cast<__nv_bfloat16*>(smem_raw);            // [W][C]
+    const int yp = blockIdx.x, dp = blockIdx.y, b = blockIdx.z;
+    const int Wp = W + 2, Hp = H + 2;
+    const int cpv = C / 8;
+    const bool rim = (yp == 0 || yp == H + 1 || dp == 0 || dp == D + 1);
+    if (!rim) {
+        const float* src = x + (((size_t)b * C * D + (dp - 1)) * H + (yp - 1)) * W;
+        const size_t cstride = (size_t)D * H * W;
+        for (int i = threadIdx.x; i < C * W; i += blockDim.x) {
+            const int c = i / W, xx = i - c * W;
+            s[xx * C + c] = __float2bfloat16_rn(__ldg(src + c * cstride + xx));
+        }
+    }
+    __syncthreads();
+    const uint4* v = reinterpret_cast<const uint4*>(s);
+    uint4* orow = y + (((size_t)b * (D + 2) + dp) * Hp + yp) * (size_t)(Wp * cpv);
+    for (int i = threadIdx.x; i < Wp * cpv; i += blockDim.x) {
+        const int xp = i / cpv, k = i - xp * cpv;
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (!rim && xp >= 1 && xp <= W) val = v[(xp - 1) * cpv + k];
+        st_stream_u4(orow + i, val);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+unpack_ndhwc_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int C, int D, int H, int W) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __nv_bfloat16* s = reinterpret_cast<__nv_bfloat16*>(smem_raw);            // [W][C+2] (padded against conflicts)
+    const int yy = blockIdx.x, d = blockIdx.y, b = blockIdx.z;
+    const int Wp = W + 2, Hp = H + 2;
+    const int CP = C + 2;
+    const __nv_bfloat16* src = x + ((((size_t)b * (D + 2) + d + 1) * Hp + yy + 1) * Wp + 1) * (size_t)C;
+    for (int i = threadIdx.x; i < W * C; i += blockDim.x) {
+        const int xx = i / C, c = i - xx * C;
+        s[xx * CP + c] = src[i];
+    }
+    __syncthreads();
+    float* dst = y + (((size_t)b * C * D + d) * H + yy) * W;
+    const size_t cstride = (size_t)D * H * W;
+    for (int i = threadIdx.x; i < C * W; i += blockDim.x) {
+        const int c = i / W, xx = i - c * W;
+        dst[c * cstride + xx] = __bfloat162float(s[xx * CP + c]);
+    }
+}
+
+}  // namespace
+
+extern "C" int dsm_concat_volume_fwd(const float* fL, const float* fR, void* out,
+                                     int B, int C, int D, int H, int W,
+                                     int mode, int out_dtype, int out_layout, void* stream) {
+    if (!fL || !fR || !out || B <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0) return DSM_EINVAL;
+    if (mode < DSM_VOL_PSM || mode > DSM_VOL_GC_RIGHT) return DSM_EINVAL;
+    if (B > 65535 || 2 * C > 65535) return DSM_EUNSUPPORTED;
+    if (!dsm_aligned16(out)) return DSM_EALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (out_dtype == DSM_F32 && out_layout == DSM_NCDHW) {
+        const size_t smem = (size_t)W * sizeof(float);
+        if (smem > 48 * 1024) return DSM_EUNSUPPORTED;
+        concat_ncdhw_kernel<<<dim3(H, 2 * C, B), 128, smem, st>>>(fL, fR, (float*)out, C, D, H, W, mode);
+        return dsm_launch_status();
+    }
+    if (out_dtype == DSM_BF16 && out_layout == DSM_NDHWC_PADDED) {
+        if (C % 8 != 0) return DSM_EUNSUPPORTED;
+        const size_t smem = 2 * (size_t)W * C * sizeof(__nv_bfloat16);
+        if (smem > 200 * 1024) return DSM_EUNSUPPORTED;
+        cudaError_t e = cudaFuncSetAttribute(concat_ndhwc_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        // enough CTAs for >= 4 waves over 148 SMs: split the padded disparity range into slabs
+        int slabs = dsm_ceil_div(4 * DSM_NUM_SMS_B200, (H + 2) * B);
+        if (slabs < 1) slabs = 1;
+        if (slabs > D + 2) slabs = D + 2;
+        const int dslab = dsm_ceil_div(D + 2, slabs);
+        slabs = dsm_ceil_div(D + 2, dslab);
+        concat_ndhwc_bf16_kernel<<<dim3(H + 2, slabs, B), 256, smem, st>>>(fL, fR, (uint4*)out, C, D, H, W, mode, dslab);
+        return dsm_launch_status();
+    }
+    return DSM_EUNSUPPORTED;
+}
+
+extern "C" int dsm_concat_volume_bwd(const void* gout, float* gL, float* gR,
+                                     int B, int C, int D, int H, int W,
+                                     int mode, int dtype, int layout, void* stream) {
+    if (!gout || !gL || !gR || B <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0) return DSM_EINVAL;
+    if (mode < DSM_VOL_PSM || mode > DSM_VOL_GC_RIGHT) return DSM_EINVAL;
+    if (dtype != DSM_F32 || layout != DSM_NCDHW) return DSM_EUNSUPPORTED;
+    const long long n = (long long)B * C * H * W;
+    const long long blocks = dsm_ceil_div_ll(n, 256);
+    if (blocks > 0x7fffffffLL) return DSM_EUNSUPPORTED;
+    concat_bwd_ncdhw_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float*)gout, gL, gR, B, C, D, H, W, mode);
+    return dsm_launch_status();
+}
+
+extern "C" int dsm_pack_ndhwc(const float* x, void* y, int B, int C, int D, int H, int W, void* stream) {
+    if (!x || !y || B <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0) return DSM_EINVAL;
+    if (C % 8 != 0 || D + 2 > 65535 || B > 65535) return DSM_EUNSUPPORTED;
+    if (!dsm_aligned16(y)) return DSM_EALIGN;
+    const size_t smem = (size_t)W * C * sizeof(__nv_bfloat16);
+    if (smem > 200 * 1024) return DSM_EUNSUPPORTED;
+    cudaError_t e = cudaFuncSetAttribute(pack_ndhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    pack_ndhwc_kernel<<<dim3(H + 2, D + 2, B), 256, smem, (cudaStream_t)stream>>>(x, (uint4*)y, C, D, H, W);
+    return dsm_launch_status();
+}
+
+extern "C" int dsm_unpack_ndhwc(const void* x, float* y, int B, int C, int D, int H, int W, void* stream) {
+    if (!x || !y || B <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0) return DSM_EINVAL;
+    if (D > 65535 || B > 65535) return DSM_EUNSUPPORTED;
+    const size_t smem = (size_t)W * (C + 2) * sizeof(__nv_bfloat16);
+    if (smem > 200 * 1024) return DSM_EUNSUPPORTED;
+    cudaError_t e = cudaFuncSetAttribute(unpack_ndhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    unpack_ndhwc_kernel<<<dim3(H, D, B), 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, y, C, D, H, W);
+    return dsm_launch_status();
+}

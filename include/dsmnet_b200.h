@@ -1,0 +1,133 @@
+/*
+ * dsmnet_b200.h — C-ABI of the B200-native (sm_100a) stereo cost-volume hot path.
+ *
+ * The reference (sunshinnnn/DSMnet) has no native layer and no FFI: its hot path is Python
+ * that composes stock torch ops.  Each entry point below replaces one such composition; the
+ * reference lines it replaces are cited next to it (paths relative to the reference root).
+ *
+ * Conventions (all entry points):
+ *   - every pointer is a DEVICE pointer into memory owned by the caller; the library never
+ *     allocates, frees or retains pointers; there is no hidden scratch;
+ *   - `stream` is the caller's cudaStream_t (CUstream); all work is enqueued on it
+ *     asynchronously: no host synchronisation, CUDA-graph capturable;
+ *   - return 0 = ok, >0 = cudaError_t of a failed launch, <0 = DSM_E* below;
+ *   - re-entrant from any host thread, no global mutable state; the caller has made the
+ *     target device current;
+ *   - tensors are dense, row-major in the order written (last index fastest).
+ *
+ * There is no CPU fallback anywhere behind this interface.
+ */
+#ifndef DSMNET_B200_H
+#define DSMNET_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSM_ABI_VERSION 1
+
+/* error codes (<0) */
+#define DSM_EINVAL       (-1)  /* bad shape / null pointer / bad enum                   */
+#define DSM_EUNSUPPORTED (-2)  /* shape or mode outside what the kernels are built for  */
+#define DSM_EALIGN       (-3)  /* pointer not aligned as the kernel requires (16 B)     */
+#define DSM_EDRIVER      (-4)  /* driver entry point (cuTensorMapEncodeTiled) missing   */
+
+/* concat-volume modes */
+#define DSM_VOL_PSM      0 /* models/psmnet/stackhourglass.py:124-133 : both halves 0 for x<d */
+#define DSM_VOL_GC       1 /* models/gcnet.py:131-135 : left half copied for every x          */
+#define DSM_VOL_GC_RIGHT 2 /* models/gcnet.py:157-164 (xR) : right-reference volume           */
+
+/* dtypes / layouts of a cost volume */
+#define DSM_F32  0
+#define DSM_BF16 1
+#define DSM_NCDHW        0 /* [B][2C][D][H][W]            — the reference's layout            */
+#define DSM_NDHWC_PADDED 1 /* [B][D+2][H+2][W+2][2C]      — the 3-D stack's layout, zero rim  */
+
+int         dsm_abi_version(void);
+const char* dsm_strerror(int code);
+
+/* ---- op 1: 1-D correlation. Replaces Corr1d.forward, models/util_conv.py:71-81 ---------
+ * out[b,d,y,x] = sum_c fL[b,c,y,x] * fR[b,c,y,x-d*stride]  (x >= d*stride and d < W), else 0.
+ * fL,fR: [B][C][H][W] fp32; out: [B][D][H][W] fp32. (The k>1 average pool of :82-85 stays a
+ * stock pooling op in the caller.)                                                           */
+int dsm_corr1d_fwd(const float* fL, const float* fR, float* out,
+                   int B, int C, int H, int W, int D, int stride, void* stream);
+/* backward of the above (autograd of util_conv.py:76-81): gL,gR: [B][C][H][W] (overwritten) */
+int dsm_corr1d_bwd(const float* gout, const float* fL, const float* fR, float* gL, float* gR,
+                   int B, int C, int H, int W, int D, int stride, void* stream);
+
+/* ---- op 2: concatenation cost volume. Replaces the loops at
+ * models/psmnet/stackhourglass.py:124-133, models/gcnet.py:131-135 and :156-164 -------------
+ * fL,fR: [B][C][H][W] fp32. out: 2C channels, D disparities, dtype/layout as given.
+ * With DSM_NDHWC_PADDED the whole buffer including the zero rim is written.                  */
+int dsm_concat_volume_fwd(const float* fL, const float* fR, void* out,
+                          int B, int C, int D, int H, int W,
+                          int mode, int out_dtype, int out_layout, void* stream);
+/* backward: gL,gR [B][C][H][W] fp32 (overwritten) from gout in the given dtype/layout        */
+int dsm_concat_volume_bwd(const void* gout, float* gL, float* gR,
+                          int B, int C, int D, int H, int W,
+                          int mode, int dtype, int layout, void* stream);
+
+/* ---- op 3: 3-D convolution block (k=3, pad=1), tcgen05/TMEM implicit GEMM ----------------
+ * Replaces Conv3d/ConvTranspose3d + BatchNorm3d (+ReLU, +residual add) of
+ * models/psmnet/submodule.py:16-19, stackhourglass.py:26-41,46-60,73-98,135-149,
+ * models/util_conv.py:150-179, models/gcnet.py:38-61.
+ *   x        : bf16 [B][D+2][H+2][W+2][Cin], zero rim (DSM_NDHWC_PADDED)
+ *   w_packed : bf16 [27][CoutP][Cin], tap = (kd*3+kh)*3+kw, CoutP = max(16, Cout) rounded up
+ *              to a multiple of 16 (extra rows zero).  For transposed convs the tap refers to
+ *              the ConvTranspose3d kernel index (weight[ci][co][kd][kh][kw]).
+ *   scale,shift : fp32 [CoutP] per-channel affine applied to the accumulator (folded
+ *              BatchNorm + bias), either may be NULL (1 / 0)
+ *   residual : same dtype/geometry as y, added before ReLU; NULL for none
+ *   y        : y_dtype DSM_BF16 -> bf16 DSM_NDHWC_PADDED [B][Do+2][Ho+2][Wo+2][Cout] (only the
+ *              interior is written: the rim must have been zeroed once by the caller);
+ *              y_dtype DSM_F32 (Cout==1 only) -> fp32 [B][Do][Ho][Wo]
+ *   (D,H,W)  : INPUT extent; output extent is the same (stride 1), floor((n-1)/2)+1
+ *              (stride 2) or 2n (transposed: k3,s2,p1,output_padding 1)
+ *   ws       : unused, may be NULL (kept so the signature does not change when a split-K
+ *              variant appears)                                                              */
+int dsm_conv3d_fwd(const void* x, const void* w_packed, const float* scale, const float* shift,
+                   const void* residual, void* y,
+                   int B, int Cin, int Cout, int D, int H, int W,
+                   int stride, int transposed, int relu, int y_dtype,
+                   void* ws, size_t ws_bytes, void* stream);
+
+/* layout converters at the reference boundary (NCDHW fp32 <-> padded NDHWC bf16)             */
+int dsm_pack_ndhwc(const float* x_ncdhw, void* y_padded_bf16, int B, int C, int D, int H, int W, void* stream);
+int dsm_unpack_ndhwc(const void* x_padded_bf16, float* y_ncdhw, int B, int C, int D, int H, int W, void* stream);
+
+/* ---- op 4: soft-argmin disparity regression ---------------------------------------------
+ * Replaces F.softmax + disparityregression, models/psmnet/submodule.py:56-63 with
+ * stackhourglass.py:155-166, and models/gcnet.py:104-111 (sign=-1).
+ * cost: [B][D][H][W] fp32; disp: [B][H][W] fp32; disp = sum_d d*softmax_d(sign*cost).        */
+int dsm_softargmin_fwd(const float* cost, float* disp, int B, int D, int H, int W, float sign, void* stream);
+int dsm_softargmin_bwd(const float* cost, const float* disp, const float* gdisp, float* gcost,
+                       int B, int D, int H, int W, float sign, void* stream);
+/* plain regression of submodule.py:60-63 on probabilities: disp = sum_d d*prob[b,d,y,x]      */
+int dsm_disparity_regression_fwd(const float* prob, float* disp, int B, int D, int H, int W, void* stream);
+int dsm_disparity_regression_bwd(const float* gdisp, float* gprob, int B, int D, int H, int W, void* stream);
+/* fused head of stackhourglass.py:152-166: trilinear upsample of cost_lr [B][Dl][Hl][Wl] to
+ * (D,H,W), softmax over D, regression.  align_corners=1 is the PyTorch<=0.3 behaviour the
+ * reference was written for, 0 the modern default.                                           */
+int dsm_upsample_softargmin_fwd(const float* cost_lr, float* disp, int B, int Dl, int Hl, int Wl,
+                                int D, int H, int W, int align_corners, void* stream);
+
+/* ---- op 5: imwrap bilinear warp. Replaces imwrap_BCHW, utils/imwrap.py:59-71 -------------
+ * src: [B][C][H0][W0]; disp: [B][H][W]; row: [W], col: [H] (the torch.linspace vectors of
+ * imwrap.py:57-58, computed by the caller exactly as there); out: [B][C][H][W].
+ * out = grid_sample(src + delt, grid, bilinear, zeros, align_corners=True),
+ * grid.x = k*(row[j] - disp*2/(W0-1)), k = -1 if fliplr else 1, grid.y = col[i].             */
+int dsm_warp_fwd(const float* src, const float* disp, const float* row, const float* col,
+                 float delt, int fliplr, float* out,
+                 int B, int C, int H0, int W0, int H, int W, void* stream);
+/* backward: gsrc [B][C][H0][W0] is zeroed by the callee then scatter-added; gdisp [B][H][W]  */
+int dsm_warp_bwd(const float* gout, const float* src, const float* disp, const float* row,
+                 const float* col, float delt, int fliplr, float* gsrc, float* gdisp,
+                 int B, int C, int H0, int W0, int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSMNET_B200_H */
