@@ -1,0 +1,123 @@
+"""3-D convolution blocks on the tcgen05/TMEM implicit-GEMM kernel (``dsm_conv3d_fwd``).
+
+Host-side half of op 3: weight re-packing, eval-mode BatchNorm folding and the fused-layer call.
+A ``FusedConv3d`` is what one ``convbn_3d(...)`` (+ReLU, +residual) of the reference becomes
+(models/psmnet/submodule.py:16-19, stackhourglass.py:26-41,45-60; GC-Net util_conv.py:150-179):
+  y = [relu]( conv(x) * scale + shift [+ residual] )
+with x, y, residual in the padded-NDHWC bf16 layout (``PaddedVolume``) and fp32 accumulation, or
+fp32 NCDHW output for the single-channel classifier convolutions.
+"""
+from __future__ import annotations
+
+from typing import Optional, Union
+
+import torch
+
+from . import _lib
+from .volume_layout import PaddedVolume
+
+BN_EPS = 1e-5
+
+
+def pack_weight(weight: torch.Tensor, transposed: bool) -> torch.Tensor:
+    """[Cout,Cin,3,3,3] (Conv3d) or [Cin,Cout,3,3,3] (ConvTranspose3d) fp32 ->
+    bf16 [27][CoutP][Cin], tap = (kd*3+kh)*3+kw, CoutP = max(16, Cout) (zero rows appended)."""
+    if weight.dim() != 5 or tuple(weight.shape[2:]) != (3, 3, 3):
+        raise _lib.DsmError("only 3x3x3 kernels are supported")
+    w = weight.detach().float()
+    w = w.permute(2, 3, 4, 1, 0) if transposed else w.permute(2, 3, 4, 0, 1)     # [3,3,3,Cout,Cin]
+    cout, cin = w.shape[3], w.shape[4]
+    w = w.reshape(27, cout, cin)
+    coutp = max(16, cout)
+    if coutp != cout:
+        w = torch.cat([w, w.new_zeros(27, coutp - cout, cin)], dim=1)
+    return w.to(torch.bfloat16).contiguous()
+
+
+def fold_affine(cout: int, bn=None, bias: Optional[torch.Tensor] = None, eps: float = BN_EPS):
+    """Eval-mode BatchNorm3d (+ conv bias) -> per-channel (scale, shift), fp32, padded to CoutP.
+    scale = gamma/sqrt(var+eps); shift = beta - mean*scale + bias*scale."""
+    dev = bias.device if bias is not None else (bn.weight.device if bn is not None else None)
+    if bn is None:
+        scale = torch.ones(cout, device=dev)
+        shift = torch.zeros(cout, device=dev)
+    else:
+        scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + (bn.eps if hasattr(bn, "eps") else eps))
+        shift = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+    if bias is not None:
+        shift = shift + bias.detach().float() * scale
+    coutp = max(16, cout)
+    if coutp != cout:
+        scale = torch.cat([scale, scale.new_ones(coutp - cout)])
+        shift = torch.cat([shift, shift.new_zeros(coutp - cout)])
+    return scale.contiguous(), shift.contiguous()
+
+
+def conv_out_dims(D, H, W, stride, transposed):
+    if transposed:
+        return 2 * D, 2 * H, 2 * W
+    if stride == 2:
+        return (D - 1) // 2 + 1, (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    return D, H, W
+
+
+class FusedConv3d:
+    """One fused layer with device-resident packed weights."""
+
+    def __init__(self, weight, bn=None, bias=None, stride=1, transposed=False, relu=False, device=None, variant=0):
+        self.transposed, self.stride, self.relu = bool(transposed), int(stride), bool(relu)
+        if self.transposed:
+            self.cin, self.cout = weight.shape[0], weight.shape[1]
+            self.stride = 2
+        else:
+            self.cout, self.cin = weight.shape[0], weight.shape[1]
+        device = device if device is not None else weight.device
+        self.w = pack_weight(weight, self.transposed).to(device)
+        scale, shift = fold_affine(self.cout, bn, bias)
+        self.identity_affine = bn is None and bias is None
+        self.scale, self.shift = scale.to(device), shift.to(device)
+        self.variant = variant
+
+    def out_dims(self, x: PaddedVolume):
+        return conv_out_dims(x.D, x.H, x.W, self.stride, self.transposed)
+
+    def __call__(self, x: PaddedVolume, out: Union[PaddedVolume, torch.Tensor, None] = None,
+                 residual: Union[PaddedVolume, torch.Tensor, None] = None):
+        """``out``: a PaddedVolume (bf16) or, for Cout==1, an fp32 [B,D,H,W] tensor; allocated when None.
+        Its extent may be a crop of the natural output size (myadd_3d semantics)."""
+        if x.C != self.cin:
+            raise _lib.DsmError("FusedConv3d: expected %d input channels, got %d" % (self.cin, x.C))
+        nD, nH, nW = self.out_dims(x)
+        f32 = self.cout == 1
+        if out is None:
+            if residual is not None:
+                rD, rH, rW = (residual.D, residual.H, residual.W) if isinstance(residual, PaddedVolume) else residual.shape[-3:]
+                nD, nH, nW = min(nD, rD), min(nH, rH), min(nW, rW)
+            out = torch.empty(x.B, nD, nH, nW, device=x.data.device, dtype=torch.float32) if f32 else \
+                PaddedVolume.empty(x.B, self.cout, nD, nH, nW, x.data.device)
+        if f32:
+            oD, oH, oW = out.shape[-3:]
+            optr = out.data_ptr()
+            rptr = 0 if residual is None else residual.data_ptr()
+            if residual is not None and tuple(residual.shape[-3:]) != (oD, oH, oW):
+                raise _lib.DsmError("residual/out extent mismatch")
+        else:
+            oD, oH, oW = out.D, out.H, out.W
+            optr = out.data.data_ptr()
+            rptr = 0
+            if residual is not None:
+                if (residual.D, residual.H, residual.W, residual.C) != (oD, oH, oW, self.cout):
+                    raise _lib.DsmError("residual/out extent mismatch")
+                rptr = residual.data.data_ptr()
+        _lib.check(_lib.lib().dsm_conv3d_fwd_ex(
+            x.data.data_ptr(), self.w.data_ptr(),
+            0 if self.identity_affine else self.scale.data_ptr(), 0 if self.identity_affine else self.shift.data_ptr(),
+            rptr, optr, x.B, self.cin, self.cout, x.D, x.H, x.W, self.stride, int(self.transposed), int(self.relu),
+            _lib.DSM_F32 if f32 else _lib.DSM_BF16, oD, oH, oW, self.variant, _lib.stream_ptr(x.data.device)),
+            "dsm_conv3d_fwd")
+        return out
+
+
+def conv_timeouts() -> int:
+    """Pipeline waits that timed out inside conv kernels since load (0 in a healthy run)."""
+    return _lib.lib().dsm_debug_conv_timeouts()

@@ -41,19 +41,53 @@ struct ConvGeom {
     long long P;             // rows of the flattened padded input
     int tiles_w, tiles_h;    // BOX tiling of the output plane (16 x 8 patches)
     int desc_variant;        // 0: base_offset 0; 1: base_offset from address bits [7,10)
+    int debug_level;         // 0 = normal; 1..3 stop after: setup | TMA | MMA (bring-up bisection)
     int cls_begin[9];
     int a_off[27];           // FLAT/SHIFT: row offset of the tap; BOX: map | ow<<4 | oh<<5 | od<<6
     int w_row[27];           // first row of the tap in the packed weights
 };
 
 __device__ int g_conv_timeouts = 0;
+__device__ int* g_conv_progress = nullptr;   // bring-up only: host-mapped int[4], one slot per warp of CTA 1
 
+__device__ __forceinline__ void mark(int code) {
+#ifdef DSM_CONV_TRACE
+    int* p = g_conv_progress;
+    if (p && blockIdx.x == 1 && blockIdx.y == 0 && (threadIdx.x & 31) == 0) {
+        *reinterpret_cast<volatile int*>(p + (threadIdx.x >> 5)) = code;
+        __threadfence_system();
+    }
+#else
+    (void)code;
+#endif
+}
+
+// ptxas lowers tcgen05.wait::ld to nothing and relies on the register scoreboard of the first
+// consumer.  A thread that never reads its tcgen05.ld result (an invalid rim voxel) would then run
+// on to the CTA barrier / TMEM dealloc / EXIT with the load still in flight — observed on B200 as
+// a hung kernel.  This forces every thread to consume one loaded register (one ISETP, and a
+// shared store that can only fire for a single NaN payload, which changes nothing).
+__device__ __forceinline__ void consume_tmem_load(uint32_t v0, uint32_t scratch_smem) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.eq.u32 q, %0, 0xFFF0DEAD;\n\t"
+        "@q st.shared.u32 [%1], %0;\n\t}"
+        :: "r"(v0), "r"(scratch_smem) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Bounded wait: a broken pipeline must end the kernel (with a counted timeout), never hang the GPU.
 __device__ __forceinline__ bool wait_bar(uint32_t bar, uint32_t parity) {
     if (ptx::mbar_try_wait(bar, parity)) return true;
     if (*reinterpret_cast<volatile int*>(&g_conv_timeouts)) return false;
-    const long long t0 = clock64();
+    const unsigned long long t0 = globaltimer_ns();
     while (!ptx::mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 1500000000LL || *reinterpret_cast<volatile int*>(&g_conv_timeouts)) {
+        if (globaltimer_ns() - t0 > 200000000ULL /*0.2 s*/ || *reinterpret_cast<volatile int*>(&g_conv_timeouts)) {
             atomicAdd(&g_conv_timeouts, 1);
             return false;
         }
@@ -112,6 +146,7 @@ conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
     uint8_t* base_ptr = smem_raw + (base - raw);
     const uint32_t bars = base + C::STAGES * C::STAGE;          // full[S], empty[S], accum, tmem slot
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + C::STAGES * C::STAGE + 8 * (2 * C::STAGES + 1));
+    const uint32_t scratch_smem = bars + 8u * (2 * C::STAGES + 1) + 8u;   // unused word after the TMEM slot
     float* s_scale = reinterpret_cast<float*>(base_ptr + C::STAGES * C::STAGE + 256);
     float* s_shift = s_scale + NP;
     auto full_bar = [&](int s) { return bars + 8u * s; };
@@ -134,11 +169,14 @@ conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    mark(10);
 
     const int tap0 = g.cls_begin[cls];
     const int ntaps = g.cls_begin[cls + 1] - tap0;
     const int ngroups = (MODE == MODE_SHIFT) ? ntaps / 3 : ntaps;
-    const int n_it = ngroups * g.nchunks;
+    int n_it = ngroups * g.nchunks;
+    if (g.debug_level == 1) n_it = 0;
+    if (g.debug_level == 2 && n_it > C::STAGES) n_it = C::STAGES;   // no slot reuse: producer never waits
 
     if (warp == 0) {
       if (lane == 0) {
@@ -173,6 +211,7 @@ conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
             const uint32_t ph = (uint32_t)(it / C::STAGES) & 1u;
             wait_bar(full_bar(s), ph);
             ptx::tc_fence_after();
+            if (g.debug_level == 2) continue;
             const uint32_t sa = base + s * C::STAGE, sb = sa + C::A_BYTES;
 #pragma unroll
             for (int j = 0; j < C::NB; ++j) {
@@ -188,16 +227,25 @@ conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
             }
             ptx::umma_commit(empty_bar(s));      // frees the stage when these MMAs retire
         }
-        ptx::umma_commit(accum_bar);             // accumulator complete
+        if (g.debug_level == 1 || g.debug_level == 2) ptx::mbar_arrive(accum_bar);
+        else ptx::umma_commit(accum_bar);        // accumulator complete
       }
     }
     __syncwarp();
+    mark(20);
 
     // ================= epilogue (all 4 warps, one TMEM lane = one voxel per thread) =======
     wait_bar(accum_bar, 0u);
     __syncwarp();
     ptx::tc_fence_after();
+    mark(30);
 
+    if (g.debug_level >= 1 && g.debug_level <= 3) {   // bring-up: skip the TMEM read-back
+        ptx::tc_fence_before();
+        __syncthreads();
+        if (warp == 1) ptx::tmem_dealloc(tmem, C::TMEM_COLS);
+        return;
+    }
     const int r = tid;                           // row of the tile == TMEM lane
     bool valid = false;
     int ob = 0, od = 0, oh = 0, ow = 0;
@@ -220,13 +268,16 @@ conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
             }
         }
     }
-    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    if (g.debug_level == 6) { uint32_t hw; asm volatile("mov.u32 %0, %%warpid;" : "=r"(hw)); taddr = tmem + (((hw & 3u) * 32u) << 16); }
+    mark(40);
 
     if (g.y_f32) {
         // single output channel (classifier / GC-Net l37): fp32, unpadded [B][Do][Ho][Wo]
         uint32_t v[16];
         ptx::tmem_ld16(taddr, v);
         ptx::tc_wait_ld();
+        consume_tmem_load(v[0], scratch_smem);
         if (valid) {
             const size_t o = (((size_t)ob * g.Do + od) * g.Ho + oh) * g.Wo + ow;
             float a = fmaf(__uint_as_float(v[0]), s_scale[0], s_shift[0]);
@@ -242,9 +293,16 @@ conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
 #pragma unroll
         for (int c0 = 0; c0 < NP; c0 += CH) {
             uint32_t v[CH];
-            if (CH == 32) ptx::tmem_ld32(taddr + c0, v); else ptx::tmem_ld16(taddr + c0, v);
-            ptx::tc_wait_ld();
-            if (valid) {
+            if (g.debug_level == 4) {
+#pragma unroll
+                for (int i = 0; i < CH; ++i) v[i] = 0u;
+            } else {
+                if (CH == 32) ptx::tmem_ld32(taddr + c0, v); else ptx::tmem_ld16(taddr + c0, v);
+                ptx::tc_wait_ld();
+                consume_tmem_load(v[0], scratch_smem);
+            }
+            mark(50 + c0 / CH);
+            if (valid && g.debug_level != 5) {
 #pragma unroll
                 for (int q = 0; q < CH / 8; ++q) {
                     float f[8];
@@ -269,9 +327,12 @@ conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
         }
     }
 
+    mark(60);
     ptx::tc_fence_before();
     __syncthreads();
+    mark(70);
     if (warp == 1) ptx::tmem_dealloc(tmem, C::TMEM_COLS);
+    mark(80);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -355,7 +416,7 @@ int conv3d_dispatch(const void* x, const void* w, const float* scale, const floa
     memset(&g, 0, sizeof(g));
     g.B = B; g.Di = D; g.Hi = H; g.Wi = W; g.Do = Do; g.Ho = Ho; g.Wo = Wo;
     g.Cout = Cout; g.transposed = transposed; g.relu = relu; g.y_f32 = (y_dtype == DSM_F32);
-    g.nchunks = Cin / KC; g.P = P; g.desc_variant = variant & 1;
+    g.nchunks = Cin / KC; g.P = P; g.desc_variant = variant & 1; g.debug_level = (variant >> 8) & 7;
     const int row_bytes = KC * 2;
     const int mode = (!transposed && stride == 2) ? MODE_BOX : ((variant & 2) && !transposed ? MODE_SHIFT : MODE_FLAT);
 
@@ -449,6 +510,11 @@ extern "C" int dsm_conv3d_fwd_ex(const void* x, const void* w_packed, const floa
                                  int Do, int Ho, int Wo, int variant, void* stream) {
     return conv3d_dispatch(x, w_packed, scale, shift, residual, y, B, Cin, Cout, D, H, W, stride, transposed, relu,
                            y_dtype, Do, Ho, Wo, variant, stream);
+}
+
+// bring-up aid: `host_mapped` = device-visible int[4] the kernel writes progress codes into (NULL = off)
+extern "C" int dsm_debug_conv_set_progress(int* host_mapped) {
+    return (int)cudaMemcpyToSymbol(g_conv_progress, &host_mapped, sizeof(int*));
 }
 
 // number of pipeline waits that timed out since the library was loaded (0 in a healthy run)

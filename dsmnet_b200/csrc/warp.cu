@@ -108,7 +108,34 @@ warp_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ src, c
     gdisp[((size_t)b * H + i) * W + j] = -k * (2.0f / wm1) * (gix * (wm1 * 0.5f));
 }
 
+__global__ void __launch_bounds__(128)
+warp_indices_kernel(const float* __restrict__ disp, const float* __restrict__ row, const float* __restrict__ col,
+                    float k, int* __restrict__ x0, int* __restrict__ y0, int H0, int W0, int H, int W) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y, b = blockIdx.z;
+    if (j >= W) return;
+    const size_t o = ((size_t)b * H + i) * W + j;
+    const float wm1 = (float)(W0 - 1), hm1 = (float)(H0 - 1);
+    const float q  = __fdiv_rn(__fmul_rn(__ldg(disp + o), 2.0f), wm1);
+    const float gx = __fmul_rn(k, __fsub_rn(__ldg(row + j), q));
+    const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.0f), 2.0f), wm1);
+    const float iy = __fmul_rn(__fdiv_rn(__fadd_rn(__ldg(col + i), 1.0f), 2.0f), hm1);
+    x0[o] = (int)floorf(ix); y0[o] = (int)floorf(iy);
+}
+
 }  // namespace
+
+// test hook for the "bit-exact warp indexing" requirement: the north-west source pixel (x0,y0)
+// [B][H][W] int32 that dsm_warp_fwd/bwd use for every output pixel (same arithmetic as make_tap).
+extern "C" int dsm_warp_indices(const float* disp, const float* row, const float* col, int fliplr,
+                                int* x0, int* y0, int B, int H0, int W0, int H, int W, void* stream) {
+    if (!disp || !row || !col || !x0 || !y0 || B <= 0) return DSM_EINVAL;
+    if (H0 < 2 || W0 < 2 || H < 2 || W < 2) return DSM_EINVAL;
+    if (H > 65535 || B > 65535) return DSM_EUNSUPPORTED;
+    warp_indices_kernel<<<dim3(dsm_ceil_div(W, 128), H, B), 128, 0, (cudaStream_t)stream>>>(
+        disp, row, col, fliplr ? -1.0f : 1.0f, x0, y0, H0, W0, H, W);
+    return dsm_launch_status();
+}
 
 extern "C" int dsm_warp_fwd(const float* src, const float* disp, const float* row, const float* col,
                             float delt, int fliplr, float* out,

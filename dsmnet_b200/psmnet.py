@@ -1,0 +1,270 @@
+"""PSMNet (stacked hourglass) with the cost-volume hot path on the sm_100a kernels.
+
+Mirrors the reference's model surface (models/psmnet/stackhourglass.py, submodule.py): same
+class names, constructor arguments and parameter / buffer names (``dres0.0.0.weight``,
+``dres2.conv5.1.running_var`` ...) so a reference ``state_dict`` loads unchanged, and
+``PSMNet(maxdisp)(left, right, mode)`` returns ``([0, 0, 0], [pred3, pred2, pred1])`` with
+``pred*`` of shape (B, H, W) exactly like stackhourglass.py:168.
+
+The 2-D feature extractor is a caller of the hot path and stays stock PyTorch (cuDNN); the
+path from the two feature maps on — concat volume (stackhourglass.py:124-133), dres0..classif3
+(:135-149) and the three upsample+softmax+regression heads (:152-166) — runs as:
+  concat_volume (padded NDHWC bf16)  ->  25 fused tcgen05 conv blocks  ->  3 fp32 Cout=1 convs
+  ->  3 fused upsample+soft-argmin kernels.
+Inference (eval-mode BatchNorm folded into the conv epilogue).  Training the 3-D stack needs the
+conv backward kernels and is not part of this round: calling it in train mode raises.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from .conv3d import FusedConv3d
+from .cost_volume import concat_volume
+from .softargmin import upsample_softargmin
+from .volume_layout import PaddedVolume
+
+
+def convbn_3d(in_planes, out_planes, kernel_size, stride, pad):
+    """Parameter container with the reference's layout (submodule.py:16-19)."""
+    return nn.Sequential(nn.Conv3d(in_planes, out_planes, kernel_size=kernel_size, padding=pad, stride=stride, bias=False),
+                         nn.BatchNorm3d(out_planes))
+
+
+class hourglass(nn.Module):
+    """Parameters as in stackhourglass.py:22-41; the forward is driven by PSMNetHotPath."""
+
+    def __init__(self, inplanes):
+        super().__init__()
+        self.conv1 = nn.Sequential(convbn_3d(inplanes, inplanes * 2, 3, 2, 1), nn.ReLU(inplace=True))
+        self.conv2 = convbn_3d(inplanes * 2, inplanes * 2, 3, 1, 1)
+        self.conv3 = nn.Sequential(convbn_3d(inplanes * 2, inplanes * 2, 3, 2, 1), nn.ReLU(inplace=True))
+        self.conv4 = nn.Sequential(convbn_3d(inplanes * 2, inplanes * 2, 3, 1, 1), nn.ReLU(inplace=True))
+        self.conv5 = nn.Sequential(nn.ConvTranspose3d(inplanes * 2, inplanes * 2, kernel_size=3, padding=1,
+                                                      output_padding=1, stride=2, bias=False),
+                                   nn.BatchNorm3d(inplanes * 2))
+        self.conv6 = nn.Sequential(nn.ConvTranspose3d(inplanes * 2, inplanes, kernel_size=3, padding=1,
+                                                      output_padding=1, stride=2, bias=False),
+                                   nn.BatchNorm3d(inplanes))
+
+
+class _Plan:
+    """Packed weights + folded BatchNorm of every 3-D layer, built once per parameter version."""
+
+    def __init__(self, m: "PSMNetHotPath", device, variant=0):
+        def cb(seq, stride=1, transposed=False, relu=False):
+            return FusedConv3d(seq[0].weight, seq[1], None, stride, transposed, relu, device, variant)
+
+        self.dres0_0 = cb(m.dres0[0], relu=True)
+        self.dres0_2 = cb(m.dres0[2], relu=True)
+        self.dres1_0 = cb(m.dres1[0], relu=True)
+        self.dres1_2 = cb(m.dres1[2])
+        self.hg = []
+        for h in (m.dres2, m.dres3, m.dres4):
+            self.hg.append(dict(
+                conv1=cb(h.conv1[0], stride=2, relu=True), conv2=cb(h.conv2, relu=True),
+                conv3=cb(h.conv3[0], stride=2, relu=True), conv4=cb(h.conv4[0], relu=True),
+                conv5=cb(h.conv5, transposed=True, relu=True), conv6=cb(h.conv6, transposed=True)))
+        self.cls = []
+        for c in (m.classif1, m.classif2, m.classif3):
+            self.cls.append((cb(c[0], relu=True), FusedConv3d(c[2].weight, None, None, 1, False, False, device, variant)))
+
+
+class PSMNetHotPath(nn.Module):
+    """The north-star path as one module: (fL, fR) feature maps -> [pred3, pred2, pred1].
+
+    Holds the 3-D parameters under the reference's names.  ``forward(fL, fR, out_hw)``."""
+
+    def __init__(self, maxdisp=192, align_corners=True, variant=0):
+        super().__init__()
+        self.maxdisp = maxdisp
+        self.align_corners = align_corners        # PyTorch<=0.3 F.upsample semantics
+        self.variant = variant
+        self.dres0 = nn.Sequential(convbn_3d(64, 32, 3, 1, 1), nn.ReLU(inplace=True),
+                                   convbn_3d(32, 32, 3, 1, 1), nn.ReLU(inplace=True))
+        self.dres1 = nn.Sequential(convbn_3d(32, 32, 3, 1, 1), nn.ReLU(inplace=True),
+                                   convbn_3d(32, 32, 3, 1, 1))
+        self.dres2 = hourglass(32)
+        self.dres3 = hourglass(32)
+        self.dres4 = hourglass(32)
+        self.classif1 = nn.Sequential(convbn_3d(32, 32, 3, 1, 1), nn.ReLU(inplace=True),
+                                      nn.Conv3d(32, 1, kernel_size=3, padding=1, stride=1, bias=False))
+        self.classif2 = nn.Sequential(convbn_3d(32, 32, 3, 1, 1), nn.ReLU(inplace=True),
+                                      nn.Conv3d(32, 1, kernel_size=3, padding=1, stride=1, bias=False))
+        self.classif3 = nn.Sequential(convbn_3d(32, 32, 3, 1, 1), nn.ReLU(inplace=True),
+                                      nn.Conv3d(32, 1, kernel_size=3, padding=1, stride=1, bias=False))
+        for m in self.modules():                  # init as stackhourglass.py:100-114
+            if isinstance(m, nn.Conv3d):
+                n = m.kernel_size[0] * m.kernel_size[1] * m.kernel_size[2] * m.out_channels
+                m.weight.data.normal_(0, math.sqrt(2. / n))
+            elif isinstance(m, nn.BatchNorm3d):
+                m.weight.data.fill_(1); m.bias.data.zero_()
+        self._plan: Optional[_Plan] = None
+        self._plan_key = None
+        self._ws: Dict[Tuple, dict] = {}
+
+    # -- plan / workspace caches ------------------------------------------------------------
+    def _get_plan(self, device):
+        key = (str(device),) + tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+        if self._plan is None or key != self._plan_key:
+            self._plan = _Plan(self, device, self.variant)
+            self._plan_key = key
+        return self._plan
+
+    def _workspace(self, B, D, H, W, device):
+        """Activation buffers for one problem size (zero rims written once, then reused)."""
+        key = (B, D, H, W, str(device))
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        def half(n): return (n - 1) // 2 + 1
+        D2, H2, W2 = half(D), half(H), half(W)
+        D4, H4, W4 = half(D2), half(H2), half(W2)
+        P = PaddedVolume.empty
+        ws = dict(
+            vol=P(B, 64, D, H, W, device, zero_rim=False),
+            a=P(B, 32, D, H, W, device), c0=P(B, 32, D, H, W, device), t=P(B, 32, D, H, W, device),
+            cost0=P(B, 32, D, H, W, device),
+            out=[P(B, 32, D, H, W, device) for _ in range(3)],
+            h1=P(B, 64, D2, H2, W2, device),
+            pre=[P(B, 64, D2, H2, W2, device) for _ in range(3)],
+            post=[P(B, 64, D2, H2, W2, device) for _ in range(3)],
+            h3=P(B, 64, D4, H4, W4, device), h4=P(B, 64, D4, H4, W4, device),
+            cost=[torch.empty(B, D, H, W, device=device, dtype=torch.float32) for _ in range(3)],
+        )
+        self._ws[key] = ws
+        return ws
+
+    # -- the path -----------------------------------------------------------------------------
+    def aggregate(self, fL, fR):
+        """concat volume + dres0..classif3 -> (cost1, cost2, cost3), fp32 [B, D/4, H/4, W/4] each."""
+        if self.training:
+            raise _lib.DsmError("PSMNetHotPath: training-mode 3-D stack (conv backward, batch-stat BN) is not "
+                                "implemented on the sm_100a path yet; call .eval() — there is no fallback")
+        B, C, H, W = fL.shape
+        D = self.maxdisp // 4
+        plan = self._get_plan(fL.device)
+        ws = self._workspace(B, D, H, W, fL.device)
+        vol = concat_volume(fL, fR, D, "psm", padded_bf16=True, out=ws["vol"])
+        plan.dres0_0(vol, ws["a"])
+        plan.dres0_2(ws["a"], ws["c0"])
+        plan.dres1_0(ws["c0"], ws["t"])
+        cost0 = plan.dres1_2(ws["t"], ws["cost0"], residual=ws["c0"])            # :136
+        x = cost0
+        pre_prev = post_prev = None
+        pre1 = None
+        for i, hg in enumerate(plan.hg):
+            presqu = None if i == 0 else pre1                                   # :141,144 (pre1 both times)
+            postsqu = post_prev
+            hg["conv1"](x, ws["h1"])
+            pre = hg["conv2"](ws["h1"], ws["pre"][i], residual=postsqu)         # :46-50
+            hg["conv3"](pre, ws["h3"])
+            hg["conv4"](ws["h3"], ws["h4"])
+            post = hg["conv5"](ws["h4"], ws["post"][i], residual=presqu if presqu is not None else pre)   # :55-58
+            x = hg["conv6"](post, ws["out"][i], residual=cost0)                 # :60 then "+ cost0" (:139,142,145)
+            if i == 0:
+                pre1 = pre
+            post_prev = post
+        costs = []
+        prev = None
+        for i, (c0, c2) in enumerate(plan.cls):
+            c0(ws["out"][i], ws["t"])
+            prev = c2(ws["t"], ws["cost"][i], residual=prev)                    # :147-149 cumulative adds
+            costs.append(prev)
+        return costs
+
+    def forward(self, fL, fR, out_hw):
+        c1, c2, c3 = self.aggregate(fL, fR)
+        size = (self.maxdisp, out_hw[0], out_hw[1])
+        return [upsample_softargmin(c, size, self.align_corners) for c in (c3, c2, c1)]
+
+
+# --------------------------------------------------------------------------------------------
+# 2-D feature extractor (caller of the hot path; stock PyTorch).  Same parameter names as the
+# reference's feature_extraction (submodule.py:65-140) so that checkpoints load.
+# --------------------------------------------------------------------------------------------
+
+def convbn(in_planes, out_planes, kernel_size, stride, pad, dilation):
+    return nn.Sequential(nn.Conv2d(in_planes, out_planes, kernel_size=kernel_size, stride=stride,
+                                   padding=dilation if dilation > 1 else pad, dilation=dilation, bias=False),
+                         nn.BatchNorm2d(out_planes))
+
+
+class BasicBlock(nn.Module):
+    expansion = 1
+
+    def __init__(self, inplanes, planes, stride, downsample, pad, dilation):
+        super().__init__()
+        self.conv1 = nn.Sequential(convbn(inplanes, planes, 3, stride, pad, dilation), nn.ReLU(inplace=True))
+        self.conv2 = convbn(planes, planes, 3, 1, pad, dilation)
+        self.downsample = downsample
+
+    def forward(self, x):
+        out = self.conv2(self.conv1(x))
+        return out + (x if self.downsample is None else self.downsample(x))
+
+
+class feature_extraction(nn.Module):
+    def __init__(self, align_corners=True):
+        super().__init__()
+        self.align_corners = align_corners
+        self.inplanes = 32
+        self.firstconv = nn.Sequential(convbn(3, 32, 3, 2, 1, 1), nn.ReLU(inplace=True),
+                                       convbn(32, 32, 3, 1, 1, 1), nn.ReLU(inplace=True),
+                                       convbn(32, 32, 3, 1, 1, 1), nn.ReLU(inplace=True))
+        self.layer1 = self._make_layer(32, 3, 1, 1, 1)
+        self.layer2 = self._make_layer(64, 16, 2, 1, 1)
+        self.layer3 = self._make_layer(128, 3, 1, 1, 1)
+        self.layer4 = self._make_layer(128, 3, 1, 1, 2)
+        for i, k in enumerate((64, 32, 16, 8), start=1):
+            setattr(self, "branch%d" % i, nn.Sequential(nn.AvgPool2d((k, k), stride=(k, k)),
+                                                        convbn(128, 32, 1, 1, 0, 1), nn.ReLU(inplace=True)))
+        self.lastconv = nn.Sequential(convbn(320, 128, 3, 1, 1, 1), nn.ReLU(inplace=True),
+                                      nn.Conv2d(128, 32, kernel_size=1, padding=0, stride=1, bias=False))
+
+    def _make_layer(self, planes, blocks, stride, pad, dilation):
+        downsample = None
+        if stride != 1 or self.inplanes != planes:
+            downsample = nn.Sequential(nn.Conv2d(self.inplanes, planes, kernel_size=1, stride=stride, bias=False),
+                                       nn.BatchNorm2d(planes))
+        layers = [BasicBlock(self.inplanes, planes, stride, downsample, pad, dilation)]
+        self.inplanes = planes
+        layers += [BasicBlock(planes, planes, 1, None, pad, dilation) for _ in range(1, blocks)]
+        return nn.Sequential(*layers)
+
+    def forward(self, x):
+        out = self.layer1(self.firstconv(x))
+        raw = self.layer2(out)
+        skip = self.layer4(self.layer3(raw))
+        hw = (skip.size(2), skip.size(3))
+        br = [F.interpolate(getattr(self, "branch%d" % i)(skip), hw, mode="bilinear", align_corners=self.align_corners)
+              for i in (1, 2, 3, 4)]
+        feat = torch.cat((raw, skip, br[3], br[2], br[1], br[0]), 1)
+        return self.lastconv(feat)
+
+
+class PSMNet(PSMNetHotPath):
+    """Drop-in for the reference's PSMNet (stackhourglass.py:64-168)."""
+
+    def __init__(self, maxdisp=192, align_corners=True):
+        super().__init__(maxdisp, align_corners)
+        self.name = "psmnet"
+        self.count_levels = 1
+        self.feature_extraction = feature_extraction(align_corners)
+        for m in self.feature_extraction.modules():
+            if isinstance(m, nn.Conv2d):
+                n = m.kernel_size[0] * m.kernel_size[1] * m.out_channels
+                m.weight.data.normal_(0, math.sqrt(2. / n))
+            elif isinstance(m, nn.BatchNorm2d):
+                m.weight.data.fill_(1); m.bias.data.zero_()
+
+    def forward(self, left, right, mode="train"):
+        refimg_fea = self.feature_extraction(left)
+        targetimg_fea = self.feature_extraction(right)
+        preds = PSMNetHotPath.forward(self, refimg_fea.float(), targetimg_fea.float(), (left.size(2), left.size(3)))
+        return [0, 0, 0], preds

@@ -127,6 +127,27 @@ int dsm_warp_bwd(const float* gout, const float* src, const float* disp, const f
                  const float* col, float delt, int fliplr, float* gsrc, float* gdisp,
                  int B, int C, int H0, int W0, int H, int W, void* stream);
 
+/* test hook: the integer north-west source pixel (x0,y0), int32 [B][H][W], that the warp kernels
+ * derive for each output pixel — lets a test assert bit-exact sampling indices against the oracle. */
+int dsm_warp_indices(const float* disp, const float* row, const float* col, int fliplr,
+                     int* x0, int* y0, int B, int H0, int W0, int H, int W, void* stream);
+
+/* ---- extended / diagnostic entry points ---------------------------------------------------
+ * dsm_conv3d_fwd_ex: as dsm_conv3d_fwd, with (Do,Ho,Wo) = extent of the y/residual buffers when
+ * that is a crop of the natural output size (the reference's crop-to-min add, myadd_3d /
+ * myAdd3d, stackhourglass.py:10-20, util_fun.py:41-51; pass 0,0,0 for the natural size) and
+ * `variant` (bit0: descriptor base-offset mode, bit1: row-shifted-descriptor kernel for stride-1
+ * convolutions, bits 8-10: bring-up level; 0 = default path).                                  */
+int dsm_conv3d_fwd_ex(const void* x, const void* w_packed, const float* scale, const float* shift,
+                      const void* residual, void* y,
+                      int B, int Cin, int Cout, int D, int H, int W,
+                      int stride, int transposed, int relu, int y_dtype,
+                      int Do, int Ho, int Wo, int variant, void* stream);
+/* number of bounded pipeline waits that expired inside conv kernels since load (0 when healthy) */
+int dsm_debug_conv_timeouts(void);
+/* bring-up aid (library built with -DDSM_CONV_TRACE): host-mapped int[4] progress slots */
+int dsm_debug_conv_set_progress(int* host_mapped);
+
 #ifdef __cplusplus
 }
 #endif

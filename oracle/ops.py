@@ -1,0 +1,402 @@
+"""CPU oracle for the stereo cost-volume hot path — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+A restatement, in closed form on CPU (torch CPU fp32/fp64 tensors + numpy), of what the reference
+sunshinnnn/DSMnet computes on the path this repo accelerates.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl reference`` legs may import
+this package; nothing under ``dsmnet_b200/`` does.
+
+Parity status: the reference ships NO golden vectors or tests for this path, so
+the oracle is pinned against outputs of the reference's own code, executed in the build
+container through ``oracle/refshim.py`` and frozen as fixtures by ``tests/golden/make_golden.py``
+(``tests/test_oracle_golden.py`` re-checks every fixture on CPU; when ``/root/reference`` is
+present ``tests/test_oracle_vs_reference.py`` re-runs the reference live).
+
+The arithmetic of conv3d / conv_transpose3d / batch-norm / grid_sample / trilinear upsample /
+softmax lives in a third-party dependency that is not vendored in the reference: PyTorch
+(pinned by the reference only as "PyTorch 0.3.0+", README.md:25-26; this container has
+torch 2.11.0+cu128).  For those the oracle calls the same torch CPU functional with the
+PyTorch<=0.3 semantics pinned explicitly (align_corners=True), which is the reference's own call.
+
+Every function cites the reference lines it restates (paths relative to the reference root).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# ------------------------------------------------------------------------------------------
+# op 1 — Corr1d   (models/util_conv.py:56-86)
+# ------------------------------------------------------------------------------------------
+
+def corr1d(fL: torch.Tensor, fR: torch.Tensor, D: int, stride: int = 1, kernel_size: int = 1) -> torch.Tensor:
+    """out[b,d,y,x] = sum_c fL[b,c,y,x]*fR[b,c,y,x-d*stride] for x>=d*stride, d<W; else 0.
+
+    Restates Corr1d.forward (util_conv.py:71-86) with simfun_default (:68-69): no 1/C
+    normalisation; the loop stops at d >= W (:79); kernel_size>1 appends a k x k stride-1
+    zero-padded average pool with count_include_pad (:82-85)."""
+    B, C, H, W = fL.shape
+    out = fL.new_zeros(B, D, H, W)
+    for d in range(min(D, W)):
+        s = d * stride
+        if s >= W:
+            continue
+        out[:, d, :, s:] = (fL[:, :, :, s:] * fR[:, :, :, : W - s]).sum(dim=1)
+    if kernel_size > 1:
+        assert kernel_size % 2 == 1
+        out = F.avg_pool2d(out, kernel_size, stride=1, padding=kernel_size // 2)
+    return out
+
+
+def corr1d_grads(g: torch.Tensor, fL: torch.Tensor, fR: torch.Tensor, stride: int = 1) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Closed-form backward of corr1d without pooling:
+    gL[b,c,y,x] = sum_d g[b,d,y,x]*fR[b,c,y,x-d*s];  gR[b,c,y,x'] = sum_d g[b,d,y,x'+d*s]*fL[b,c,y,x'+d*s]."""
+    B, C, H, W = fL.shape
+    D = g.shape[1]
+    gL = torch.zeros_like(fL)
+    gR = torch.zeros_like(fR)
+    for d in range(min(D, W)):
+        s = d * stride
+        if s >= W:
+            continue
+        gd = g[:, d : d + 1, :, s:]
+        gL[:, :, :, s:] += gd * fR[:, :, :, : W - s]
+        gR[:, :, :, : W - s] += gd * fL[:, :, :, s:]
+    return gL, gR
+
+
+# ------------------------------------------------------------------------------------------
+# op 2 — concatenation cost volume
+# ------------------------------------------------------------------------------------------
+
+def concat_volume(fL: torch.Tensor, fR: torch.Tensor, D: int, mode: str = "psm") -> torch.Tensor:
+    """NCDHW volume [B,2C,D,H,W].
+
+    mode "psm"      : models/psmnet/stackhourglass.py:124-133 — both halves zero for x<d.
+    mode "gc"       : models/gcnet.py:131-135 — left half copied for every x, right half shifted.
+    mode "gc_right" : models/gcnet.py:157,159,163-164 (xR) — fR copied, fL shifted the other way."""
+    B, C, H, W = fL.shape
+    vol = fL.new_zeros(B, 2 * C, D, H, W)
+    for d in range(D):
+        if mode == "psm":
+            if d < W:
+                vol[:, :C, d, :, d:] = fL[:, :, :, d:]
+                vol[:, C:, d, :, d:] = fR[:, :, :, : W - d]
+        elif mode == "gc":
+            vol[:, :C, d] = fL
+            if d < W:
+                vol[:, C:, d, :, d:] = fR[:, :, :, : W - d]
+        elif mode == "gc_right":
+            vol[:, :C, d] = fR
+            if d < W:
+                vol[:, C:, d, :, : W - d] = fL[:, :, :, d:]
+        else:
+            raise ValueError(mode)
+    return vol
+
+
+def concat_volume_grads(g: torch.Tensor, D: int, mode: str = "psm") -> Tuple[torch.Tensor, torch.Tensor]:
+    """Closed-form backward: returns (gL, gR), each [B,C,H,W]."""
+    B, C2, D_, H, W = g.shape
+    C = C2 // 2
+    gA = g.new_zeros(B, C, H, W)   # gradient of the tensor copied into the first half
+    gB = g.new_zeros(B, C, H, W)   # gradient of the shifted tensor
+    for d in range(D):
+        if mode == "psm":
+            if d < W:
+                gA[:, :, :, d:] += g[:, :C, d, :, d:]
+                gB[:, :, :, : W - d] += g[:, C:, d, :, d:]
+        elif mode == "gc":
+            gA += g[:, :C, d]
+            if d < W:
+                gB[:, :, :, : W - d] += g[:, C:, d, :, d:]
+        elif mode == "gc_right":
+            gA += g[:, :C, d]
+            if d < W:
+                gB[:, :, :, d:] += g[:, C:, d, :, : W - d]
+        else:
+            raise ValueError(mode)
+    if mode == "gc_right":
+        return gB, gA          # first half was fR, shifted one was fL
+    return gA, gB
+
+
+# ------------------------------------------------------------------------------------------
+# op 3 — 3-D convolution blocks
+# ------------------------------------------------------------------------------------------
+
+def fold_bn(weight_shape_cout: int, bn: Optional[Dict[str, torch.Tensor]], bias: Optional[torch.Tensor],
+            eps: float = 1e-5) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Eval-mode BatchNorm3d (+conv bias) as a per-channel affine:
+    scale = gamma/sqrt(var+eps), shift = beta - mean*scale (+ bias*scale)."""
+    if bn is None:
+        scale = torch.ones(weight_shape_cout)
+        shift = torch.zeros(weight_shape_cout)
+    else:
+        scale = bn["weight"] / torch.sqrt(bn["running_var"] + eps)
+        shift = bn["bias"] - bn["running_mean"] * scale
+    if bias is not None:
+        shift = shift + bias * scale
+    return scale.float(), shift.float()
+
+
+def crop_add(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """myadd_3d / myAdd3d crop-to-min add (stackhourglass.py:10-20, util_fun.py:41-51)."""
+    d = min(a.shape[2], b.shape[2]); h = min(a.shape[3], b.shape[3]); w = min(a.shape[4], b.shape[4])
+    return a[:, :, :d, :h, :w] + b[:, :, :d, :h, :w]
+
+
+def conv3d_block(x: torch.Tensor, weight: torch.Tensor, scale: Optional[torch.Tensor] = None,
+                 shift: Optional[torch.Tensor] = None, stride: int = 1, transposed: bool = False,
+                 residual: Optional[torch.Tensor] = None, relu: bool = False,
+                 operand_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """Conv3d(k3,p1,stride) or ConvTranspose3d(k3,s2,p1,output_padding=1), then the folded
+    BatchNorm affine, then optional crop-add of `residual`, then optional ReLU.
+
+    Restates convbn_3d (submodule.py:16-19), the hourglass wiring (stackhourglass.py:26-41,45-60)
+    and conv3d_bn/deconv3d_bn (util_conv.py:150-179).  `operand_dtype=torch.bfloat16` rounds the
+    conv operands (not the accumulation) the way the tensor-core kernel does."""
+    if operand_dtype is not None:
+        x = x.to(operand_dtype).float()
+        weight = weight.to(operand_dtype).float()
+    if transposed:
+        y = F.conv_transpose3d(x, weight, None, stride=2, padding=1, output_padding=1)
+    else:
+        y = F.conv3d(x, weight, None, stride=stride, padding=1)
+    if scale is not None:
+        y = y * scale.view(1, -1, 1, 1, 1)
+    if shift is not None:
+        y = y + shift.view(1, -1, 1, 1, 1)
+    if residual is not None:
+        y = crop_add(y, residual)
+    if relu:
+        y = F.relu(y)
+    return y
+
+
+# ------------------------------------------------------------------------------------------
+# op 4 — soft-argmin
+# ------------------------------------------------------------------------------------------
+
+def disparity_regression(prob: torch.Tensor) -> torch.Tensor:
+    """disparityregression.forward (submodule.py:60-63): sum_d d*prob[b,d,y,x] -> [B,H,W]."""
+    disp = torch.arange(0, prob.shape[1], dtype=prob.dtype)
+    return prob.permute(0, 2, 3, 1).matmul(disp)
+
+
+def softargmin(cost: torch.Tensor, sign: float = 1.0) -> torch.Tensor:
+    """softmax over dim 1 of sign*cost, then regression.  PSMNet: stackhourglass.py:155-157
+    (F.softmax without dim on a 4-D tensor = dim 1), sign=+1; GC-Net: gcnet.py:104-109
+    (Softmax2d of MINUS the cost), sign=-1.  Returns [B,H,W]."""
+    return disparity_regression(F.softmax(sign * cost, dim=1))
+
+
+def upsample_softargmin(cost_lr: torch.Tensor, size: Sequence[int], align_corners: bool = True) -> torch.Tensor:
+    """PSMNet head (stackhourglass.py:152-166): F.upsample(cost[B,1,Dl,Hl,Wl], [D,H,W], 'trilinear')
+    -> squeeze(1) -> softmax(dim 1) -> regression.  `align_corners=True` is what F.upsample did in
+    the PyTorch the reference targets (<= 0.3.1)."""
+    up = F.interpolate(cost_lr.unsqueeze(1), size=list(size), mode="trilinear", align_corners=align_corners)
+    return softargmin(up.squeeze(1), 1.0)
+
+
+# ------------------------------------------------------------------------------------------
+# op 5 — imwrap
+# ------------------------------------------------------------------------------------------
+
+def imwrap_rowcol(h0: int, w0: int, h: int, w: int, LeftTop=(0, 0), scale_factor=1) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The two torch.linspace vectors of imwrap.py:50-58, computed exactly as there (python
+    floats -> torch.linspace fp32)."""
+    x, y = LeftTop
+    x = x * 2.0 / (w0 - 1) - 1
+    y = y * 2.0 / (h0 - 1) - 1
+    x1 = x + (w - 1) * scale_factor * 2.0 / (w0 - 1)
+    y1 = y + (h - 1) * scale_factor * 2.0 / (h0 - 1)
+    return torch.linspace(x, x1, w), torch.linspace(y, y1, h)
+
+
+def imwrap(im_src: torch.Tensor, disp: torch.Tensor, fliplr: bool = False, LeftTop=(0, 0), scale_factor=1,
+           delt: float = 0.0) -> torch.Tensor:
+    """imwrap_BCHW (utils/imwrap.py:37-72) with `delt` explicit instead of drawn at :70.
+    grid_sample is pinned to bilinear / zeros / align_corners=True (the behaviour the grid of
+    :51-54 is built for)."""
+    bn, _, h0, w0 = im_src.shape
+    bn, c, h, w = disp.shape
+    assert c == 1 and min(h, w, h0, w0) > 1
+    row, col = imwrap_rowcol(h0, w0, h, w, LeftTop, scale_factor)
+    grid = torch.zeros(bn, h, w, 2)
+    grid[..., 0] = row.view(1, 1, w)
+    grid[..., 1] = col.view(1, h, 1)
+    grid = grid.type_as(im_src)
+    k = -1.0 if fliplr else 1
+    gx = k * (grid[:, :, :, 0] - disp.squeeze(1) * 2.0 / (w0 - 1))
+    grid = torch.stack([gx, grid[:, :, :, 1]], dim=3)
+    return F.grid_sample(im_src + delt, grid, mode="bilinear", padding_mode="zeros", align_corners=True)
+
+
+def imwrap_closed_form(im_src: np.ndarray, disp: np.ndarray, row: np.ndarray, col: np.ndarray, fliplr: bool,
+                       delt: float) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Independent numpy restatement of the same op in fp32; returns
+    (out, x0, y0) where x0/y0 are the integer north-west source indices (the 'warp indexing'
+    that must match bit-exactly)."""
+    f = np.float32
+    B, C, H0, W0 = im_src.shape
+    _, _, H, W = disp.shape
+    k = f(-1.0) if fliplr else f(1.0)
+    q = (disp[:, 0].astype(f) * f(2.0)) / f(W0 - 1)
+    gx = k * (row.astype(f)[None, None, :] - q)
+    gy = np.broadcast_to(col.astype(f)[None, :, None], gx.shape)
+    ix = ((gx + f(1)) / f(2)) * f(W0 - 1)
+    iy = ((gy + f(1)) / f(2)) * f(H0 - 1)
+    x0 = np.floor(ix); y0 = np.floor(iy)
+    tx = (ix - x0).astype(f); ty = (iy - y0).astype(f)
+    ex = f(1) - tx; ey = f(1) - ty
+    x0 = x0.astype(np.int64); y0 = y0.astype(np.int64)
+    out = np.zeros((B, C, H, W), dtype=f)
+    src = im_src.astype(f) + f(delt)
+    bidx = np.arange(B)[:, None, None]
+    for (dx, dy, wgt) in ((0, 0, ex * ey), (1, 0, tx * ey), (0, 1, ex * ty), (1, 1, tx * ty)):
+        xx = x0 + dx; yy = y0 + dy
+        ok = (xx >= 0) & (xx < W0) & (yy >= 0) & (yy < H0)
+        xc = np.clip(xx, 0, W0 - 1); yc = np.clip(yy, 0, H0 - 1)
+        v = src[bidx, :, yc, xc]                      # [B,H,W,C]
+        out += np.moveaxis(v * (wgt * ok)[..., None], 3, 1).astype(f)
+    return out, x0, y0
+
+
+# ------------------------------------------------------------------------------------------
+# the north-star path: PSMNet cost volume -> stacked hourglass -> three soft-argmin heads
+# ------------------------------------------------------------------------------------------
+
+def _bn(params: Dict[str, torch.Tensor], prefix: str) -> Dict[str, torch.Tensor]:
+    return {k: params[prefix + "." + k] for k in ("weight", "bias", "running_mean", "running_var")}
+
+
+def _convbn(params, prefix, x, stride=1, transposed=False, residual=None, relu=False, operand_dtype=None):
+    """`prefix` names an nn.Sequential(conv, bn) as in convbn_3d (submodule.py:16-19)."""
+    w = params[prefix + ".0.weight"]
+    cout = w.shape[1] if transposed else w.shape[0]
+    scale, shift = fold_bn(cout, _bn(params, prefix + ".1"), None)
+    return conv3d_block(x, w, scale, shift, stride, transposed, residual, relu, operand_dtype)
+
+
+def _hourglass(params, p, x, presqu, postsqu, operand_dtype=None):
+    """hourglass.forward (stackhourglass.py:43-62)."""
+    out = _convbn(params, p + ".conv1.0", x, stride=2, relu=True, operand_dtype=operand_dtype)
+    pre = _convbn(params, p + ".conv2", out, residual=postsqu, relu=True, operand_dtype=operand_dtype)
+    out = _convbn(params, p + ".conv3.0", pre, stride=2, relu=True, operand_dtype=operand_dtype)
+    out = _convbn(params, p + ".conv4.0", out, relu=True, operand_dtype=operand_dtype)
+    post = _convbn(params, p + ".conv5", out, transposed=True, residual=presqu if presqu is not None else pre,
+                   relu=True, operand_dtype=operand_dtype)
+    out = _convbn(params, p + ".conv6", post, transposed=True, operand_dtype=operand_dtype)
+    return out, pre, post
+
+
+def psmnet_aggregate(params: Dict[str, torch.Tensor], cost: torch.Tensor, operand_dtype=None):
+    """dres0 .. classif3 of PSMNet.forward (stackhourglass.py:135-149) with eval-mode BatchNorm.
+    Returns the three low-resolution costs (cost1, cost2, cost3), each [B,1,D/4,H/4,W/4]."""
+    od = operand_dtype
+    c0 = _convbn(params, "dres0.0", cost, relu=True, operand_dtype=od)
+    c0 = _convbn(params, "dres0.2", c0, relu=True, operand_dtype=od)
+    t = _convbn(params, "dres1.0", c0, relu=True, operand_dtype=od)
+    cost0 = _convbn(params, "dres1.2", t, residual=c0, operand_dtype=od)
+
+    out1, pre1, post1 = _hourglass(params, "dres2", cost0, None, None, od)
+    out1 = crop_add(out1, cost0)
+    out2, pre2, post2 = _hourglass(params, "dres3", out1, pre1, post1, od)
+    out2 = crop_add(out2, cost0)
+    out3, pre3, post3 = _hourglass(params, "dres4", out2, pre1, post2, od)   # NB: pre1, as in :144
+    out3 = crop_add(out3, cost0)
+
+    def classif(p, x):
+        t = _convbn(params, p + ".0", x, relu=True, operand_dtype=od)
+        return conv3d_block(t, params[p + ".2.weight"], operand_dtype=od)
+
+    cost1 = classif("classif1", out1)
+    cost2 = classif("classif2", out2) + cost1
+    cost3 = classif("classif3", out3) + cost2
+    return cost1, cost2, cost3
+
+
+def psmnet_hotpath(params: Dict[str, torch.Tensor], fL: torch.Tensor, fR: torch.Tensor, maxdisp: int,
+                   out_hw: Tuple[int, int], align_corners: bool = True, operand_dtype=None):
+    """The north-star path: PSMNet.forward from the feature maps on (stackhourglass.py:123-168):
+    concat volume -> dres0..classif3 -> 3x (trilinear upsample, softmax, regression).
+    Returns [pred3, pred2, pred1], each [B,H,W] (the order of :168)."""
+    cost = concat_volume(fL, fR, maxdisp // 4, "psm")
+    cost1, cost2, cost3 = psmnet_aggregate(params, cost, operand_dtype)
+    size = [maxdisp, out_hw[0], out_hw[1]]
+    preds = [upsample_softargmin(c.squeeze(1), size, align_corners) for c in (cost3, cost2, cost1)]
+    return preds
+
+
+def psmnet_random_params(seed: int = 0, calibrate_on: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    """Synthetic parameters of the 3-D part of PSMNet with the reference's names and init
+    (stackhourglass.py:73-114: conv weights N(0, sqrt(2/(k^3*Cout))), BN weight 1 / bias 0).
+    With `calibrate_on` (a cost volume) the BatchNorm running statistics are set, layer by layer,
+    to the batch statistics of that volume so that eval-mode activations stay O(1) (SURVEY hard
+    part 4); otherwise running stats are (0, 1)."""
+    g = torch.Generator().manual_seed(seed)
+    params: Dict[str, torch.Tensor] = {}
+
+    def conv(name, cin, cout, transposed=False):
+        n = 27 * cout
+        shape = (cin, cout, 3, 3, 3) if transposed else (cout, cin, 3, 3, 3)
+        # nn.ConvTranspose3d is not an nn.Conv3d instance: the reference's init loop leaves it at
+        # torch's default init; we use the same normal law for both (synthetic weights).
+        params[name + ".weight"] = torch.randn(shape, generator=g) * math.sqrt(2.0 / n)
+
+    def bn(name, c):
+        params[name + ".weight"] = torch.ones(c)
+        params[name + ".bias"] = torch.zeros(c)
+        params[name + ".running_mean"] = torch.zeros(c)
+        params[name + ".running_var"] = torch.ones(c)
+
+    def convbn(name, cin, cout, transposed=False):
+        conv(name + ".0", cin, cout, transposed); bn(name + ".1", cout)
+
+    convbn("dres0.0", 64, 32); convbn("dres0.2", 32, 32)
+    convbn("dres1.0", 32, 32); convbn("dres1.2", 32, 32)
+    for h in ("dres2", "dres3", "dres4"):
+        convbn(h + ".conv1.0", 32, 64); convbn(h + ".conv2", 64, 64)
+        convbn(h + ".conv3.0", 64, 64); convbn(h + ".conv4.0", 64, 64)
+        convbn(h + ".conv5", 64, 64, True); convbn(h + ".conv6", 64, 32, True)
+    for c in ("classif1", "classif2", "classif3"):
+        convbn(c + ".0", 32, 32); conv(c + ".2", 32, 1)
+    if calibrate_on is not None:
+        calibrate_bn_(params, calibrate_on)
+    return params
+
+
+def calibrate_bn_(params: Dict[str, torch.Tensor], cost: torch.Tensor) -> None:
+    """Set every BatchNorm's running_mean/var to the statistics its input conv produces on
+    `cost` (what one train-mode pass with momentum 1 would store; biased variance is used, the
+    synthetic harness only needs O(1) activations).  Walks the graph in execution order."""
+    def stat(prefix, y):
+        params[prefix + ".running_mean"] = y.mean(dim=(0, 2, 3, 4))
+        params[prefix + ".running_var"] = y.var(dim=(0, 2, 3, 4), unbiased=False) + 1e-3
+
+    def cb(prefix, x, stride=1, transposed=False, residual=None, relu=False):
+        w = params[prefix + ".0.weight"]
+        raw = conv3d_block(x, w, None, None, stride, transposed)
+        stat(prefix + ".1", raw)
+        return _convbn(params, prefix, x, stride, transposed, residual, relu)
+
+    def hg(p, x, presqu, postsqu):
+        out = cb(p + ".conv1.0", x, stride=2, relu=True)
+        pre = cb(p + ".conv2", out, residual=postsqu, relu=True)
+        out = cb(p + ".conv3.0", pre, stride=2, relu=True)
+        out = cb(p + ".conv4.0", out, relu=True)
+        post = cb(p + ".conv5", out, transposed=True, residual=presqu if presqu is not None else pre, relu=True)
+        out = cb(p + ".conv6", post, transposed=True)
+        return out, pre, post
+
+    c0 = cb("dres0.0", cost, relu=True); c0 = cb("dres0.2", c0, relu=True)
+    t = cb("dres1.0", c0, relu=True); cost0 = cb("dres1.2", t, residual=c0)
+    out1, pre1, post1 = hg("dres2", cost0, None, None); out1 = crop_add(out1, cost0)
+    out2, pre2, post2 = hg("dres3", out1, pre1, post1); out2 = crop_add(out2, cost0)
+    out3, pre3, post3 = hg("dres4", out2, pre1, post2); out3 = crop_add(out3, cost0)
+    for c, x in (("classif1", out1), ("classif2", out2), ("classif3", out3)):
+        cb(c + ".0", x, relu=True)

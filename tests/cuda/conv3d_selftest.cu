@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cstdint>
+#include <ctime>
+#include <unistd.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -17,6 +19,8 @@
 extern "C" int dsm_conv3d_fwd_ex(const void*, const void*, const float*, const float*, const void*, void*,
                                  int, int, int, int, int, int, int, int, int, int, int, int, int, int, void*);
 extern "C" int dsm_debug_conv_timeouts(void);
+extern "C" int dsm_debug_conv_set_progress(int*);
+static volatile int* g_prog = nullptr;
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(2); } } while (0)
 
@@ -110,9 +114,22 @@ static int run_case(const Case& c, bool timing, int reps) {
     void* y = c.f32 ? (void*)dyf : (void*)dyb;
     const void* res = c.f32 ? (const void*)dresf : (const void*)dresb;
 
+    printf("  launching %s (variant 0x%x)...\n", c.name, c.variant);
     int rc = dsm_conv3d_fwd_ex(dx, dw, sc, sh, res, y, c.B, c.Cin, c.Cout, c.D, c.H, c.W, c.stride, c.transposed, c.relu,
                                c.f32 ? DSM_F32 : DSM_BF16, 0, 0, 0, c.variant, nullptr);
+    {   // watchdog: never sit on a hung kernel; report how far CTA 1 got and leave
+        double waited = 0;
+        while (cudaStreamQuery(nullptr) == cudaErrorNotReady) {
+            struct timespec ts = {0, 20000000}; nanosleep(&ts, nullptr); waited += 0.02;
+            if (waited > 6.0) {
+                printf("  HUNG after %.1fs: progress per warp of CTA1 = %d %d %d %d\n", waited, g_prog ? g_prog[0] : -1, g_prog ? g_prog[1] : -1, g_prog ? g_prog[2] : -1, g_prog ? g_prog[3] : -1);
+                _exit(3);
+            }
+        }
+    }
     cudaError_t se = cudaDeviceSynchronize();
+    printf("  progress per warp of CTA1 = %d %d %d %d\n", g_prog ? g_prog[0] : -1, g_prog ? g_prog[1] : -1, g_prog ? g_prog[2] : -1, g_prog ? g_prog[3] : -1);
+    printf("  returned rc=%d sync=%s timeouts=%d\n", rc, cudaGetErrorString(se), dsm_debug_conv_timeouts());
     if (rc != 0 || se != cudaSuccess) {
         printf("CASE %-34s v%d : LAUNCH FAILED rc=%d (%s) sync=%s\n", c.name, c.variant, rc, dsm_strerror(rc), cudaGetErrorString(se));
         return 1;
@@ -155,9 +172,27 @@ static int run_case(const Case& c, bool timing, int reps) {
     return fail;
 }
 
+__global__ void hello_kernel(int* p) { if (threadIdx.x == 0) *p = 42; }
+
+static int g_level = 0, g_only = -1;
+
 int main(int argc, char** argv) {
+    setvbuf(stdout, nullptr, _IONBF, 0);
     const char* what = argc > 1 ? argv[1] : "quick";
+    g_level = argc > 2 ? atoi(argv[2]) : 0;      // bring-up level (see conv3d.cu debug_level)
+    g_only = argc > 3 ? atoi(argv[3]) : -1;      // run only this case index
     int fails = 0;
+    printf("selftest mode=%s level=%d only=%d\n", what, g_level, g_only);
+    {
+        int* d; CK(cudaMalloc(&d, 4)); hello_kernel<<<1, 32>>>(d); CK(cudaDeviceSynchronize());
+        int h = 0; CK(cudaMemcpy(&h, d, 4, cudaMemcpyDeviceToHost)); cudaFree(d);
+        printf("context up, hello kernel -> %d\n", h);
+        int* hp = nullptr; CK(cudaHostAlloc(&hp, 4 * sizeof(int), cudaHostAllocMapped));
+        for (int i = 0; i < 4; ++i) hp[i] = 0;
+        int* dp = nullptr; CK(cudaHostGetDevicePointer(&dp, hp, 0));
+        g_prog = hp; dsm_debug_conv_set_progress(dp);
+        if (!strcmp(what, "hello")) return h == 42 ? 0 : 1;
+    }
     if (!strcmp(what, "quick") || !strcmp(what, "full")) {
         std::vector<Case> cases = {
             // B Cin Cout D  H  W  s  T relu res aff f32 var
@@ -175,7 +210,7 @@ int main(int argc, char** argv) {
             {1, 64, 128, 6, 8, 18, 2, 0, 1, 0, 1, 0, 0, "s2 64->128"},
             {1, 128, 64, 3, 4, 9, 2, 1, 1, 1, 1, 0, 0, "deconv 128->64"},
         };
-        for (auto& c : cases) fails += run_case(c, false, 0);
+        { int idx = 0; for (auto& c : cases) { if (g_only < 0 || g_only == idx) { Case cc = c; cc.variant |= g_level << 8; fails += run_case(cc, false, 0); } ++idx; } }
     }
     if (!strcmp(what, "shift") || !strcmp(what, "full")) {
         // row-shifted descriptor experiments (MODE_SHIFT), both base-offset conventions
@@ -186,7 +221,7 @@ int main(int argc, char** argv) {
             {1, 64, 64, 4, 6, 20, 1, 0, 1, 1, 1, 0, 3, "s1 64->64 SHIFT bo=addr"},
             {1, 64, 32, 4, 6, 20, 1, 0, 1, 0, 1, 0, 2, "s1 64->32 SHIFT bo=0"},
         };
-        for (auto& c : cases) fails += run_case(c, false, 0);
+        { int idx = 0; for (auto& c : cases) { if (g_only < 0 || g_only == idx) { Case cc = c; cc.variant |= g_level << 8; fails += run_case(cc, false, 0); } ++idx; } }
     }
     if (!strcmp(what, "time") || !strcmp(what, "full")) {
         std::vector<Case> cases = {
@@ -200,7 +235,7 @@ int main(int argc, char** argv) {
             {1, 64, 64, 12, 24, 78, 2, 1, 1, 1, 1, 0, 0, "conv5 deconv 64->64"},
             {1, 64, 32, 24, 48, 156, 2, 1, 0, 1, 1, 0, 0, "conv6 deconv 64->32"},
         };
-        for (auto& c : cases) fails += run_case(c, true, 10);
+        { int idx = 0; for (auto& c : cases) { if (g_only < 0 || g_only == idx) { Case cc = c; cc.variant |= g_level << 8; fails += run_case(cc, true, 10); } ++idx; } }
     }
     if (!strcmp(what, "timeshift") || !strcmp(what, "full")) {
         std::vector<Case> cases = {
@@ -208,7 +243,7 @@ int main(int argc, char** argv) {
             {1, 32, 32, 48, 96, 312, 1, 0, 1, 1, 1, 0, 2, "32->32 SHIFT bo=0"},
             {1, 64, 64, 24, 48, 156, 1, 0, 1, 1, 1, 0, 2, "conv2 64->64 SHIFT bo=0"},
         };
-        for (auto& c : cases) fails += run_case(c, true, 10);
+        { int idx = 0; for (auto& c : cases) { if (g_only < 0 || g_only == idx) { Case cc = c; cc.variant |= g_level << 8; fails += run_case(cc, true, 10); } ++idx; } }
     }
     printf("SELFTEST %s: %d failing case(s), timeouts=%d\n", what, fails, dsm_debug_conv_timeouts());
     return fails ? 1 : 0;

@@ -1,0 +1,148 @@
+"""GPU (B200): the tcgen05 conv3d blocks and the PSMNet hot path against the oracle / golden vectors.
+
+bf16 tolerance: conv operands are rounded to bf16, accumulation is fp32, activations are stored
+in bf16.  Layer level: against the oracle run with bf16-rounded operands, error <= 2^-7 of the
+output scale (one bf16 rounding of the result).  Path level (north_star): mean |disparity delta|
+against the fp32 oracle < 0.01 px."""
+import pytest
+import torch
+
+import oracle.ops as O
+from conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def run_layer(x, weight, scale, shift, stride, transposed, residual, relu, variant=0):
+    from dsmnet_b200.conv3d import FusedConv3d, conv_timeouts
+    from dsmnet_b200.volume_layout import PaddedVolume
+
+    class BN:  # minimal stand-in carrying folded scale/shift
+        pass
+    layer = FusedConv3d(weight.cuda(), None, None, stride, transposed, relu, variant=variant)
+    if scale is not None:
+        cp = layer.scale.numel()
+        layer.scale[:scale.numel()] = scale.cuda(); layer.shift[:shift.numel()] = shift.cuda()
+        layer.identity_affine = False
+    xv = PaddedVolume.from_ncdhw(x.cuda())
+    rv = None
+    if residual is not None:
+        rv = residual.cuda().contiguous() if layer.cout == 1 else PaddedVolume.from_ncdhw(residual.cuda())
+        if layer.cout == 1:
+            rv = rv.squeeze(1)
+    y = layer(xv, None, rv)
+    assert conv_timeouts() == 0
+    return y.unsqueeze(1).cpu() if layer.cout == 1 else y.to_ncdhw().cpu()
+
+
+CASES = [
+    # cin, cout, (D,H,W), stride, transposed, residual, relu
+    (32, 32, (4, 6, 20), 1, False, True, True),
+    (64, 32, (5, 7, 19), 1, False, False, True),
+    (64, 64, (6, 9, 21), 1, False, True, True),
+    (32, 1, (4, 6, 20), 1, False, True, False),
+    (32, 64, (8, 12, 40), 2, False, False, True),
+    (64, 64, (7, 11, 37), 2, False, False, True),
+    (64, 64, (3, 5, 10), 2, True, True, True),
+    (64, 32, (3, 5, 10), 2, True, True, False),
+    (32, 1, (3, 5, 10), 2, True, False, False),
+    (128, 128, (3, 4, 9), 1, False, False, True),
+    (64, 128, (6, 8, 18), 2, False, False, True),
+    (128, 64, (3, 4, 9), 2, True, True, True),
+]
+
+
+@pytest.mark.parametrize("cin,cout,dims,stride,transposed,use_res,relu", CASES)
+def test_conv_layer_vs_oracle(cin, cout, dims, stride, transposed, use_res, relu):
+    torch.manual_seed(0)
+    B = 2
+    x = torch.randn(B, cin, *dims)
+    w = torch.randn(cin, cout, 3, 3, 3) if transposed else torch.randn(cout, cin, 3, 3, 3)
+    w = w * (2.0 / (27 * cin)) ** 0.5
+    scale = torch.rand(cout) + 0.5; shift = torch.randn(cout) * 0.3
+    ref0 = O.conv3d_block(x, w, scale, shift, stride, transposed, None, False, torch.bfloat16)
+    residual = torch.randn_like(ref0) if use_res else None
+    if residual is not None and cout != 1:
+        residual = residual.to(torch.bfloat16).float()
+    ref = O.conv3d_block(x, w, scale, shift, stride, transposed, residual, relu, torch.bfloat16)
+    out = run_layer(x, w, scale, shift, stride, transposed, residual, relu)
+    assert out.shape == ref.shape
+    tol = (2e-5 if cout == 1 else 2.0 ** -7) * float(ref.abs().max())
+    assert float((out - ref).abs().max()) <= tol
+
+
+@pytest.mark.parametrize("name,transposed", [("gc_conv_s2", False), ("gc_deconv", True)])
+def test_gc_layers_golden(name, transposed):
+    g = load_golden(name)
+    bn = {"weight": g["bn_weight"], "bias": g["bn_bias"], "running_mean": g["bn_mean"], "running_var": g["bn_var"]}
+    scale, shift = O.fold_bn(32, bn, g["bias"])
+    out = run_layer(g["x"], g["weight"], scale, shift, 2, transposed, None, True)
+    assert out.shape == g["y"].shape
+    assert float((out - g["y"]).abs().max()) <= 2.0 ** -6 * float(g["y"].abs().max())   # bf16 operands + bf16 output
+
+
+def test_crop_semantics_odd_sizes():
+    """myadd_3d crop-to-min (stackhourglass.py:10-20): deconv of an odd-sized skip connection."""
+    torch.manual_seed(1)
+    x = torch.randn(1, 64, 3, 4, 6)                       # deconv -> 6 x 8 x 12
+    w = torch.randn(64, 32, 3, 3, 3) * 0.05
+    res = torch.randn(1, 32, 5, 7, 11).to(torch.bfloat16).float()   # smaller skip -> result is 5 x 7 x 11
+    ref = O.conv3d_block(x, w, None, None, 2, True, res, True, torch.bfloat16)
+    out = run_layer(x, w, None, None, 2, True, res, True)
+    assert out.shape == ref.shape == (1, 32, 5, 7, 11)
+    assert float((out - ref).abs().max()) <= 2.0 ** -7 * float(ref.abs().max())
+
+
+def _hotpath_module(params, maxdisp):
+    from dsmnet_b200.psmnet import PSMNetHotPath
+    m = PSMNetHotPath(maxdisp)
+    missing = m.load_state_dict(params, strict=False)
+    assert not missing.unexpected_keys
+    assert all(k.endswith("num_batches_tracked") for k in missing.missing_keys), missing.missing_keys
+    return m.cuda().eval()
+
+
+def test_psmnet_hotpath_golden():
+    """the reference's own PSMNet 3-D stack + heads (fixture from its modules) vs the CUDA path."""
+    import hashlib
+    g = load_golden("psmnet_hotpath")
+    cost = O.concat_volume(g["fL"], g["fR"], g["maxdisp"] // 4, "psm")
+    params = O.psmnet_random_params(seed=g["seed"], calibrate_on=cost)
+    h = hashlib.sha256()
+    for k in sorted(params):
+        h.update(k.encode()); h.update(params[k].numpy().tobytes())
+    if h.hexdigest() != g["params_sha256"]:
+        pytest.skip("torch CPU RNG stream differs from the fixture's")
+    m = _hotpath_module(params, g["maxdisp"])
+    with torch.no_grad():
+        c1, c2, c3 = m.aggregate(g["fL"].cuda(), g["fR"].cuda())
+        preds = m(g["fL"].cuda(), g["fR"].cuda(), (g["H"], g["W"]))
+    for mine, ref in ((c1, g["cost1"]), (c2, g["cost2"]), (c3, g["cost3"])):
+        assert rel_err(mine.unsqueeze(1), ref) < 3e-2                    # bf16 activations through ~20 layers
+    for mine, ref in zip(preds, (g["pred3"], g["pred2"], g["pred1"])):
+        assert float((mine.cpu() - ref).abs().mean()) < 0.01             # north_star: mean EPE delta < 0.01 px
+
+
+@pytest.mark.parametrize("B,H,W,maxdisp", [(1, 48, 96, 48), (2, 24, 40, 32)])
+def test_psmnet_hotpath_vs_oracle(B, H, W, maxdisp):
+    torch.manual_seed(5)
+    fL = torch.randn(B, 32, H // 4, W // 4); fR = torch.randn(B, 32, H // 4, W // 4)
+    cost = O.concat_volume(fL, fR, maxdisp // 4, "psm")
+    params = O.psmnet_random_params(seed=11, calibrate_on=cost)
+    ref = O.psmnet_hotpath(params, fL, fR, maxdisp, (H, W))
+    m = _hotpath_module(params, maxdisp)
+    with torch.no_grad():
+        preds = m(fL.cuda(), fR.cuda(), (H, W))
+    from dsmnet_b200.conv3d import conv_timeouts
+    assert conv_timeouts() == 0
+    for mine, r in zip(preds, ref):
+        assert mine.shape == r.shape == (B, H, W)
+        assert float((mine.cpu() - r).abs().mean()) < 0.01
+
+
+def test_training_mode_raises():
+    from dsmnet_b200 import _lib
+    from dsmnet_b200.psmnet import PSMNetHotPath
+    m = PSMNetHotPath(32).cuda().train()
+    with pytest.raises(_lib.DsmError):
+        m(torch.randn(1, 32, 8, 12, device="cuda"), torch.randn(1, 32, 8, 12, device="cuda"), (32, 48))

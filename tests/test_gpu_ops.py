@@ -1,0 +1,222 @@
+"""GPU (B200) parity tests: every CUDA op, called through the C-ABI, against the CPU oracle on the
+same seeded inputs and against the golden vectors frozen from the reference's own code.
+
+Tolerances (BASELINE.json north_star): bit-exact for concat-volume construction and warp
+indexing; <= 1e-4 relative for the fp32 correlation, regression and warp outputs."""
+import numpy as np
+import pytest
+import torch
+
+import oracle.ops as O
+from conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+REL = 1e-4
+
+
+def dev(t):
+    return t.cuda()
+
+
+# ---------------------------------------------------------------- op 1: corr1d
+@pytest.mark.parametrize("name", ["corr1d_dispnetc", "corr1d_iresnet2", "corr1d_d_gt_w"])
+def test_corr1d_golden(name):
+    from dsmnet_b200.corr1d import Corr1d
+    g = load_golden(name)
+    fL = dev(g["fL"]).requires_grad_(); fR = dev(g["fR"]).requires_grad_()
+    out = Corr1d(g["kernel_size"], g["stride"], g["D"])(fL, fR)
+    assert rel_err(out, g["out"]) < REL
+    out.backward(dev(g["gout"]))
+    assert rel_err(fL.grad, g["gL"]) < REL and rel_err(fR.grad, g["gR"]) < REL
+
+
+@pytest.mark.parametrize("B,C,H,W,D,s", [
+    (1, 128, 96, 312, 41, 1),     # DispNetC @384x1248 (dispnetcorr.py:27,77)  — BASELINE config 1
+    (1, 128, 135, 240, 81, 1),    # iResNet stage 1 @540x960 (iresnet.py:34,107)
+    (1, 64, 270, 480, 41, 2),     # iResNet refinement (iresnet.py:69,175), stride 2
+    (2, 20, 7, 45, 13, 1),        # ragged: C, W not multiples of anything
+    (1, 6, 3, 9, 5, 2),           # tiny, W%4 != 0 -> scalar store path
+])
+def test_corr1d_vs_oracle(B, C, H, W, D, s):
+    from dsmnet_b200.corr1d import corr1d
+    torch.manual_seed(0)
+    fL = torch.relu(torch.randn(B, C, H, W)); fR = torch.relu(torch.randn(B, C, H, W))
+    ref = O.corr1d(fL, fR, D, s)
+    a = dev(fL).requires_grad_(); b = dev(fR).requires_grad_()
+    out = corr1d(a, b, D, s)
+    assert rel_err(out, ref) < REL
+    g = torch.randn(B, D, H, W)
+    gL, gR = O.corr1d_grads(g, fL, fR, s)
+    out.backward(dev(g))
+    assert rel_err(a.grad, gL) < REL and rel_err(b.grad, gR) < REL
+
+
+def test_corr1d_linearity_full_size():
+    """size-independent property at the BASELINE size: corr(a*fL, fR) = a*corr(fL, fR); corr(fL, fR1+fR2) additive."""
+    from dsmnet_b200.corr1d import corr1d
+    torch.manual_seed(1)
+    fL = torch.randn(1, 128, 96, 312, device="cuda"); r1 = torch.randn_like(fL); r2 = torch.randn_like(fL)
+    c1 = corr1d(fL, r1, 41); c2 = corr1d(fL, r2, 41); c12 = corr1d(fL, r1 + r2, 41)
+    assert rel_err(c12, c1 + c2) < REL
+    assert rel_err(corr1d(2.0 * fL, r1, 41), 2.0 * c1) < 1e-6
+    assert float(c1[:, 5, :, :5].abs().max()) == 0.0          # x < d is exactly zero
+
+
+# ---------------------------------------------------------------- op 2: concat volume
+@pytest.mark.parametrize("name,mode,dkey", [("volume_psm", "psm", None), ("volume_gc", "gc", "D"), ("volume_gc_right", "gc_right", "D")])
+def test_volume_golden_bit_exact(name, mode, dkey):
+    from dsmnet_b200.cost_volume import concat_volume
+    g = load_golden(name)
+    D = g["maxdisp"] // 4 if dkey is None else g[dkey]
+    out = concat_volume(dev(g["fL"]), dev(g["fR"]), D, mode)
+    assert torch.equal(out.cpu(), g["out"])
+
+
+@pytest.mark.parametrize("mode", ["psm", "gc", "gc_right"])
+@pytest.mark.parametrize("shape", [(1, 32, 12, 40, 9), (2, 8, 5, 13, 20), (1, 32, 96, 312, 48)])
+def test_volume_vs_oracle(mode, shape):
+    from dsmnet_b200.cost_volume import concat_volume
+    B, C, H, W, D = shape
+    torch.manual_seed(2)
+    fL = torch.randn(B, C, H, W); fR = torch.randn(B, C, H, W)
+    ref = O.concat_volume(fL, fR, D, mode)
+    a = dev(fL).requires_grad_(); b = dev(fR).requires_grad_()
+    out = concat_volume(a, b, D, mode)
+    assert torch.equal(out.detach().cpu(), ref)                       # bit-exact (pure copies)
+    if B * C * H * W * D < 5e6:
+        g = torch.randn_like(ref)
+        gL, gR = O.concat_volume_grads(g, D, mode)
+        out.backward(dev(g))
+        assert rel_err(a.grad, gL) < 1e-5 and rel_err(b.grad, gR) < 1e-5
+    if C % 8 == 0:
+        vol = concat_volume(dev(fL), dev(fR), D, mode, padded_bf16=True)
+        v6 = vol.view6().float().cpu()                                # [B,D+2,H+2,W+2,2C]
+        inner = v6[:, 1:-1, 1:-1, 1:-1, :].permute(0, 4, 1, 2, 3)
+        assert torch.equal(inner, ref.to(torch.bfloat16).float())     # RNE of the same values
+        rim = v6.clone(); rim[:, 1:-1, 1:-1, 1:-1, :] = 0
+        assert float(rim.abs().max()) == 0.0                          # zero rim written
+        assert torch.equal(vol.to_ncdhw().cpu(), ref.to(torch.bfloat16).float())
+
+
+def test_pack_unpack_roundtrip():
+    from dsmnet_b200.volume_layout import PaddedVolume
+    torch.manual_seed(3)
+    x = torch.randn(2, 32, 5, 7, 11)
+    v = PaddedVolume.from_ncdhw(dev(x))
+    assert torch.equal(v.to_ncdhw().cpu(), x.to(torch.bfloat16).float())
+    v6 = v.view6().float().cpu(); v6[:, 1:-1, 1:-1, 1:-1, :] = 0
+    assert float(v6.abs().max()) == 0.0
+
+
+# ---------------------------------------------------------------- op 4: soft-argmin
+def test_heads_golden():
+    from dsmnet_b200.softargmin import softargmin, upsample_softargmin, disparityregression
+    g = load_golden("head_psm")
+    assert rel_err(upsample_softargmin(dev(g["cost_lr"]), g["size"], True), g["pred"]) < REL
+    assert rel_err(softargmin(dev(g["upsampled"]).squeeze(1), 1.0), g["pred"]) < REL
+    assert rel_err(disparityregression(16)(dev(g["prob"])), g["pred"]) < REL
+    g = load_golden("head_gc")
+    assert rel_err(softargmin(dev(g["x37"]).squeeze(1), -1.0).unsqueeze(1), g["pred"]) < REL
+
+
+@pytest.mark.parametrize("B,D,H,W,sign", [(1, 192, 64, 128, 1.0), (2, 96, 17, 23, -1.0), (1, 5, 3, 7, 1.0)])
+def test_softargmin_vs_oracle(B, D, H, W, sign):
+    from dsmnet_b200.softargmin import softargmin
+    torch.manual_seed(4)
+    cost = torch.randn(B, D, H, W) * 2
+    c = cost.clone().requires_grad_()
+    ref = O.softargmin(c, sign)
+    g = torch.randn_like(ref)
+    ref.backward(g)
+    x = dev(cost).requires_grad_()
+    out = softargmin(x, sign)
+    assert rel_err(out, ref) < REL
+    out.backward(dev(g))
+    assert rel_err(x.grad, c.grad) < REL
+
+
+@pytest.mark.parametrize("ac", [True, False])
+@pytest.mark.parametrize("lr,size", [((1, 12, 24, 78), (48, 96, 312)), ((2, 5, 7, 9), (17, 26, 35)), ((1, 48, 96, 312), (192, 384, 1248))])
+def test_upsample_softargmin_vs_oracle(lr, size, ac):
+    from dsmnet_b200.softargmin import upsample_softargmin
+    torch.manual_seed(5)
+    cost = torch.randn(*lr) * 2
+    out = upsample_softargmin(dev(cost), size, ac)
+    if lr[1] == 48:      # BASELINE size: check a strip against the oracle (full-size CPU upsample is slow)
+        ref = O.upsample_softargmin(cost, size, ac)[:, 100:140]
+        assert rel_err(out[:, 100:140], ref) < REL
+    else:
+        assert rel_err(out, O.upsample_softargmin(cost, size, ac)) < REL
+
+
+def test_softargmin_properties_full_size():
+    """at the BASELINE head size (192 x 384 x 1248): shift invariance and one-hot limit."""
+    from dsmnet_b200.softargmin import softargmin
+    torch.manual_seed(6)
+    cost = torch.randn(1, 192, 384, 1248, device="cuda")
+    d = softargmin(cost, 1.0)
+    assert rel_err(softargmin(cost + 3.0, 1.0), d) < REL             # softmax shift invariance
+    assert float(d.min()) >= 0.0 and float(d.max()) <= 191.0
+    idx = torch.randint(0, 192, (1, 1, 384, 1248), device="cuda")
+    onehot = torch.full_like(cost, -80.0).scatter_(1, idx, 80.0)
+    assert float((softargmin(onehot, 1.0) - idx[:, 0].float()).abs().max()) < 1e-3
+
+
+# ---------------------------------------------------------------- op 5: imwrap
+IMWRAP = ["imwrap_plain", "imwrap_fliplr", "imwrap_lefttop", "imwrap_scale2", "imwrap_intdisp", "imwrap_oob"]
+
+
+def _indices(disp, h0, w0, LeftTop, scale, fliplr):
+    from dsmnet_b200 import _lib
+    from dsmnet_b200.imwrap import grid_vectors
+    B, _, h, w = disp.shape
+    row, col = grid_vectors(h0, w0, h, w, LeftTop, scale)
+    d = disp.cuda().contiguous(); r = row.cuda(); c = col.cuda()
+    x0 = torch.empty(B, h, w, dtype=torch.int32, device="cuda"); y0 = torch.empty_like(x0)
+    _lib.check(_lib.lib().dsm_warp_indices(d.data_ptr(), r.data_ptr(), c.data_ptr(), int(fliplr), x0.data_ptr(), y0.data_ptr(),
+                                           B, h0, w0, h, w, _lib.stream_ptr()), "dsm_warp_indices")
+    return x0.cpu().numpy(), y0.cpu().numpy(), row, col
+
+
+@pytest.mark.parametrize("name", IMWRAP)
+def test_imwrap_golden(name):
+    from dsmnet_b200.imwrap import imwrap_BCHW
+    g = load_golden(name)
+    src = dev(g["src"]).requires_grad_(); disp = dev(g["disp"]).requires_grad_()
+    out = imwrap_BCHW(src, disp, g["fliplr"], list(g["LeftTop"]), g["scale_factor"], delt=g["delt"])
+    assert rel_err(out, g["out"]) < REL
+    assert torch.equal(out.detach().cpu() != 0, g["out"] != 0)        # validity mask (loss.py:156,199)
+    out.backward(dev(g["gout"]))
+    assert rel_err(src.grad, g["gsrc"]) < REL
+    assert rel_err(disp.grad, g["gdisp"]) < 2e-4
+    # bit-exact sampling indices vs the independent closed form
+    _, _, h0, w0 = g["src"].shape
+    x0, y0, row, col = _indices(g["disp"], h0, w0, tuple(g["LeftTop"]), g["scale_factor"], g["fliplr"])
+    _, rx0, ry0 = O.imwrap_closed_form(g["src"].numpy(), g["disp"].numpy(), row.numpy(), col.numpy(), g["fliplr"], g["delt"])
+    assert np.array_equal(x0, rx0) and np.array_equal(y0, ry0)
+
+
+def test_imwrap_iresnet_size():
+    """iResNet feature-constancy warp (iresnet.py:169): (1,32,540,960) by (1,1,540,960)."""
+    from dsmnet_b200.imwrap import imwrap_BCHW
+    torch.manual_seed(7)
+    src = torch.rand(1, 32, 540, 960); disp = torch.rand(1, 1, 540, 960) * 96
+    disp[:, :, ::3] = disp[:, :, ::3].round()                      # integer disparities on a third of the rows
+    ref = O.imwrap(src, disp, delt=5e-5)
+    out = imwrap_BCHW(dev(src), dev(disp), delt=5e-5)
+    assert rel_err(out, ref) < REL
+    x0, y0, row, col = _indices(disp, 540, 960, (0, 0), 1, False)
+    _, rx0, ry0 = O.imwrap_closed_form(src[:, :1].numpy(), disp.numpy(), row.numpy(), col.numpy(), False, 5e-5)
+    assert np.array_equal(x0, rx0) and np.array_equal(y0, ry0)
+    # zero disparity is the identity (+delt)
+    ident = imwrap_BCHW(dev(src), torch.zeros(1, 1, 540, 960, device="cuda"), delt=0.0)
+    assert float((ident.cpu() - src).abs().max()) < 1e-5
+
+
+def test_imwrap_rng_stream():
+    """the drop-in consumes exactly one torch.rand(1) per call, like imwrap.py:70."""
+    from dsmnet_b200.imwrap import imwrap_BCHW
+    src = torch.rand(1, 1, 8, 8, device="cuda"); disp = torch.zeros(1, 1, 8, 8, device="cuda")
+    torch.manual_seed(11); imwrap_BCHW(src, disp); after = torch.rand(1)
+    torch.manual_seed(11); torch.rand(1); expect = torch.rand(1)
+    assert torch.equal(after, expect)
