@@ -191,7 +191,7 @@ class PSMNetHotPath(nn.Module):
 
 def convbn(in_planes, out_planes, kernel_size, stride, pad, dilation):
     return nn.Sequential(nn.Conv2d(in_planes, out_planes, kernel_size=kernel_size, stride=stride,
-                                   padding=dilation if dilation > 1 else pad, dilation=dilation, bias=False),
+                                   padding=dilation, dilation=dilation, bias=False),   # sic: `pad` unused (submodule.py:12)
                          nn.BatchNorm2d(out_planes))
 
 
