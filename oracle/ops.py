@@ -152,13 +152,16 @@ def crop_add(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 def conv3d_block(x: torch.Tensor, weight: torch.Tensor, scale: Optional[torch.Tensor] = None,
                  shift: Optional[torch.Tensor] = None, stride: int = 1, transposed: bool = False,
                  residual: Optional[torch.Tensor] = None, relu: bool = False,
-                 operand_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+                 operand_dtype: Optional[torch.dtype] = None,
+                 storage_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
     """Conv3d(k3,p1,stride) or ConvTranspose3d(k3,s2,p1,output_padding=1), then the folded
     BatchNorm affine, then optional crop-add of `residual`, then optional ReLU.
 
     Restates convbn_3d (submodule.py:16-19), the hourglass wiring (stackhourglass.py:26-41,45-60)
     and conv3d_bn/deconv3d_bn (util_conv.py:150-179).  `operand_dtype=torch.bfloat16` rounds the
-    conv operands (not the accumulation) the way the tensor-core kernel does."""
+    conv operands (not the accumulation) the way the tensor-core kernel does; `storage_dtype`
+    additionally rounds the block's result the way the kernel stores activations (so a following
+    residual add reads the rounded value).  Both None = the reference's fp32 arithmetic."""
     if operand_dtype is not None:
         x = x.to(operand_dtype).float()
         weight = weight.to(operand_dtype).float()
@@ -174,6 +177,8 @@ def conv3d_block(x: torch.Tensor, weight: torch.Tensor, scale: Optional[torch.Te
         y = crop_add(y, residual)
     if relu:
         y = F.relu(y)
+    if storage_dtype is not None:
+        y = y.to(storage_dtype).float()
     return y
 
 
@@ -275,22 +280,24 @@ def _bn(params: Dict[str, torch.Tensor], prefix: str) -> Dict[str, torch.Tensor]
 
 
 def _convbn(params, prefix, x, stride=1, transposed=False, residual=None, relu=False, operand_dtype=None):
-    """`prefix` names an nn.Sequential(conv, bn) as in convbn_3d (submodule.py:16-19)."""
+    """`prefix` names an nn.Sequential(conv, bn) as in convbn_3d (submodule.py:16-19).
+    `operand_dtype` may be a (operand, storage) pair."""
     w = params[prefix + ".0.weight"]
     cout = w.shape[1] if transposed else w.shape[0]
     scale, shift = fold_bn(cout, _bn(params, prefix + ".1"), None)
-    return conv3d_block(x, w, scale, shift, stride, transposed, residual, relu, operand_dtype)
+    od, sd = operand_dtype if isinstance(operand_dtype, tuple) else (operand_dtype, None)
+    return conv3d_block(x, w, scale, shift, stride, transposed, residual, relu, od, sd)
 
 
-def _hourglass(params, p, x, presqu, postsqu, operand_dtype=None):
-    """hourglass.forward (stackhourglass.py:43-62)."""
+def _hourglass(params, p, x, presqu, postsqu, operand_dtype=None, add_after=None):
+    """hourglass.forward (stackhourglass.py:43-62); `add_after` is the caller's myadd_3d(out, cost0)."""
     out = _convbn(params, p + ".conv1.0", x, stride=2, relu=True, operand_dtype=operand_dtype)
     pre = _convbn(params, p + ".conv2", out, residual=postsqu, relu=True, operand_dtype=operand_dtype)
     out = _convbn(params, p + ".conv3.0", pre, stride=2, relu=True, operand_dtype=operand_dtype)
     out = _convbn(params, p + ".conv4.0", out, relu=True, operand_dtype=operand_dtype)
     post = _convbn(params, p + ".conv5", out, transposed=True, residual=presqu if presqu is not None else pre,
                    relu=True, operand_dtype=operand_dtype)
-    out = _convbn(params, p + ".conv6", post, transposed=True, operand_dtype=operand_dtype)
+    out = _convbn(params, p + ".conv6", post, transposed=True, residual=add_after, operand_dtype=operand_dtype)
     return out, pre, post
 
 
@@ -303,16 +310,14 @@ def psmnet_aggregate(params: Dict[str, torch.Tensor], cost: torch.Tensor, operan
     t = _convbn(params, "dres1.0", c0, relu=True, operand_dtype=od)
     cost0 = _convbn(params, "dres1.2", t, residual=c0, operand_dtype=od)
 
-    out1, pre1, post1 = _hourglass(params, "dres2", cost0, None, None, od)
-    out1 = crop_add(out1, cost0)
-    out2, pre2, post2 = _hourglass(params, "dres3", out1, pre1, post1, od)
-    out2 = crop_add(out2, cost0)
-    out3, pre3, post3 = _hourglass(params, "dres4", out2, pre1, post2, od)   # NB: pre1, as in :144
-    out3 = crop_add(out3, cost0)
+    # the "+ cost0" of :139,142,145 is the residual of conv6 (so that a storage dtype rounds once)
+    out1, pre1, post1 = _hourglass(params, "dres2", cost0, None, None, od, cost0)
+    out2, pre2, post2 = _hourglass(params, "dres3", out1, pre1, post1, od, cost0)
+    out3, pre3, post3 = _hourglass(params, "dres4", out2, pre1, post2, od, cost0)   # NB: pre1, as in :144
 
     def classif(p, x):
         t = _convbn(params, p + ".0", x, relu=True, operand_dtype=od)
-        return conv3d_block(t, params[p + ".2.weight"], operand_dtype=od)
+        return conv3d_block(t, params[p + ".2.weight"], operand_dtype=od[0] if isinstance(od, tuple) else od)
 
     cost1 = classif("classif1", out1)
     cost2 = classif("classif2", out2) + cost1
@@ -326,6 +331,8 @@ def psmnet_hotpath(params: Dict[str, torch.Tensor], fL: torch.Tensor, fR: torch.
     concat volume -> dres0..classif3 -> 3x (trilinear upsample, softmax, regression).
     Returns [pred3, pred2, pred1], each [B,H,W] (the order of :168)."""
     cost = concat_volume(fL, fR, maxdisp // 4, "psm")
+    if isinstance(operand_dtype, tuple) and operand_dtype[1] is not None:
+        cost = cost.to(operand_dtype[1]).float()
     cost1, cost2, cost3 = psmnet_aggregate(params, cost, operand_dtype)
     size = [maxdisp, out_hw[0], out_hw[1]]
     preds = [upsample_softargmin(c.squeeze(1), size, align_corners) for c in (cost3, cost2, cost1)]
@@ -338,15 +345,16 @@ def psmnet_random_params(seed: int = 0, calibrate_on: Optional[torch.Tensor] = N
     With `calibrate_on` (a cost volume) the BatchNorm running statistics are set, layer by layer,
     to the batch statistics of that volume so that eval-mode activations stay O(1) (SURVEY hard
     part 4); otherwise running stats are (0, 1)."""
-    g = torch.Generator().manual_seed(seed)
-    params: Dict[str, torch.Tensor] = {}
+    rs = np.random.RandomState(seed)     # numpy's MT19937 stream is identical on every host
+    params: Dict[str, torch.Tensor] = {}  # (torch's CPU randn is not: it depends on the SIMD width)
 
     def conv(name, cin, cout, transposed=False):
         n = 27 * cout
         shape = (cin, cout, 3, 3, 3) if transposed else (cout, cin, 3, 3, 3)
         # nn.ConvTranspose3d is not an nn.Conv3d instance: the reference's init loop leaves it at
         # torch's default init; we use the same normal law for both (synthetic weights).
-        params[name + ".weight"] = torch.randn(shape, generator=g) * math.sqrt(2.0 / n)
+        w = rs.standard_normal(size=shape).astype(np.float32) * np.float32(math.sqrt(2.0 / n))
+        params[name + ".weight"] = torch.from_numpy(w)
 
     def bn(name, c):
         params[name + ".weight"] = torch.ones(c)

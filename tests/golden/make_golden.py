@@ -30,8 +30,9 @@ def save(name, **arrays):
 
 def params_digest(params):
     h = hashlib.sha256()
-    for k in sorted(params):
-        h.update(k.encode()); h.update(params[k].detach().numpy().tobytes())
+    for k in sorted(params):          # RNG-derived tensors only (BN statistics depend on the host's conv kernels)
+        if params[k].dim() == 5:
+            h.update(k.encode()); h.update(params[k].detach().numpy().tobytes())
     return h.hexdigest()
 
 
@@ -96,7 +97,9 @@ def main():
 
     # ---- op 3 + the north-star path: the reference's PSMNet 3-D stack ----------------------------
     maxdisp, H, W = 32, 32, 80
-    fL = torch.randn(1, 32, H // 4, W // 4); fR = torch.randn(1, 32, H // 4, W // 4)
+    rs = np.random.RandomState(2024)
+    fL = torch.from_numpy(rs.standard_normal((1, 32, H // 4, W // 4)).astype(np.float32))
+    fR = torch.from_numpy(rs.standard_normal((1, 32, H // 4, W // 4)).astype(np.float32))
     cost = R.psm_volume(fL, fR, maxdisp)
     params = O.psmnet_random_params(seed=7, calibrate_on=cost)
     net = R.make_psmnet(maxdisp, seed=0)

@@ -64,9 +64,9 @@ def test_psmnet_hotpath():
     params = O.psmnet_random_params(seed=g["seed"], calibrate_on=cost)
     h = hashlib.sha256()
     for k in sorted(params):
-        h.update(k.encode()); h.update(params[k].numpy().tobytes())
-    if h.hexdigest() != g["params_sha256"]:
-        pytest.skip("torch CPU RNG stream differs from the one the fixture was generated with")
+        if params[k].dim() == 5:
+            h.update(k.encode()); h.update(params[k].numpy().tobytes())
+    assert h.hexdigest() == g["params_sha256"], "synthetic weights are not the ones the fixture was made with"
     c1, c2, c3 = O.psmnet_aggregate(params, cost)
     for mine, ref in ((c1, g["cost1"]), (c2, g["cost2"]), (c3, g["cost3"])):
         assert rel_err(mine, ref) < 1e-4
