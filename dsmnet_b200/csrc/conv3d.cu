@@ -418,7 +418,9 @@ int conv3d_dispatch(const void* x, const void* w, const float* scale, const floa
     g.Cout = Cout; g.transposed = transposed; g.relu = relu; g.y_f32 = (y_dtype == DSM_F32);
     g.nchunks = Cin / KC; g.P = P; g.desc_variant = variant & 1; g.debug_level = (variant >> 8) & 7;
     const int row_bytes = KC * 2;
-    const int mode = (!transposed && stride == 2) ? MODE_BOX : ((variant & 2) && !transposed ? MODE_SHIFT : MODE_FLAT);
+    // bit1 of `variant` SET selects the per-tap kernel (MODE_FLAT); the default for stride-1 convolutions is the
+    // row-shifted-descriptor kernel (validated bit-identical on B200), except N=128 whose stage would not fit twice
+    const int mode = (!transposed && stride == 2) ? MODE_BOX : ((!(variant & 2) && !transposed && NP <= 64) ? MODE_SHIFT : MODE_FLAT);
 
     {   // weights: [27*NP][Cin]
         cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)27 * NP};
@@ -501,8 +503,8 @@ extern "C" int dsm_conv3d_fwd(const void* x, const void* w_packed, const float* 
 
 // Extended form: (Do,Ho,Wo) is the extent of the y / residual buffers when it is a crop of the
 // natural output size (the reference's myadd_3d / myAdd3d crop-to-min semantics,
-// stackhourglass.py:10-20, util_fun.py:41-51); `variant` bit0 = descriptor base-offset mode,
-// bit1 = MODE_SHIFT (row-shifted descriptors) for stride-1 convolutions.
+// stackhourglass.py:10-20, util_fun.py:41-51); `variant` bit0 = descriptor base-offset mode (experiment),
+// bit1 = force the per-tap kernel instead of the row-shifted-descriptor kernel for stride-1 convolutions.
 extern "C" int dsm_conv3d_fwd_ex(const void* x, const void* w_packed, const float* scale, const float* shift,
                                  const void* residual, void* y,
                                  int B, int Cin, int Cout, int D, int H, int W,

@@ -136,8 +136,8 @@ int dsm_warp_indices(const float* disp, const float* row, const float* col, int 
  * dsm_conv3d_fwd_ex: as dsm_conv3d_fwd, with (Do,Ho,Wo) = extent of the y/residual buffers when
  * that is a crop of the natural output size (the reference's crop-to-min add, myadd_3d /
  * myAdd3d, stackhourglass.py:10-20, util_fun.py:41-51; pass 0,0,0 for the natural size) and
- * `variant` (bit0: descriptor base-offset mode, bit1: row-shifted-descriptor kernel for stride-1
- * convolutions, bits 8-10: bring-up level; 0 = default path).                                  */
+ * `variant` (bit0: descriptor base-offset experiment, bit1: force the per-tap kernel instead of the
+ * default row-shifted-descriptor kernel for stride-1 convolutions, bits 8-10: bring-up level; 0 = default).                                  */
 int dsm_conv3d_fwd_ex(const void* x, const void* w_packed, const float* scale, const float* shift,
                       const void* residual, void* y,
                       int B, int Cin, int Cout, int D, int H, int W,

@@ -1,0 +1,116 @@
+"""GPU (B200): BASELINE.json's full sizes (PSMNet 384x1248, maxdisp 192: volume 64x48x96x312).
+
+The CPU oracle needs ~10 s per pass at this size, so most checks here are size-independent
+properties that are exact in bf16: with a one-hot ("delta") filter a convolution is a pure shift /
+subsample / zero-stuffing of its input, which exercises every tile boundary, the zero rim, all
+eight stride-2 sub-lattices and all eight transposed-conv parity classes over the whole volume.
+One full-size pass of the north-star path is compared with the oracle, and the north_star's
+tolerance (mean end-point-error delta < 0.01 px) is asserted there."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import oracle.ops as O
+
+pytestmark = pytest.mark.gpu
+D, H, W = 48, 96, 312
+
+
+def _delta_weight(cin, cout, tap, transposed):
+    kd, kh, kw = tap
+    w = torch.zeros(cin, cout, 3, 3, 3) if transposed else torch.zeros(cout, cin, 3, 3, 3)
+    for c in range(min(cin, cout)):
+        w[c, c, kd, kh, kw] = 1.0
+    return w
+
+
+def _run(x, w, stride, transposed):
+    from dsmnet_b200.conv3d import FusedConv3d, conv_timeouts
+    from dsmnet_b200.volume_layout import PaddedVolume
+    y = FusedConv3d(w.cuda(), None, None, stride, transposed, False)(PaddedVolume.from_ncdhw(x))
+    torch.cuda.synchronize()
+    assert conv_timeouts() == 0
+    return y.to_ncdhw()
+
+
+@pytest.mark.parametrize("tap", [(1, 1, 1), (0, 0, 0), (2, 2, 2), (0, 1, 2), (2, 0, 1)])
+def test_stride1_delta_filter_is_a_shift(tap):
+    torch.manual_seed(0)
+    x = torch.randn(1, 32, D, H, W, device="cuda").to(torch.bfloat16).float()
+    y = _run(x, _delta_weight(32, 32, tap, False), 1, False)
+    xp = F.pad(x, (1, 1, 1, 1, 1, 1))
+    kd, kh, kw = tap
+    assert torch.equal(y, xp[:, :, kd:kd + D, kh:kh + H, kw:kw + W])
+
+
+@pytest.mark.parametrize("tap", [(1, 1, 1), (0, 0, 0), (2, 2, 2), (0, 1, 2), (1, 2, 0)])
+def test_stride2_delta_filter_is_a_subsample(tap):
+    torch.manual_seed(1)
+    x = torch.randn(1, 32, D, H, W, device="cuda").to(torch.bfloat16).float()
+    y = _run(x, _delta_weight(32, 64, tap, False), 2, False)
+    xp = F.pad(x, (1, 1, 1, 1, 1, 1))
+    kd, kh, kw = tap
+    ref = xp[:, :, kd:kd + D:2, kh:kh + H:2, kw:kw + W:2]
+    assert y.shape == (1, 64, D // 2, H // 2, W // 2)
+    assert torch.equal(y[:, :32], ref) and float(y[:, 32:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("tap", [(1, 1, 1), (0, 0, 0), (2, 2, 2), (0, 1, 2), (2, 1, 0)])
+def test_transposed_delta_filter_is_zero_stuffing(tap):
+    torch.manual_seed(2)
+    d, h, w = D // 2, H // 2, W // 2
+    x = torch.randn(1, 64, d, h, w, device="cuda").to(torch.bfloat16).float()
+    wt = _delta_weight(64, 32, tap, True)
+    y = _run(x, wt, 2, True)
+    ref = F.conv_transpose3d(x[:, :32], wt[:32].cuda(), stride=2, padding=1, output_padding=1)   # exact: one term per output
+    assert y.shape == (1, 32, D, H, W)
+    assert torch.equal(y, ref)
+
+
+def test_concat_volume_checksum_full_size():
+    """sum over d of the PSM volume = closed-form weighted sums of the inputs (exact in fp64)."""
+    from dsmnet_b200.cost_volume import concat_volume
+    torch.manual_seed(3)
+    fL = torch.randn(1, 32, H, W, device="cuda"); fR = torch.randn(1, 32, H, W, device="cuda")
+    vol = concat_volume(fL, fR, D, "psm").double()
+    xs = torch.arange(W, device="cuda")
+    cnt = torch.clamp(xs + 1, max=D).double()                           # number of d with d <= x
+    assert torch.allclose(vol[:, :32].sum(2), fL.double() * cnt, rtol=0, atol=1e-9)
+    right = torch.zeros(1, 32, H, W, device="cuda", dtype=torch.float64)
+    for d in range(D):
+        right[..., d:] += fR.double()[..., : W - d]
+    assert torch.allclose(vol[:, 32:].sum(2), right, rtol=0, atol=1e-9)
+
+
+def test_north_star_path_full_size():
+    """one 384x1248 pair through the CUDA path vs the CPU oracle (fp32 reference arithmetic)."""
+    from dsmnet_b200.psmnet import PSMNetHotPath
+    from dsmnet_b200.conv3d import conv_timeouts
+    torch.manual_seed(4)
+    maxdisp, HI, WI = 192, 384, 1248
+    # features with stereo structure: the right map is the left map shifted by a smooth disparity
+    fL = torch.randn(1, 32, H, W)
+    gt4 = (10 + 20 * torch.linspace(0, 1, W)).view(1, 1, 1, W).expand(1, 1, H, W)          # 1/4-res disparity
+    grid_x = (torch.arange(W).view(1, 1, W) + gt4[:, 0]).clamp(0, W - 1)
+    gx = grid_x / (W - 1) * 2 - 1
+    gy = (torch.arange(H).view(1, H, 1).expand(1, H, W) / (H - 1)) * 2 - 1
+    fR = F.grid_sample(fL, torch.stack([gx, gy], -1), mode="bilinear", padding_mode="border", align_corners=True)
+    gt = F.interpolate(gt4 * 4, size=(HI, WI), mode="bilinear", align_corners=True)[:, 0]
+    cost = O.concat_volume(fL, fR, maxdisp // 4, "psm")
+    params = O.psmnet_random_params(seed=21, calibrate_on=cost)
+    ref = O.psmnet_hotpath(params, fL, fR, maxdisp, (HI, WI))
+    m = PSMNetHotPath(maxdisp)
+    m.load_state_dict(params, strict=False)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        preds = m(fL.cuda(), fR.cuda(), (HI, WI))
+    torch.cuda.synchronize()
+    assert conv_timeouts() == 0
+    for name, mine, r in zip(("pred3", "pred2", "pred1"), preds, ref):
+        mine = mine.cpu()
+        assert mine.shape == (1, HI, WI) and bool(torch.isfinite(mine).all())
+        epe_ref = float((r - gt).abs().mean()); epe_mine = float((mine - gt).abs().mean())
+        d = float((mine - r).abs().mean())
+        print("%s: EPE ref %.4f ours %.4f (delta %.5f px); mean |ours - ref| %.4f px" % (name, epe_ref, epe_mine, abs(epe_mine - epe_ref), d))
+        assert abs(epe_mine - epe_ref) < 0.01          # north_star: mean EPE delta < 0.01 px
+        assert d < 0.25                                # bf16 operand format error on this random-weight net
