@@ -208,9 +208,11 @@ def test_imwrap_iresnet_size():
     x0, y0, row, col = _indices(disp, 540, 960, (0, 0), 1, False)
     _, rx0, ry0 = O.imwrap_closed_form(src[:, :1].numpy(), disp.numpy(), row.numpy(), col.numpy(), False, 5e-5)
     assert np.array_equal(x0, rx0) and np.array_equal(y0, ry0)
-    # zero disparity is the identity (+delt)
+    # zero disparity is the identity up to the reference's own normalise/un-normalise round trip
+    # (the fp32 sampling coordinate misses the integer by <= 2e-6*W)
     ident = imwrap_BCHW(dev(src), torch.zeros(1, 1, 540, 960, device="cuda"), delt=0.0)
-    assert float((ident.cpu() - src).abs().max()) < 1e-5
+    assert float((ident.cpu() - src).abs().max()) < 3e-4
+    assert float((ident.cpu() - O.imwrap(src, torch.zeros(1, 1, 540, 960), delt=0.0)).abs().max()) < 1e-5
 
 
 def test_imwrap_rng_stream():
