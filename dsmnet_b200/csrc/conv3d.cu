@@ -40,8 +40,8 @@ struct ConvGeom {
     int nchunks;             // Cin / KC
     long long P;             // rows of the flattened padded input
     int tiles_w, tiles_h;    // BOX tiling of the output plane (16 x 8 patches)
+    int ntiles, mtiles;      // total tiles (all classes); FLAT/SHIFT: 128-row tiles per class
     int desc_variant;        // 0: base_offset 0; 1: base_offset from address bits [7,10)
-    int debug_level;         // 0 = normal; 1..3 stop after: setup | TMA | MMA (bring-up bisection)
     int cls_begin[9];
     int a_off[27];           // FLAT/SHIFT: row offset of the tap; BOX: map | ow<<4 | oh<<5 | od<<6
     int w_row[27];           // first row of the tap in the packed weights
@@ -49,18 +49,6 @@ struct ConvGeom {
 
 __device__ int g_conv_timeouts = 0;
 __device__ int* g_conv_progress = nullptr;   // bring-up only: host-mapped int[4], one slot per warp of CTA 1
-
-__device__ __forceinline__ void mark(int code) {
-#ifdef DSM_CONV_TRACE
-    int* p = g_conv_progress;
-    if (p && blockIdx.x == 1 && blockIdx.y == 0 && (threadIdx.x & 31) == 0) {
-        *reinterpret_cast<volatile int*>(p + (threadIdx.x >> 5)) = code;
-        __threadfence_system();
-    }
-#else
-    (void)code;
-#endif
-}
 
 // ptxas lowers tcgen05.wait::ld to nothing and relies on the register scoreboard of the first
 // consumer.  A thread that never reads its tcgen05.ld result (an invalid rim voxel) would then run
@@ -104,15 +92,57 @@ struct Cfg {
     static constexpr int B_TILE = NP * ROWB;
     static constexpr int B_BYTES = ((NB * B_TILE + 1023) / 1024) * 1024;
     static constexpr int STAGE = A_BYTES + B_BYTES;
-    static constexpr int S_RAW = (96 * 1024) / STAGE;
-    static constexpr int STAGES = S_RAW > 6 ? 6 : (S_RAW < 2 ? 2 : S_RAW);
+    // two CTAs per SM when a useful ring (>= 4 stages) fits in ~100 KB, otherwise one CTA with up to 200 KB
+    static constexpr int CTAS_PER_SM = (4 * STAGE <= 100 * 1024) ? 2 : 1;
+    static constexpr int BUDGET = (CTAS_PER_SM == 2 ? 100 : 200) * 1024;
+    static constexpr int S_RAW = BUDGET / STAGE;
+    static constexpr int STAGES = S_RAW > 8 ? 8 : (S_RAW < 2 ? 2 : S_RAW);
     static constexpr int TX_BYTES = A_ROWS * ROWB + NB * B_TILE;
-    static constexpr int TMEM_COLS = NP < 32 ? 32 : NP;
-    static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * NP * 4;
+    static constexpr int ACC_COLS = NP < 32 ? 32 : NP;        // TMEM columns of one accumulator
+    static constexpr int NUM_ACC = 2;                         // double-buffered: MMA of tile i+1 overlaps epilogue of tile i
+    static constexpr int TMEM_COLS = NUM_ACC * ACC_COLS;      // 64 / 128 / 256: a power of two
+    static constexpr int BAR_BYTES = 512;
+    static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + BAR_BYTES + 2 * NP * 4;
+    static constexpr int THREADS = 192;                       // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
 };
 
+// Which tile is it, and does it produce anything?
+struct TileInfo {
+    long long p0;      // FLAT/SHIFT: first row of the tile in the flattened padded input
+    int cls;           // transposed conv: output parity class
+    int b, d, h, w;    // BOX: batch, output plane, 8-row and 16-column patch index
+    bool skip;
+};
+
+template <int MODE>
+__device__ __forceinline__ TileInfo decode_tile(const ConvGeom& g, int t, long long plane, long long vol, int Dp) {
+    TileInfo ti;
+    ti.p0 = 0; ti.cls = 0; ti.b = ti.d = ti.h = ti.w = 0; ti.skip = false;
+    if (MODE == MODE_BOX) {
+        ti.w = t % g.tiles_w; t /= g.tiles_w;
+        ti.h = t % g.tiles_h; t /= g.tiles_h;
+        ti.d = t % g.Do;      ti.b = t / g.Do;
+    } else {
+        ti.cls = t / g.mtiles;
+        ti.p0 = (long long)(t - ti.cls * g.mtiles) * 128;
+        // tiles that lie completely inside a rim plane (d' = 0 or D+1) produce nothing
+        const long long pl = min(ti.p0 + 127, g.P - 1);
+        const long long b0 = ti.p0 / vol, b1 = pl / vol;
+        const int dp0 = (int)((ti.p0 - b0 * vol) / plane), dp1 = (int)((pl - b1 * vol) / plane);
+        ti.skip = (b0 == b1 && dp0 == dp1 && (dp0 == 0 || dp0 == Dp - 1));
+    }
+    return ti;
+}
+
+// Persistent, warp-specialised implicit-GEMM kernel.  grid = #SMs x CTAS_PER_SM (or fewer tiles),
+// every CTA walks tiles blockIdx.x, +gridDim.x, ...:
+//   warp 0 (one lane) : TMA producer — keeps the smem ring full, running ahead across tiles
+//   warp 1 (one lane) : tcgen05.mma issuer — accumulates a tile into one of two TMEM buffers
+//   warps 2..5        : epilogue — tcgen05.ld the finished buffer (lane quadrant = warp % 4),
+//                       hand it back, then affine + residual + ReLU + store while the next tile's
+//                       MMAs already run into the other buffer.
 template <int KC, int NP, int MODE>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(192)
 conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvGeom g,
                     const float* __restrict__ scale, const float* __restrict__ shift,
                     const void* __restrict__ residual, void* __restrict__ y) {
@@ -121,37 +151,21 @@ conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
     const int Dp = g.Di + 2, Hp = g.Hi + 2, Wp = g.Wi + 2;
     const long long plane = (long long)Hp * Wp, vol = plane * Dp;
 
-    // ---- which tile ---------------------------------------------------------------------
-    long long p0 = 0;
-    int cls = 0, bx_b = 0, bx_d = 0, bx_h = 0, bx_w = 0;
-    if (MODE == MODE_BOX) {
-        int t = blockIdx.x;
-        bx_w = t % g.tiles_w; t /= g.tiles_w;
-        bx_h = t % g.tiles_h; t /= g.tiles_h;
-        bx_d = t % g.Do;      bx_b = t / g.Do;
-    } else {
-        p0 = (long long)blockIdx.x * 128;
-        cls = blockIdx.y;
-        // tiles that lie completely inside a rim plane (d' = 0 or D+1) produce nothing
-        const long long pl = min(p0 + 127, g.P - 1);
-        const long long b0 = p0 / vol, b1 = pl / vol;
-        const int dp0 = (int)((p0 - b0 * vol) / plane), dp1 = (int)((pl - b1 * vol) / plane);
-        if (b0 == b1 && dp0 == dp1 && (dp0 == 0 || dp0 == Dp - 1)) return;
-    }
-
     // ---- shared memory carve-up ---------------------------------------------------------
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = ptx::smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - raw);
-    const uint32_t bars = base + C::STAGES * C::STAGE;          // full[S], empty[S], accum, tmem slot
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + C::STAGES * C::STAGE + 8 * (2 * C::STAGES + 1));
-    const uint32_t scratch_smem = bars + 8u * (2 * C::STAGES + 1) + 8u;   // unused word after the TMEM slot
-    float* s_scale = reinterpret_cast<float*>(base_ptr + C::STAGES * C::STAGE + 256);
-    float* s_shift = s_scale + NP;
+    const uint32_t bars = base + C::STAGES * C::STAGE;     // full[S], empty[S], tmem_full[2], tmem_empty[2], slot, scratch
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
-    const uint32_t accum_bar = bars + 8u * (2 * C::STAGES);
+    auto tfull_bar = [&](int a) { return bars + 8u * (2 * C::STAGES + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (2 * C::STAGES + C::NUM_ACC + a); };
+    constexpr int NBARS = 2 * C::STAGES + 2 * C::NUM_ACC;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + C::STAGES * C::STAGE + 8 * NBARS);
+    const uint32_t scratch_smem = bars + 8u * NBARS + 8u;
+    float* s_scale = reinterpret_cast<float*>(base_ptr + C::STAGES * C::STAGE + C::BAR_BYTES);
+    float* s_shift = s_scale + NP;
 
     if (tid < NP) {
         s_scale[tid] = scale ? __ldg(scale + tid) : 1.f;
@@ -161,7 +175,7 @@ conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
         ptx::prefetch_tensormap(&maps.w);
         ptx::prefetch_tensormap(&maps.a[0]);
         for (int s = 0; s < C::STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
-        ptx::mbar_init(accum_bar, 1);
+        for (int a = 0; a < C::NUM_ACC; ++a) { ptx::mbar_init(tfull_bar(a), 1); ptx::mbar_init(tempty_bar(a), 4); }
         ptx::fence_mbar_init();
     }
     if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), C::TMEM_COLS);
@@ -169,170 +183,176 @@ conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    mark(10);
-
-    const int tap0 = g.cls_begin[cls];
-    const int ntaps = g.cls_begin[cls + 1] - tap0;
-    const int ngroups = (MODE == MODE_SHIFT) ? ntaps / 3 : ntaps;
-    int n_it = ngroups * g.nchunks;
-    if (g.debug_level == 1) n_it = 0;
-    if (g.debug_level == 2 && n_it > C::STAGES) n_it = C::STAGES;   // no slot reuse: producer never waits
 
     if (warp == 0) {
-      if (lane == 0) {
-        // ================= TMA producer =================
-        for (int it = 0; it < n_it; ++it) {
-            const int s = it % C::STAGES;
-            const uint32_t ph = (uint32_t)(it / C::STAGES) & 1u;
-            wait_bar(empty_bar(s), ph ^ 1u);
-            const int grp = it / g.nchunks, kc = it - grp * g.nchunks;
-            const int t = tap0 + ((MODE == MODE_SHIFT) ? 3 * grp : grp);
-            const uint32_t sa = base + s * C::STAGE, sb = sa + C::A_BYTES;
-            ptx::mbar_arrive_expect_tx(full_bar(s), C::TX_BYTES);
-            if (MODE == MODE_BOX) {
-                const int code = g.a_off[t];
-                ptx::tma_load_5d(sa, &maps.a[code & 7], full_bar(s), kc * KC,
-                                 bx_w * 16 + ((code >> 4) & 1), bx_h * 8 + ((code >> 5) & 1),
-                                 bx_d + ((code >> 6) & 1), bx_b);
-            } else {
-                ptx::tma_load_2d(sa, &maps.a[0], full_bar(s), kc * KC, (int)(p0 + g.a_off[t]));
-            }
+        if (lane == 0) {
+            // ================= TMA producer =================
+            int it = 0;                                    // ring position, runs on across tiles
+            for (int t = blockIdx.x; t < g.ntiles; t += gridDim.x) {
+                const TileInfo ti = decode_tile<MODE>(g, t, plane, vol, Dp);
+                if (ti.skip) continue;
+                const int tap0 = g.cls_begin[ti.cls];
+                const int ntaps = g.cls_begin[ti.cls + 1] - tap0;
+                const int ngroups = (MODE == MODE_SHIFT) ? ntaps / 3 : ntaps;
+                for (int grp = 0; grp < ngroups; ++grp) {
+                    const int tp = tap0 + ((MODE == MODE_SHIFT) ? 3 * grp : grp);
+                    for (int kc = 0; kc < g.nchunks; ++kc, ++it) {
+                        const int s = it % C::STAGES;
+                        const uint32_t ph = (uint32_t)(it / C::STAGES) & 1u;
+                        wait_bar(empty_bar(s), ph ^ 1u);
+                        const uint32_t sa = base + s * C::STAGE, sb = sa + C::A_BYTES;
+                        ptx::mbar_arrive_expect_tx(full_bar(s), C::TX_BYTES);
+                        if (MODE == MODE_BOX) {
+                            const int code = g.a_off[tp];
+                            ptx::tma_load_5d(sa, &maps.a[code & 7], full_bar(s), kc * KC,
+                                             ti.w * 16 + ((code >> 4) & 1), ti.h * 8 + ((code >> 5) & 1),
+                                             ti.d + ((code >> 6) & 1), ti.b);
+                        } else {
+                            ptx::tma_load_2d(sa, &maps.a[0], full_bar(s), kc * KC, (int)(ti.p0 + g.a_off[tp]));
+                        }
 #pragma unroll
-            for (int j = 0; j < C::NB; ++j)
-                ptx::tma_load_2d(sb + j * C::B_TILE, &maps.w, full_bar(s), kc * KC, g.w_row[t + j]);
-        }
-      }
-    } else if (warp == 1) {
-      if (lane == 0) {
-        // ================= MMA issuer =================
-        constexpr uint32_t idesc = ptx::make_idesc_bf16(NP);
-        for (int it = 0; it < n_it; ++it) {
-            const int s = it % C::STAGES;
-            const uint32_t ph = (uint32_t)(it / C::STAGES) & 1u;
-            wait_bar(full_bar(s), ph);
-            ptx::tc_fence_after();
-            if (g.debug_level == 2) continue;
-            const uint32_t sa = base + s * C::STAGE, sb = sa + C::A_BYTES;
-#pragma unroll
-            for (int j = 0; j < C::NB; ++j) {
-#pragma unroll
-                for (int k = 0; k < KC / 16; ++k) {
-                    const uint32_t a_addr = sa + j * C::ROWB + k * 32;
-                    const uint32_t b_addr = sb + j * C::B_TILE + k * 32;
-                    const uint32_t abo = g.desc_variant ? ((a_addr >> 7) & 7u) : 0u;
-                    const uint64_t ad = ptx::make_kmajor_desc(a_addr, C::ROWB, abo);
-                    const uint64_t bd = ptx::make_kmajor_desc(b_addr, C::ROWB, 0u);
-                    ptx::umma_bf16(tmem, ad, bd, idesc, (it | j | k) ? 1u : 0u);
+                        for (int j = 0; j < C::NB; ++j)
+                            ptx::tma_load_2d(sb + j * C::B_TILE, &maps.w, full_bar(s), kc * KC, g.w_row[tp + j]);
+                    }
                 }
             }
-            ptx::umma_commit(empty_bar(s));      // frees the stage when these MMAs retire
         }
-        if (g.debug_level == 1 || g.debug_level == 2) ptx::mbar_arrive(accum_bar);
-        else ptx::umma_commit(accum_bar);        // accumulator complete
-      }
-    }
-    __syncwarp();
-    mark(20);
-
-    // ================= epilogue (all 4 warps, one TMEM lane = one voxel per thread) =======
-    wait_bar(accum_bar, 0u);
-    __syncwarp();
-    ptx::tc_fence_after();
-    mark(30);
-
-    if (g.debug_level >= 1 && g.debug_level <= 3) {   // bring-up: skip the TMEM read-back
-        ptx::tc_fence_before();
-        __syncthreads();
-        if (warp == 1) ptx::tmem_dealloc(tmem, C::TMEM_COLS);
-        return;
-    }
-    const int r = tid;                           // row of the tile == TMEM lane
-    bool valid = false;
-    int ob = 0, od = 0, oh = 0, ow = 0;
-    if (MODE == MODE_BOX) {
-        ob = bx_b; od = bx_d; oh = bx_h * 8 + (r >> 4); ow = bx_w * 16 + (r & 15);
-        valid = (oh < g.Ho) && (ow < g.Wo);
-    } else {
-        const long long p = p0 + r;
-        if (p < g.P) {
-            const long long b = p / vol, rem = p - b * vol;
-            const int dp = (int)(rem / plane);
-            const int rem2 = (int)(rem - (long long)dp * plane);
-            const int hp = rem2 / Wp, wp = rem2 - hp * Wp;
-            if (dp >= 1 && dp <= g.Di && hp >= 1 && hp <= g.Hi && wp >= 1 && wp <= g.Wi) {
-                ob = (int)b;
-                if (g.transposed) {
-                    od = 2 * (dp - 1) + ((cls >> 2) & 1); oh = 2 * (hp - 1) + ((cls >> 1) & 1); ow = 2 * (wp - 1) + (cls & 1);
-                } else { od = dp - 1; oh = hp - 1; ow = wp - 1; }
-                valid = (od < g.Do) && (oh < g.Ho) && (ow < g.Wo);
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ================= MMA issuer =================
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(NP);
+            int it = 0, tcount = 0;
+            for (int t = blockIdx.x; t < g.ntiles; t += gridDim.x) {
+                const TileInfo ti = decode_tile<MODE>(g, t, plane, vol, Dp);
+                if (ti.skip) continue;
+                const int ntaps = g.cls_begin[ti.cls + 1] - g.cls_begin[ti.cls];
+                const int n_it = ((MODE == MODE_SHIFT) ? ntaps / 3 : ntaps) * g.nchunks;
+                const int acc = tcount & 1;
+                const uint32_t acc_ph = (uint32_t)(tcount >> 1) & 1u;
+                wait_bar(tempty_bar(acc), acc_ph ^ 1u);    // epilogue has drained this buffer
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem + acc * C::ACC_COLS;
+                for (int i = 0; i < n_it; ++i, ++it) {
+                    const int s = it % C::STAGES;
+                    const uint32_t ph = (uint32_t)(it / C::STAGES) & 1u;
+                    wait_bar(full_bar(s), ph);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = base + s * C::STAGE, sb = sa + C::A_BYTES;
+#pragma unroll
+                    for (int j = 0; j < C::NB; ++j) {
+#pragma unroll
+                        for (int k = 0; k < KC / 16; ++k) {
+                            const uint64_t ad = ptx::make_kmajor_desc(sa + j * C::ROWB + k * 32, C::ROWB, 0u);
+                            const uint64_t bd = ptx::make_kmajor_desc(sb + j * C::B_TILE + k * 32, C::ROWB, 0u);
+                            ptx::umma_bf16(d_tmem, ad, bd, idesc, (i | j | k) ? 1u : 0u);
+                        }
+                    }
+                    ptx::umma_commit(empty_bar(s));        // frees the stage when these MMAs retire
+                }
+                ptx::umma_commit(tfull_bar(acc));          // accumulator complete
+                ++tcount;
             }
         }
-    }
-    uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
-    if (g.debug_level == 6) { uint32_t hw; asm volatile("mov.u32 %0, %%warpid;" : "=r"(hw)); taddr = tmem + (((hw & 3u) * 32u) << 16); }
-    mark(40);
-
-    if (g.y_f32) {
-        // single output channel (classifier / GC-Net l37): fp32, unpadded [B][Do][Ho][Wo]
-        uint32_t v[16];
-        ptx::tmem_ld16(taddr, v);
-        ptx::tc_wait_ld();
-        consume_tmem_load(v[0], scratch_smem);
-        if (valid) {
-            const size_t o = (((size_t)ob * g.Do + od) * g.Ho + oh) * g.Wo + ow;
-            float a = fmaf(__uint_as_float(v[0]), s_scale[0], s_shift[0]);
-            if (residual) a += __ldg(reinterpret_cast<const float*>(residual) + o);
-            if (g.relu) a = fmaxf(a, 0.f);
-            reinterpret_cast<float*>(y)[o] = a;
-        }
     } else {
-        constexpr int CH = NP >= 32 ? 32 : 16;
-        const size_t o = ((((size_t)ob * (g.Do + 2) + od + 1) * (g.Ho + 2) + oh + 1) * (g.Wo + 2) + ow + 1) * (size_t)g.Cout;
-        const uint4* res = residual ? reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(residual) + o) : nullptr;
-        uint4* out = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y) + o);
-#pragma unroll
-        for (int c0 = 0; c0 < NP; c0 += CH) {
-            uint32_t v[CH];
-            if (g.debug_level == 4) {
-#pragma unroll
-                for (int i = 0; i < CH; ++i) v[i] = 0u;
+        // ================= epilogue warps (one TMEM lane = one voxel per thread) =================
+        const int q = warp & 3;                            // TMEM lane quadrant this warp may read
+        const int r = q * 32 + lane;                       // row of the tile
+        int tcount = 0;
+        for (int t = blockIdx.x; t < g.ntiles; t += gridDim.x) {
+            const TileInfo ti = decode_tile<MODE>(g, t, plane, vol, Dp);
+            if (ti.skip) continue;
+            // ---- where does this row go? ----
+            bool valid = false;
+            int ob = 0, od = 0, oh = 0, ow = 0;
+            if (MODE == MODE_BOX) {
+                ob = ti.b; od = ti.d; oh = ti.h * 8 + (r >> 4); ow = ti.w * 16 + (r & 15);
+                valid = (oh < g.Ho) && (ow < g.Wo);
             } else {
-                if (CH == 32) ptx::tmem_ld32(taddr + c0, v); else ptx::tmem_ld16(taddr + c0, v);
+                const long long p = ti.p0 + r;
+                if (p < g.P) {
+                    const long long b = p / vol, rem = p - b * vol;
+                    const int dp = (int)(rem / plane);
+                    const int rem2 = (int)(rem - (long long)dp * plane);
+                    const int hp = rem2 / Wp, wp = rem2 - hp * Wp;
+                    if (dp >= 1 && dp <= g.Di && hp >= 1 && hp <= g.Hi && wp >= 1 && wp <= g.Wi) {
+                        ob = (int)b;
+                        if (g.transposed) {
+                            od = 2 * (dp - 1) + ((ti.cls >> 2) & 1); oh = 2 * (hp - 1) + ((ti.cls >> 1) & 1); ow = 2 * (wp - 1) + (ti.cls & 1);
+                        } else { od = dp - 1; oh = hp - 1; ow = wp - 1; }
+                        valid = (od < g.Do) && (oh < g.Ho) && (ow < g.Wo);
+                    }
+                }
+            }
+            const int acc = tcount & 1;
+            const uint32_t acc_ph = (uint32_t)(tcount >> 1) & 1u;
+            ++tcount;
+            wait_bar(tfull_bar(acc), acc_ph);
+            __syncwarp();
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + acc * C::ACC_COLS;
+
+            if (g.y_f32) {
+                // single output channel (classifier / GC-Net l37): fp32, unpadded [B][Do][Ho][Wo]
+                uint32_t v[16];
+                ptx::tmem_ld16(taddr, v);
                 ptx::tc_wait_ld();
                 consume_tmem_load(v[0], scratch_smem);
-            }
-            mark(50 + c0 / CH);
-            if (valid && g.debug_level != 5) {
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+                if (valid) {
+                    const size_t o = (((size_t)ob * g.Do + od) * g.Ho + oh) * g.Wo + ow;
+                    float a = fmaf(__uint_as_float(v[0]), s_scale[0], s_shift[0]);
+                    if (residual) a += __ldg(reinterpret_cast<const float*>(residual) + o);
+                    if (g.relu) a = fmaxf(a, 0.f);
+                    reinterpret_cast<float*>(y)[o] = a;
+                }
+            } else {
+                constexpr int CH = NP >= 32 ? 32 : 16;
+                const size_t o = ((((size_t)ob * (g.Do + 2) + od + 1) * (g.Ho + 2) + oh + 1) * (g.Wo + 2) + ow + 1) * (size_t)g.Cout;
+                const uint4* res = residual ? reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(residual) + o) : nullptr;
+                uint4* out = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y) + o);
 #pragma unroll
-                for (int q = 0; q < CH / 8; ++q) {
-                    float f[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        f[i] = fmaf(__uint_as_float(v[q * 8 + i]), s_scale[c0 + q * 8 + i], s_shift[c0 + q * 8 + i]);
-                    if (res) {
-                        const uint4 rv = __ldg(res + (c0 / 8) + q);
-                        f[0] += bf16_lo(rv.x); f[1] += bf16_hi(rv.x); f[2] += bf16_lo(rv.y); f[3] += bf16_hi(rv.y);
-                        f[4] += bf16_lo(rv.z); f[5] += bf16_hi(rv.z); f[6] += bf16_lo(rv.w); f[7] += bf16_hi(rv.w);
+                for (int c0 = 0; c0 < NP; c0 += CH) {
+                    uint32_t v[CH];
+                    if (CH == 32) ptx::tmem_ld32(taddr + c0, v); else ptx::tmem_ld16(taddr + c0, v);
+                    ptx::tc_wait_ld();
+                    consume_tmem_load(v[0], scratch_smem);
+                    if (c0 + CH >= NP) {                   // last chunk is in registers: hand the buffer back
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
                     }
-                    if (g.relu) {
+                    if (valid) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+                        for (int qq = 0; qq < CH / 8; ++qq) {
+                            float f[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                f[i] = fmaf(__uint_as_float(v[qq * 8 + i]), s_scale[c0 + qq * 8 + i], s_shift[c0 + qq * 8 + i]);
+                            if (res) {
+                                const uint4 rv = __ldg(res + (c0 / 8) + qq);
+                                f[0] += bf16_lo(rv.x); f[1] += bf16_hi(rv.x); f[2] += bf16_lo(rv.y); f[3] += bf16_hi(rv.y);
+                                f[4] += bf16_lo(rv.z); f[5] += bf16_hi(rv.z); f[6] += bf16_lo(rv.w); f[7] += bf16_hi(rv.w);
+                            }
+                            if (g.relu) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+                            }
+                            uint4 ov;
+                            ov.x = pack_bf16x2(f[0], f[1]); ov.y = pack_bf16x2(f[2], f[3]);
+                            ov.z = pack_bf16x2(f[4], f[5]); ov.w = pack_bf16x2(f[6], f[7]);
+                            out[(c0 / 8) + qq] = ov;
+                        }
                     }
-                    uint4 ov;
-                    ov.x = pack_bf16x2(f[0], f[1]); ov.y = pack_bf16x2(f[2], f[3]);
-                    ov.z = pack_bf16x2(f[4], f[5]); ov.w = pack_bf16x2(f[6], f[7]);
-                    out[(c0 / 8) + q] = ov;
                 }
             }
         }
     }
 
-    mark(60);
     ptx::tc_fence_before();
     __syncthreads();
-    mark(70);
     if (warp == 1) ptx::tmem_dealloc(tmem, C::TMEM_COLS);
-    mark(80);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -372,7 +392,11 @@ int launch_cfg(const ConvMaps& maps, const ConvGeom& g, dim3 grid, const float* 
     auto kern = conv3d_igemm_kernel<KC, NP, MODE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) return (int)e;
-    kern<<<grid, 128, C::SMEM, st>>>(maps, g, scale, shift, residual, y);
+    int nsm = DSM_NUM_SMS_B200, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    int nblocks = nsm * C::CTAS_PER_SM;
+    if (nblocks > (int)grid.x) nblocks = (int)grid.x;
+    kern<<<nblocks, C::THREADS, C::SMEM, st>>>(maps, g, scale, shift, residual, y);
     return dsm_launch_status();
 }
 
@@ -416,7 +440,7 @@ int conv3d_dispatch(const void* x, const void* w, const float* scale, const floa
     memset(&g, 0, sizeof(g));
     g.B = B; g.Di = D; g.Hi = H; g.Wi = W; g.Do = Do; g.Ho = Ho; g.Wo = Wo;
     g.Cout = Cout; g.transposed = transposed; g.relu = relu; g.y_f32 = (y_dtype == DSM_F32);
-    g.nchunks = Cin / KC; g.P = P; g.desc_variant = variant & 1; g.debug_level = (variant >> 8) & 7;
+    g.nchunks = Cin / KC; g.P = P; g.desc_variant = variant & 1;
     const int row_bytes = KC * 2;
     // bit1 of `variant` SET selects the per-tap kernel (MODE_FLAT); the default for stride-1 convolutions is the
     // row-shifted-descriptor kernel (validated bit-identical on B200), except N=128 whose stage would not fit twice
@@ -450,6 +474,7 @@ int conv3d_dispatch(const void* x, const void* w, const float* scale, const floa
         g.tiles_w = dsm_ceil_div(Wo, 16); g.tiles_h = dsm_ceil_div(Ho, 8);
         const long long nt = (long long)B * Do * g.tiles_h * g.tiles_w;
         if (nt > 0x7fffffffLL) return DSM_EUNSUPPORTED;
+        g.ntiles = (int)nt; g.mtiles = (int)nt;
         grid = dim3((unsigned)nt, 1, 1);
     } else {
         cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)P};
@@ -481,7 +506,9 @@ int conv3d_dispatch(const void* x, const void* w, const float* scale, const floa
             }
             g.cls_begin[8] = n;   // 27
         }
-        grid = dim3((unsigned)dsm_ceil_div_ll(P, 128), ncls, 1);
+        g.mtiles = (int)dsm_ceil_div_ll(P, 128);
+        g.ntiles = g.mtiles * ncls;
+        grid = dim3((unsigned)g.ntiles, 1, 1);
     }
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == MODE_BOX)   return launch_mode<MODE_BOX>(KC, NP, maps, g, grid, scale, shift, residual, y, st);

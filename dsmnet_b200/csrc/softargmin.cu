@@ -130,10 +130,24 @@ __device__ __forceinline__ void src_index(int dst, float scale, int in_size, int
     i1 = min(i0 + 1, in_size - 1);
 }
 
+// MAXDL: the low-res depth extent is kept in registers (template bound), D-axis source index and
+// weight come from a per-CTA shared table.  Since a linear interpolation never exceeds its end
+// points, max_d of the upsampled column <= max_dl of the bilinearly interpolated low-res column:
+// that maximum is known before the D loop, so the softmax is a single pass with one ex2 per d.
+template <int MAXDL>
 __global__ void __launch_bounds__(128)
 upsample_softargmin_kernel(const float* __restrict__ cost, float* __restrict__ disp,
                            int Dl, int Hl, int Wl, int D, int H, int W,
                            float sd, float sh, float sw, int align_corners) {
+    extern __shared__ __align__(8) unsigned char smem_raw[];
+    int* s_d0 = reinterpret_cast<int*>(smem_raw);            // [D]
+    float* s_l1 = reinterpret_cast<float*>(s_d0 + D);        // [D]
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        int d0, d1; float l1;
+        src_index(d, sd, Dl, align_corners, d0, d1, l1);
+        s_d0[d] = d0; s_l1[d] = (d1 == d0) ? 0.f : l1;       // clamped top: both taps are the same plane
+    }
+    __syncthreads();
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y, b = blockIdx.z;
     if (x >= W) return;
@@ -144,27 +158,36 @@ upsample_softargmin_kernel(const float* __restrict__ cost, float* __restrict__ d
     const float* base = cost + (size_t)b * Dl * Hl * Wl;
     const size_t pl = (size_t)Hl * Wl;
     const int o00 = h0 * Wl + w0, o01 = h0 * Wl + w1, o10 = h1 * Wl + w0, o11 = h1 * Wl + w1;
-    auto plane = [&](int dl) -> float {
-        const float* p = base + (size_t)dl * pl;
-        return lh0 * (lw0 * __ldg(p + o00) + lw1 * __ldg(p + o01)) + lh1 * (lw0 * __ldg(p + o10) + lw1 * __ldg(p + o11));
-    };
-    int cur0 = -1, cur1 = -1;
-    float c0 = 0.f, c1 = 0.f;
-    Online o; o.init();
-    for (int dd = 0; dd < D; dd += DCH) {
-        const int n = min(DCH, D - dd);
-        float v[DCH];
+    float c[MAXDL + 1];
+    float m = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < DCH; ++i) if (i < n) {
-            int d0, d1; float ld1;
-            src_index(dd + i, sd, Dl, align_corners, d0, d1, ld1);
-            if (d0 != cur0) { if (d0 == cur1) c0 = c1; else c0 = plane(d0); cur0 = d0; }
-            if (d1 != cur1) { c1 = (d1 == cur0) ? c0 : plane(d1); cur1 = d1; }
-            v[i] = (1.f - ld1) * c0 + ld1 * c1;
-        }
-        o.chunk(v, n, dd);
+    for (int dl = 0; dl < MAXDL; ++dl) {
+        if (dl < Dl) {
+            const float* p = base + (size_t)dl * pl;
+            c[dl] = lh0 * (lw0 * __ldg(p + o00) + lw1 * __ldg(p + o01)) + lh1 * (lw0 * __ldg(p + o10) + lw1 * __ldg(p + o11));
+            m = fmaxf(m, c[dl]);
+        } else c[dl] = 0.f;
     }
-    disp[((size_t)b * H + y) * W + x] = o.t / o.s;
+    c[MAXDL] = 0.f;
+    constexpr float LOG2E = 1.4426950408889634f;
+    const float ml = m * LOG2E;
+    float s = 0.f, t = 0.f;
+    // walk the low-res intervals; the table tells which output planes fall into each
+    int d = 0;
+#pragma unroll
+    for (int dl = 0; dl < MAXDL; ++dl) {
+        if (dl < Dl) {
+            const float a0 = c[dl], a1 = c[dl + 1];
+            while (d < D && s_d0[d] == dl) {
+                const float l1 = s_l1[d];
+                const float v = (1.f - l1) * a0 + l1 * a1;
+                const float e = exp2f(fmaf(v, LOG2E, -ml));
+                s += e; t = fmaf((float)d, e, t);
+                ++d;
+            }
+        }
+    }
+    disp[((size_t)b * H + y) * W + x] = t / s;
 }
 
 }  // namespace
@@ -217,7 +240,14 @@ extern "C" int dsm_upsample_softargmin_fwd(const float* cost_lr, float* disp, in
         if (align_corners) return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
         return (float)in / (float)out;
     };
-    upsample_softargmin_kernel<<<dim3(dsm_ceil_div(W, 128), H, B), 128, 0, (cudaStream_t)stream>>>(
-        cost_lr, disp, Dl, Hl, Wl, D, H, W, scale(Dl, D), scale(Hl, H), scale(Wl, W), align_corners);
+    const size_t smem = (size_t)D * (sizeof(int) + sizeof(float));
+    if (smem > 48 * 1024) return DSM_EUNSUPPORTED;
+    const dim3 grid(dsm_ceil_div(W, 128), H, B);
+    cudaStream_t st = (cudaStream_t)stream;
+#define DSM_UPS(MAXDL) upsample_softargmin_kernel<MAXDL><<<grid, 128, smem, st>>>( \
+        cost_lr, disp, Dl, Hl, Wl, D, H, W, scale(Dl, D), scale(Hl, H), scale(Wl, W), align_corners)
+    if (Dl <= 16) DSM_UPS(16); else if (Dl <= 48) DSM_UPS(48); else if (Dl <= 96) DSM_UPS(96);
+    else return DSM_EUNSUPPORTED;
+#undef DSM_UPS
     return dsm_launch_status();
 }
