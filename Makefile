@@ -7,7 +7,7 @@ HDRS      := $(wildcard dsmnet_b200/csrc/*.cuh) include/dsmnet_b200.h
 OBJ       := $(patsubst dsmnet_b200/csrc/%.cu,build/%.o,$(CSRC))
 LIB       := dsmnet_b200/libdsmnet_b200.so
 
-all: $(LIB) tests/cuda/conv3d_selftest
+all: $(LIB) tests/cuda/conv3d_selftest tests/cuda/mma_bench
 
 build/%.o: dsmnet_b200/csrc/%.cu $(HDRS)
 	@mkdir -p build
@@ -19,7 +19,10 @@ $(LIB): $(OBJ)
 tests/cuda/conv3d_selftest: tests/cuda/conv3d_selftest.cu $(LIB)
 	$(NVCC) $(ARCH) -lineinfo -O2 -std=c++17 -o $@ $< -Ldsmnet_b200 -ldsmnet_b200 -Xlinker -rpath -Xlinker '$$ORIGIN/../../dsmnet_b200'
 
+tests/cuda/mma_bench: tests/cuda/mma_bench.cu dsmnet_b200/csrc/ptx.cuh
+	$(NVCC) $(ARCH) -lineinfo -O2 -std=c++17 -o $@ $<
+
 clean:
-	rm -rf build $(LIB) tests/cuda/conv3d_selftest
+	rm -rf build $(LIB) tests/cuda/conv3d_selftest tests/cuda/mma_bench
 
 .PHONY: all clean

@@ -93,7 +93,7 @@ struct Cfg {
     static constexpr int B_BYTES = ((NB * B_TILE + 1023) / 1024) * 1024;
     static constexpr int STAGE = A_BYTES + B_BYTES;
     // two CTAs per SM when a useful ring (>= 4 stages) fits in ~100 KB, otherwise one CTA with up to 200 KB
-    static constexpr int CTAS_PER_SM = (4 * STAGE <= 100 * 1024) ? 2 : 1;
+    static constexpr int CTAS_PER_SM = (3 * STAGE <= 100 * 1024) ? 2 : 1;
     static constexpr int BUDGET = (CTAS_PER_SM == 2 ? 100 : 200) * 1024;
     static constexpr int S_RAW = BUDGET / STAGE;
     static constexpr int STAGES = S_RAW > 8 ? 8 : (S_RAW < 2 ? 2 : S_RAW);
@@ -185,22 +185,22 @@ conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ================= TMA producer =================
-            int it = 0;                                    // ring position, runs on across tiles
-            for (int t = blockIdx.x; t < g.ntiles; t += gridDim.x) {
-                const TileInfo ti = decode_tile<MODE>(g, t, plane, vol, Dp);
-                if (ti.skip) continue;
-                const int tap0 = g.cls_begin[ti.cls];
-                const int ntaps = g.cls_begin[ti.cls + 1] - tap0;
-                const int ngroups = (MODE == MODE_SHIFT) ? ntaps / 3 : ntaps;
-                for (int grp = 0; grp < ngroups; ++grp) {
-                    const int tp = tap0 + ((MODE == MODE_SHIFT) ? 3 * grp : grp);
-                    for (int kc = 0; kc < g.nchunks; ++kc, ++it) {
-                        const int s = it % C::STAGES;
-                        const uint32_t ph = (uint32_t)(it / C::STAGES) & 1u;
-                        wait_bar(empty_bar(s), ph ^ 1u);
-                        const uint32_t sa = base + s * C::STAGE, sb = sa + C::A_BYTES;
+        // ================= TMA producer (whole warp walks the loop, one elected lane issues) =================
+        int it = 0;                                    // ring position, runs on across tiles
+        for (int t = blockIdx.x; t < g.ntiles; t += gridDim.x) {
+            const TileInfo ti = decode_tile<MODE>(g, t, plane, vol, Dp);
+            if (ti.skip) continue;
+            const int tap0 = g.cls_begin[ti.cls];
+            const int ntaps = g.cls_begin[ti.cls + 1] - tap0;
+            const int ngroups = (MODE == MODE_SHIFT) ? ntaps / 3 : ntaps;
+            for (int grp = 0; grp < ngroups; ++grp) {
+                const int tp = tap0 + ((MODE == MODE_SHIFT) ? 3 * grp : grp);
+                for (int kc = 0; kc < g.nchunks; ++kc, ++it) {
+                    const int s = it % C::STAGES;
+                    const uint32_t ph = (uint32_t)(it / C::STAGES) & 1u;
+                    wait_bar(empty_bar(s), ph ^ 1u);
+                    const uint32_t sa = base + s * C::STAGE, sb = sa + C::A_BYTES;
+                    if (ptx::elect_one_sync()) {
                         ptx::mbar_arrive_expect_tx(full_bar(s), C::TX_BYTES);
                         if (MODE == MODE_BOX) {
                             const int code = g.a_off[tp];
@@ -214,44 +214,47 @@ conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
                         for (int j = 0; j < C::NB; ++j)
                             ptx::tma_load_2d(sb + j * C::B_TILE, &maps.w, full_bar(s), kc * KC, g.w_row[tp + j]);
                     }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ================= MMA issuer =================
-            constexpr uint32_t idesc = ptx::make_idesc_bf16(NP);
-            int it = 0, tcount = 0;
-            for (int t = blockIdx.x; t < g.ntiles; t += gridDim.x) {
-                const TileInfo ti = decode_tile<MODE>(g, t, plane, vol, Dp);
-                if (ti.skip) continue;
-                const int ntaps = g.cls_begin[ti.cls + 1] - g.cls_begin[ti.cls];
-                const int n_it = ((MODE == MODE_SHIFT) ? ntaps / 3 : ntaps) * g.nchunks;
-                const int acc = tcount & 1;
-                const uint32_t acc_ph = (uint32_t)(tcount >> 1) & 1u;
-                wait_bar(tempty_bar(acc), acc_ph ^ 1u);    // epilogue has drained this buffer
+        // ================= MMA issuer (whole warp walks the loop, one elected lane issues) =================
+        constexpr uint32_t idesc = ptx::make_idesc_bf16(NP);
+        int it = 0, tcount = 0;
+        for (int t = blockIdx.x; t < g.ntiles; t += gridDim.x) {
+            const TileInfo ti = decode_tile<MODE>(g, t, plane, vol, Dp);
+            if (ti.skip) continue;
+            const int ntaps = g.cls_begin[ti.cls + 1] - g.cls_begin[ti.cls];
+            const int n_it = ((MODE == MODE_SHIFT) ? ntaps / 3 : ntaps) * g.nchunks;
+            const int acc = tcount & 1;
+            const uint32_t acc_ph = (uint32_t)(tcount >> 1) & 1u;
+            wait_bar(tempty_bar(acc), acc_ph ^ 1u);        // epilogue has drained this buffer
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem + acc * C::ACC_COLS;
+            for (int i = 0; i < n_it; ++i, ++it) {
+                const int s = it % C::STAGES;
+                const uint32_t ph = (uint32_t)(it / C::STAGES) & 1u;
+                wait_bar(full_bar(s), ph);
                 ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem + acc * C::ACC_COLS;
-                for (int i = 0; i < n_it; ++i, ++it) {
-                    const int s = it % C::STAGES;
-                    const uint32_t ph = (uint32_t)(it / C::STAGES) & 1u;
-                    wait_bar(full_bar(s), ph);
-                    ptx::tc_fence_after();
-                    const uint32_t sa = base + s * C::STAGE, sb = sa + C::A_BYTES;
+                const uint32_t sa = base + s * C::STAGE, sb = sa + C::A_BYTES;
+                if (ptx::elect_one_sync()) {
+                    const uint64_t ad0 = ptx::make_kmajor_desc(sa, C::ROWB, 0u);
+                    const uint64_t bd0 = ptx::make_kmajor_desc(sb, C::ROWB, 0u);
 #pragma unroll
                     for (int j = 0; j < C::NB; ++j) {
 #pragma unroll
                         for (int k = 0; k < KC / 16; ++k) {
-                            const uint64_t ad = ptx::make_kmajor_desc(sa + j * C::ROWB + k * 32, C::ROWB, 0u);
-                            const uint64_t bd = ptx::make_kmajor_desc(sb + j * C::B_TILE + k * 32, C::ROWB, 0u);
-                            ptx::umma_bf16(d_tmem, ad, bd, idesc, (i | j | k) ? 1u : 0u);
+                            ptx::umma_bf16(d_tmem, ptx::desc_advance(ad0, j * C::ROWB + k * 32),
+                                           ptx::desc_advance(bd0, j * C::B_TILE + k * 32), idesc, (i | j | k) ? 1u : 0u);
                         }
                     }
                     ptx::umma_commit(empty_bar(s));        // frees the stage when these MMAs retire
+                    if (i == n_it - 1) ptx::umma_commit(tfull_bar(acc));   // accumulator complete
                 }
-                ptx::umma_commit(tfull_bar(acc));          // accumulator complete
-                ++tcount;
+                __syncwarp();
             }
+            ++tcount;
         }
     } else {
         // ================= epilogue warps (one TMEM lane = one voxel per thread) =================
@@ -444,7 +447,7 @@ int conv3d_dispatch(const void* x, const void* w, const float* scale, const floa
     const int row_bytes = KC * 2;
     // bit1 of `variant` SET selects the per-tap kernel (MODE_FLAT); the default for stride-1 convolutions is the
     // row-shifted-descriptor kernel (validated bit-identical on B200), except N=128 whose stage would not fit twice
-    const int mode = (!transposed && stride == 2) ? MODE_BOX : ((!(variant & 2) && !transposed && NP <= 64) ? MODE_SHIFT : MODE_FLAT);
+    const int mode = (!transposed && stride == 2) ? MODE_BOX : ((!(variant & 2) && !transposed && NP <= 64 && !(KC == 64 && NP == 64 && !(variant & 4))) ? MODE_SHIFT : MODE_FLAT);
 
     {   // weights: [27*NP][Cin]
         cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)27 * NP};

@@ -10,6 +10,18 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// one lane of a fully converged warp (ptxas then emits the single-thread tcgen05/TMA instructions
+// directly instead of wrapping each in an elect-and-retry loop)
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, %1;\n\t"
+        "@px mov.s32 %0, 1;\n\t}"
+        : "+r"(pred) : "r"(0xFFFFFFFFu));
+    return pred != 0;
+}
+
 // ---- mbarrier -------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
@@ -108,6 +120,8 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr, uint32_t ro
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (sbo << 32) | (1ull << 46) |
            ((uint64_t)(base_offset & 7u) << 49) | (layout << 61);
 }
+// advance a descriptor by `bytes` inside the same swizzle atom row / along rows (start-address field only)
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
 // Instruction descriptor, kind::f16: D=f32, A=B=bf16, both K-major, M=128, N=n.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);

@@ -408,3 +408,69 @@ def calibrate_bn_(params: Dict[str, torch.Tensor], cost: torch.Tensor) -> None:
     out3, pre3, post3 = hg("dres4", out2, pre1, post2); out3 = crop_add(out3, cost0)
     for c, x in (("classif1", out1), ("classif2", out2), ("classif3", out3)):
         cb(c + ".0", x, relu=True)
+
+
+def psmnet_matcher_params(seed: int = 0, noise: float = 0.3, sharpness: float = 0.5) -> Dict[str, torch.Tensor]:
+    """Synthetic parameters that make the PSMNet 3-D stack an actual (crude) stereo matcher, so that
+    an end-point error against a known disparity is a meaningful number (the north_star's bf16
+    tolerance is stated on mean EPE; with purely random weights the EPE is tens of pixels and
+    says nothing).  Construction, on top of He-normal noise scaled by `noise`:
+      dres0.0  centre tap computes relu(+-(fL_c - fR_c)) for the first 16 feature channels
+               -> the 32 outputs sum to a 16-channel sum of absolute differences (SAD);
+      dres0.2  3x3 in-plane box filter of each channel (cost aggregation);
+      dres1, hourglasses  reference init (stackhourglass.py:100-114); conv6 and dres1.2 scaled by
+               `noise`, so that every layer computes full-magnitude activations whose effect on
+               the cost is a perturbation;
+      classif*.0 identity centre tap + noise; classif*.2 = -sharpness on every channel's centre tap
+               -> cost = -sharpness * aggregated SAD, soft-argmin peaks at the matching disparity.
+    BatchNorm is the identity (running stats 0/1, weight 1, bias 0)."""
+    params = psmnet_random_params(seed)
+    rs = np.random.RandomState(seed + 7919)
+
+    def he(shape, cout):
+        return torch.from_numpy(rs.standard_normal(size=shape).astype(np.float32) * np.float32(math.sqrt(2.0 / (27 * cout))))
+
+    w = he((32, 64, 3, 3, 3), 32) * noise
+    for c in range(16):
+        w[c, c, 1, 1, 1] += 1.0; w[c, 32 + c, 1, 1, 1] -= 1.0
+        w[16 + c, c, 1, 1, 1] -= 1.0; w[16 + c, 32 + c, 1, 1, 1] += 1.0
+    params["dres0.0.0.weight"] = w
+    w = he((32, 32, 3, 3, 3), 32) * noise
+    for c in range(32):
+        w[c, c, 1, :, :] += 1.0 / 9.0
+    params["dres0.2.0.weight"] = w
+    params["dres1.2.0.weight"] = params["dres1.2.0.weight"] * noise
+    for h in ("dres2", "dres3", "dres4"):
+        params[h + ".conv6.0.weight"] = params[h + ".conv6.0.weight"] * noise
+    for cname in ("classif1", "classif2", "classif3"):
+        w = he((32, 32, 3, 3, 3), 32) * noise
+        for c in range(32):
+            w[c, c, 1, 1, 1] += 1.0
+        params[cname + ".0.0.weight"] = w
+        w = he((1, 32, 3, 3, 3), 1) * (noise * 0.05)
+        w[0, :, 1, 1, 1] -= sharpness
+        params[cname + ".2.weight"] = w
+    return params
+
+
+def synthetic_stereo_features(H: int, W: int, C: int = 32, d_lo: float = 10.0, d_hi: float = 30.0, seed: int = 0):
+    """A feature pair with stereo structure: fR is fL resampled by a smooth (linear-ramp) disparity
+    field, so that fL[y, x] ~ fR[y, x - disp(x)].  Returns (fL, fR, disp) with disp [1,H,W] in units
+    of feature-map pixels."""
+    rs = np.random.RandomState(seed)
+    fL = torch.from_numpy(rs.standard_normal(size=(1, C, H, W)).astype(np.float32))
+    # smooth the features a little along x so that sub-pixel interpolation is meaningful
+    fL = F.avg_pool2d(F.pad(fL, (1, 1, 0, 0), mode="replicate"), (1, 3), stride=1) * math.sqrt(3.0)
+    xr = torch.arange(W, dtype=torch.float32)
+    # disparity as a function of the RIGHT-image column x' ; the left column is x = x' + d(x')
+    d_r = d_lo + (d_hi - d_lo) * xr / (W - 1)
+    src_x = (xr + d_r).clamp(0, W - 1)                       # fR[x'] = fL[x' + d(x')]
+    gx = (src_x / (W - 1) * 2 - 1).view(1, 1, W).expand(1, H, W)
+    gy = (torch.arange(H, dtype=torch.float32) / max(H - 1, 1) * 2 - 1).view(1, H, 1).expand(1, H, W)
+    fR = F.grid_sample(fL, torch.stack([gx, gy], -1), mode="bilinear", padding_mode="border", align_corners=True)
+    # disparity seen from the LEFT image: solve x = x' + d(x') for x' (d is linear in x')
+    a = (d_hi - d_lo) / (W - 1)
+    xl = torch.arange(W, dtype=torch.float32)
+    xprime = (xl - d_lo) / (1 + a)
+    disp = (xl - xprime).view(1, 1, W).expand(1, H, W).contiguous()
+    return fL, fR, disp

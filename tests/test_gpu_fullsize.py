@@ -82,23 +82,28 @@ def test_concat_volume_checksum_full_size():
     assert torch.allclose(vol[:, 32:].sum(2), right, rtol=0, atol=1e-9)
 
 
+def _epe(pred, gt, valid):
+    return float((pred - gt)[valid].abs().mean())
+
+
 def test_north_star_path_full_size():
-    """one 384x1248 pair through the CUDA path vs the CPU oracle (fp32 reference arithmetic)."""
+    """One 384x1248 pair through the CUDA path vs the CPU oracle (fp32 reference arithmetic).
+
+    The 3-D stack carries `psmnet_matcher_params` (a crude but real stereo matcher inside the PSMNet
+    architecture, oracle/ops.py) and the features have stereo structure with a known disparity, so
+    the end-point error is a meaningful number (~1.5 px) and BASELINE.json's tolerance —
+    mean EPE delta < 0.01 px for the bf16 tensor-core convolutions — can be asserted as stated.
+    EPE is taken where the PSM volume is defined for every candidate disparity (x >= maxdisp)."""
     from dsmnet_b200.psmnet import PSMNetHotPath
     from dsmnet_b200.conv3d import conv_timeouts
-    torch.manual_seed(4)
     maxdisp, HI, WI = 192, 384, 1248
-    # features with stereo structure: the right map is the left map shifted by a smooth disparity
-    fL = torch.randn(1, 32, H, W)
-    gt4 = (10 + 20 * torch.linspace(0, 1, W)).view(1, 1, 1, W).expand(1, 1, H, W)          # 1/4-res disparity
-    grid_x = (torch.arange(W).view(1, 1, W) + gt4[:, 0]).clamp(0, W - 1)
-    gx = grid_x / (W - 1) * 2 - 1
-    gy = (torch.arange(H).view(1, H, 1).expand(1, H, W) / (H - 1)) * 2 - 1
-    fR = F.grid_sample(fL, torch.stack([gx, gy], -1), mode="bilinear", padding_mode="border", align_corners=True)
-    gt = F.interpolate(gt4 * 4, size=(HI, WI), mode="bilinear", align_corners=True)[:, 0]
-    cost = O.concat_volume(fL, fR, maxdisp // 4, "psm")
-    params = O.psmnet_random_params(seed=21, calibrate_on=cost)
+    fL, fR, disp4 = O.synthetic_stereo_features(H, W, d_lo=10.0, d_hi=30.0, seed=4)
+    gt = F.interpolate(disp4.unsqueeze(1) * 4, size=(HI, WI), mode="bilinear", align_corners=True)[:, 0]
+    valid = torch.zeros_like(gt, dtype=torch.bool)
+    valid[:, 8:-8, maxdisp + 8:-8] = True
+    params = O.psmnet_matcher_params(seed=21)
     ref = O.psmnet_hotpath(params, fL, fR, maxdisp, (HI, WI))
+    emu = O.psmnet_hotpath(params, fL, fR, maxdisp, (HI, WI), operand_dtype=(torch.bfloat16, torch.bfloat16))
     m = PSMNetHotPath(maxdisp)
     m.load_state_dict(params, strict=False)
     m = m.cuda().eval()
@@ -106,11 +111,36 @@ def test_north_star_path_full_size():
         preds = m(fL.cuda(), fR.cuda(), (HI, WI))
     torch.cuda.synchronize()
     assert conv_timeouts() == 0
-    for name, mine, r in zip(("pred3", "pred2", "pred1"), preds, ref):
+    for name, mine, r, e in zip(("pred3", "pred2", "pred1"), preds, ref, emu):
         mine = mine.cpu()
         assert mine.shape == (1, HI, WI) and bool(torch.isfinite(mine).all())
-        epe_ref = float((r - gt).abs().mean()); epe_mine = float((mine - gt).abs().mean())
-        d = float((mine - r).abs().mean())
-        print("%s: EPE ref %.4f ours %.4f (delta %.5f px); mean |ours - ref| %.4f px" % (name, epe_ref, epe_mine, abs(epe_mine - epe_ref), d))
+        epe_ref, epe_mine = _epe(r, gt, valid), _epe(mine, gt, valid)
+        d_ref = float((mine - r)[valid].abs().mean()); d_emu = float((mine - e)[valid].abs().mean())
+        print("%s: EPE ref %.4f ours %.4f (delta %.5f px); mean |ours-ref| %.4f, |ours-emu| %.4f px" %
+              (name, epe_ref, epe_mine, abs(epe_mine - epe_ref), d_ref, d_emu))
+        assert epe_ref < 3.0                           # the synthetic matcher really matches
         assert abs(epe_mine - epe_ref) < 0.01          # north_star: mean EPE delta < 0.01 px
-        assert d < 0.25                                # bf16 operand format error on this random-weight net
+        assert d_ref < 0.05 and d_emu < 0.02           # per-pixel agreement with the fp32 reference / its bf16 emulation
+
+
+def test_north_star_path_full_size_random_weights():
+    """Same pair, purely random (He-init, BN-calibrated) weights: the network is a chaotic amplifier, so the
+    gate is relative — the CUDA path must sit closer to the oracle's bf16-operand emulation than that
+    emulation sits to the fp32 reference (i.e. the kernels add no error beyond the operand format)."""
+    from dsmnet_b200.psmnet import PSMNetHotPath
+    maxdisp, HI, WI = 192, 384, 1248
+    fL, fR, _ = O.synthetic_stereo_features(H, W, seed=5)
+    cost = O.concat_volume(fL, fR, maxdisp // 4, "psm")
+    params = O.psmnet_random_params(seed=21, calibrate_on=cost)
+    ref = O.psmnet_hotpath(params, fL, fR, maxdisp, (HI, WI))
+    emu = O.psmnet_hotpath(params, fL, fR, maxdisp, (HI, WI), operand_dtype=(torch.bfloat16, torch.bfloat16))
+    m = PSMNetHotPath(maxdisp)
+    m.load_state_dict(params, strict=False)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        preds = m(fL.cuda(), fR.cuda(), (HI, WI))
+    for name, mine, r, e in zip(("pred3", "pred2", "pred1"), preds, ref, emu):
+        mine = mine.cpu()
+        d_emu = float((mine - e).abs().mean()); d_fmt = float((e - r).abs().mean()); d_ref = float((mine - r).abs().mean())
+        print("%s: mean |ours-emu| %.4f, |emu-ref| %.4f, |ours-ref| %.4f px" % (name, d_emu, d_fmt, d_ref))
+        assert d_emu < d_fmt and d_ref < 2.0 * d_fmt + 1e-3
