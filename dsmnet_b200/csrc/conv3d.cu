@@ -70,17 +70,21 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 
 // Bounded wait: a broken pipeline must end the kernel (with a counted timeout), never hang the GPU.
+// The fast path is a bare try_wait spin (the instruction itself suspends the warp for a while); the
+// global timeout flag and the wall clock are only consulted every 4096 failed polls.
 __device__ __forceinline__ bool wait_bar(uint32_t bar, uint32_t parity) {
     if (ptx::mbar_try_wait(bar, parity)) return true;
-    if (*reinterpret_cast<volatile int*>(&g_conv_timeouts)) return false;
-    const unsigned long long t0 = globaltimer_ns();
-    while (!ptx::mbar_try_wait(bar, parity)) {
-        if (globaltimer_ns() - t0 > 200000000ULL /*0.2 s*/ || *reinterpret_cast<volatile int*>(&g_conv_timeouts)) {
-            atomicAdd(&g_conv_timeouts, 1);
-            return false;
+    unsigned long long t0 = 0;
+    for (uint32_t spins = 1; ; ++spins) {
+        if (ptx::mbar_try_wait(bar, parity)) return true;
+        if ((spins & 4095u) == 0u) {
+            if (t0 == 0) t0 = globaltimer_ns();
+            if (globaltimer_ns() - t0 > 200000000ULL /*0.2 s*/ || *reinterpret_cast<volatile int*>(&g_conv_timeouts)) {
+                atomicAdd(&g_conv_timeouts, 1);
+                return false;
+            }
         }
     }
-    return true;
 }
 
 template <int KC, int NP, int MODE>
@@ -359,6 +363,334 @@ conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------
+// Plane-sharing kernel for stride-1 convolutions with few output channels (Cout <= 32).
+//
+// Measured on B200 (tests/cuda/mma_bench.cu): an SS-mode tcgen05.mma M=128,K=16 costs
+// max(N/2, 32 + N/4) cycles — the 4 KB A slab is re-read from shared memory by every instruction, so
+// N=32 tops out at 40% of the tensor pipe, N=96 at 86%.  This kernel therefore widens N by letting
+// ONE activation tile feed the three kd taps at once: a CTA owns a band of R=8 consecutive output
+// planes of one 128-voxel flat (h,w) tile, each plane with its own NP accumulator columns
+// (R*NP columns per buffer, two buffers = all 512 TMEM columns for NP=32).  The A tile of input
+// plane i contributes to output planes i-1, i, i+1 through taps kd=2,1,0, whose weight rows are laid
+// out back to back in shared memory, so one MMA with N = 3*NP updates three adjacent accumulator
+// blocks.  All 27 weight tiles stay resident in shared memory for the whole kernel (55 KB for
+// 32->32, 110 KB for 64->32); only 130-row activation tiles (the three kw taps are row-shifted
+// descriptors into the same tile) stream through the TMA ring: (R+2)*3 tile loads per R*128
+// output voxels instead of 27 (or 9) per 128.
+// ---------------------------------------------------------------------------------------------
+struct RsGeom {
+    int B, D, H, W;          // extent (stride 1: input == natural output extent)
+    int Do, Ho, Wo;          // output buffer extent (may be a crop)
+    int Cout, relu, y_f32;
+    int plane_tiles;         // ceil(Hp*Wp / 128)
+    int nbands;              // ceil(Do / R)
+    int nitems;              // B * nbands * plane_tiles
+    int w_row[27];           // first row of tap (kd*3+kh)*3+kw in the packed weights
+};
+
+template <int KC, int NP>
+struct RsCfg {
+    static constexpr int R = 8;
+    static constexpr int ROWB = KC * 2;
+    static constexpr int A_ROWS = 130;
+    static constexpr int A_BYTES = ((A_ROWS * ROWB + 1023) / 1024) * 1024;
+    static constexpr int KHS = (KC <= 32) ? 3 : 1;               // kh tiles per pipeline stage (a whole input plane when they fit)
+    static constexpr int STAGE_BYTES = KHS * A_BYTES;
+    static constexpr int W_TILE = 3 * NP * ROWB;                  // the three kd taps of one (kh,kw), kd = 2,1,0
+    static constexpr int W_BYTES = 9 * W_TILE;
+    static constexpr int BAR_BYTES = 512;
+    static constexpr int BUDGET = 225 * 1024 - W_BYTES - 1024 - BAR_BYTES - 2 * NP * 4;
+    static constexpr int S_RAW = BUDGET / STAGE_BYTES;
+    static constexpr int STAGES = S_RAW > 8 ? 8 : S_RAW;
+    static constexpr int TX_BYTES = KHS * A_ROWS * ROWB;
+    static constexpr int ACC_COLS = R * NP;
+    static constexpr int TMEM_COLS = 2 * ACC_COLS;                // 256 (NP=16) or 512 (NP=32)
+    static constexpr int SMEM = W_BYTES + STAGES * STAGE_BYTES + 1024 + BAR_BYTES + 2 * NP * 4;
+    static constexpr int THREADS = 320;                           // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+    static_assert(STAGES >= 4, "activation ring too shallow");
+    static_assert((W_TILE % 1024) == 0 && ((NP * ROWB) % 1024) == 0, "weight sub-tiles must keep the swizzle phase");
+};
+
+struct RsItem { int b, z0, nb, tile; };
+
+__device__ __forceinline__ RsItem rs_decode(const RsGeom& g, int t, int R) {
+    RsItem it;
+    it.tile = t % g.plane_tiles; t /= g.plane_tiles;
+    const int band = t % g.nbands; it.b = t / g.nbands;
+    it.z0 = band * R;
+    it.nb = min(R, g.Do - it.z0);
+    return it;
+}
+
+template <int KC, int NP>
+__global__ void __launch_bounds__(320, 1)
+conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                 const __grid_constant__ RsGeom g, const float* __restrict__ scale, const float* __restrict__ shift,
+                 const void* __restrict__ residual, void* __restrict__ y) {
+    using C = RsCfg<KC, NP>;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int Dp = g.D + 2, Hp = g.H + 2, Wp = g.W + 2;
+    const int plane = Hp * Wp;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = ptx::smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - raw);
+    const uint32_t wsm = base;                                  // resident weights
+    const uint32_t ring = base + C::W_BYTES;                    // activation ring
+    constexpr int RING_END = C::W_BYTES + C::STAGES * C::STAGE_BYTES;
+    const uint32_t bars = base + RING_END;                      // full[S], empty[S], tfull[2], tempty[2], wfull, slot, scratch
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
+    auto tfull_bar = [&](int a) { return bars + 8u * (2 * C::STAGES + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (2 * C::STAGES + 2 + a); };
+    const uint32_t wfull_bar = bars + 8u * (2 * C::STAGES + 4);
+    constexpr int NBARS = 2 * C::STAGES + 5;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + RING_END + 8 * NBARS);
+    const uint32_t scratch_smem = bars + 8u * NBARS + 8u;
+    float* s_scale = reinterpret_cast<float*>(base_ptr + RING_END + C::BAR_BYTES);
+    float* s_shift = s_scale + NP;
+
+    if (tid < NP) {
+        s_scale[tid] = scale ? __ldg(scale + tid) : 1.f;
+        s_shift[tid] = shift ? __ldg(shift + tid) : 0.f;
+    }
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&map_w);
+        ptx::prefetch_tensormap(&map_a);
+        for (int s = 0; s < C::STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { ptx::mbar_init(tfull_bar(a), 1); ptx::mbar_init(tempty_bar(a), 8); }
+        ptx::mbar_init(wfull_bar, 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), C::TMEM_COLS);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (ptx::elect_one_sync()) {                            // all 27 weight tiles, once
+            ptx::mbar_arrive_expect_tx(wfull_bar, 27 * NP * C::ROWB);
+            for (int kd = 0; kd < 3; ++kd)
+                for (int kh = 0; kh < 3; ++kh)
+                    for (int kw = 0; kw < 3; ++kw)
+                        ptx::tma_load_2d(wsm + (kh * 3 + kw) * C::W_TILE + (2 - kd) * NP * C::ROWB, &map_w, wfull_bar, 0,
+                                         g.w_row[(kd * 3 + kh) * 3 + kw]);
+        }
+        __syncwarp();
+        int s = 0; uint32_t ph = 0;                              // ring slot and its phase
+        for (int t = blockIdx.x; t < g.nitems; t += gridDim.x) {
+            const RsItem item = rs_decode(g, t, C::R);
+            for (int i = -1; i <= item.nb; ++i) {
+                const int zp = item.z0 + 1 + i;                  // padded input plane
+                if (zp <= 0 || zp >= Dp - 1) continue;           // zero rim plane: contributes nothing
+                const int row0 = (item.b * Dp + zp) * plane + item.tile * 128 - Wp - 1;
+                for (int khs = 0; khs < 3 / C::KHS; ++khs) {
+                    wait_bar(empty_bar(s), ph ^ 1u);
+                    if (ptx::elect_one_sync()) {
+                        ptx::mbar_arrive_expect_tx(full_bar(s), C::TX_BYTES);
+#pragma unroll
+                        for (int kk = 0; kk < C::KHS; ++kk)
+                            ptx::tma_load_2d(ring + s * C::STAGE_BYTES + kk * C::A_BYTES, &map_a, full_bar(s), 0,
+                                             row0 + (khs * C::KHS + kk) * Wp);
+                    }
+                    __syncwarp();
+                    if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        constexpr uint32_t idesc0 = ptx::make_idesc_bf16(0);
+        wait_bar(wfull_bar, 0);
+        ptx::tc_fence_after();
+        // descriptor words: only the start-address field of the low word changes from MMA to MMA
+        const uint64_t dsc = ptx::make_kmajor_desc(0u, C::ROWB, 0u);
+        const uint32_t desc_hi = (uint32_t)(dsc >> 32);
+        const uint32_t ring_lo = (uint32_t)dsc | (ring >> 4);
+        const uint32_t w_lo = (uint32_t)dsc | (wsm >> 4);
+        int s = 0; uint32_t ph = 0;
+        int tcount = 0;
+        for (int t = blockIdx.x; t < g.nitems; t += gridDim.x) {
+            const RsItem item = rs_decode(g, t, C::R);
+            const int acc = tcount & 1;
+            const uint32_t acc_ph = (uint32_t)(tcount >> 1) & 1u;
+            ++tcount;
+            wait_bar(tempty_bar(acc), acc_ph ^ 1u);
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem + acc * C::ACC_COLS;
+            int nt = 0;                                          // accumulator blocks [0, nt) already hold data
+            int last_i = item.nb;
+            if (item.z0 + 1 + last_i >= Dp - 1) --last_i;        // trailing rim plane is skipped
+            for (int i = -1; i <= item.nb; ++i) {
+                const int zp = item.z0 + 1 + i;
+                if (zp <= 0 || zp >= Dp - 1) continue;
+                const int jlo = max(i - 1, 0), jhi = min(i + 1, item.nb - 1);
+                const int brow = (2 - (i - jlo + 1)) * NP;        // weight row of block jlo's tap (kd = i-jlo+1)
+                const uint32_t d_lo = d_tmem + jlo * NP;
+                const uint32_t idesc = idesc0 | ((uint32_t)((jhi - jlo + 1) * NP >> 3) << 17);
+                const uint32_t b_lo_plane = w_lo + ((uint32_t)(brow * C::ROWB) >> 4);
+#pragma unroll
+                for (int khs = 0; khs < 3 / C::KHS; ++khs) {
+                    wait_bar(full_bar(s), ph);
+                    ptx::tc_fence_after();
+                    if (ptx::elect_one_sync()) {
+                        const uint32_t a_lo0 = ring_lo + (uint32_t)s * (C::STAGE_BYTES >> 4);
+#pragma unroll
+                        for (int kk = 0; kk < C::KHS; ++kk) {
+                            const int kh = khs * C::KHS + kk;
+#pragma unroll
+                            for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+                                for (int k = 0; k < KC / 16; ++k) {
+                                    const uint32_t a_lo = a_lo0 + ((kk * C::A_BYTES + kw * C::ROWB + k * 32) >> 4);
+                                    const uint32_t b_lo = b_lo_plane + (((kh * 3 + kw) * C::W_TILE + k * 32) >> 4);
+                                    if (kh == 0 && kw == 0 && k == 0) {
+                                        if (jhi >= nt) {
+                                            // first touch of block(s) [max(nt,jlo), jhi]: overwrite instead of accumulate
+                                            if (jlo < nt)
+                                                ptx::umma_bf16_lohi(d_lo, a_lo, b_lo, desc_hi, idesc0 | ((uint32_t)((nt - jlo) * NP >> 3) << 17), 1u);
+                                            const int f0 = max(nt, jlo);
+                                            ptx::umma_bf16_lohi(d_tmem + f0 * NP, a_lo, b_lo + ((uint32_t)((f0 - jlo) * NP * C::ROWB) >> 4), desc_hi,
+                                                                idesc0 | ((uint32_t)((jhi - f0 + 1) * NP >> 3) << 17), 0u);
+                                        } else {
+                                            ptx::umma_bf16_lohi(d_lo, a_lo, b_lo, desc_hi, idesc, 1u);
+                                        }
+                                    } else {
+                                        ptx::umma_bf16_lohi(d_lo, a_lo, b_lo, desc_hi, idesc, 1u);
+                                    }
+                                }
+                            }
+                        }
+                        ptx::umma_commit(empty_bar(s));
+                        if (i == last_i && khs == 3 / C::KHS - 1) ptx::umma_commit(tfull_bar(acc));
+                    }
+                    __syncwarp();
+                    if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+                }
+                nt = max(nt, jhi + 1);
+            }
+        }
+    } else {
+        // ================= epilogue: 8 warps, two per TMEM lane quadrant =================
+        // warp w reads lanes 32*(w%4)..+31 (hardware rule); the two warps of a quadrant take the even / odd
+        // output planes of the band.  Residual rows are fetched BEFORE waiting for the accumulator so
+        // that their DRAM latency hides behind the MMAs of this item.
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int r = q * 32 + lane;
+        constexpr int JJ = C::R / 2;                              // planes per warp
+        constexpr int NV = NP / 8;                                // uint4 per bf16 output row
+        const float4* sc4 = reinterpret_cast<const float4*>(s_scale);
+        const float4* sh4 = reinterpret_cast<const float4*>(s_shift);
+        int tcount = 0;
+        for (int t = blockIdx.x; t < g.nitems; t += gridDim.x) {
+            const RsItem item = rs_decode(g, t, C::R);
+            const int pq = item.tile * 128 + r;                   // position in the padded (h,w) plane
+            const int hp = pq / Wp, wp = pq - hp * Wp;
+            const bool valid = (pq < plane) && hp >= 1 && hp <= g.Ho && wp >= 1 && wp <= g.Wo;
+            const int acc = tcount & 1;
+            const uint32_t acc_ph = (uint32_t)(tcount >> 1) & 1u;
+            ++tcount;
+            const uint32_t taddr0 = tmem + ((uint32_t)(q * 32) << 16) + acc * C::ACC_COLS;
+            int my_last = -1;                                     // my last plane of this band (-1: none)
+            for (int jj = 0; jj < JJ; ++jj) if (2 * jj + half < item.nb) my_last = 2 * jj + half;
+
+            if (g.y_f32) {
+                // single output channel: fp32, unpadded [B][Do][Ho][Wo]
+                const size_t o0 = (((size_t)item.b * g.Do + item.z0) * g.Ho + (hp - 1)) * g.Wo + (wp - 1);
+                const size_t ostep = (size_t)g.Ho * g.Wo;
+                float rf[JJ];
+#pragma unroll
+                for (int jj = 0; jj < JJ; ++jj) {
+                    const int j = 2 * jj + half;
+                    rf[jj] = (residual && valid && j < item.nb) ? __ldg(reinterpret_cast<const float*>(residual) + o0 + j * ostep) : 0.f;
+                }
+                wait_bar(tfull_bar(acc), acc_ph);
+                __syncwarp();
+                ptx::tc_fence_after();
+                if (my_last < 0) { ptx::tc_fence_before(); __syncwarp(); if (lane == 0) ptx::mbar_arrive(tempty_bar(acc)); }
+#pragma unroll
+                for (int jj = 0; jj < JJ; ++jj) {
+                    const int j = 2 * jj + half;
+                    if (j < item.nb) {
+                        uint32_t v[16];
+                        ptx::tmem_ld16(taddr0 + j * NP, v);
+                        ptx::tc_wait_ld();
+                        consume_tmem_load(v[0], scratch_smem);
+                        if (j == my_last) { ptx::tc_fence_before(); __syncwarp(); if (lane == 0) ptx::mbar_arrive(tempty_bar(acc)); }
+                        if (valid) {
+                            float a = fmaf(__uint_as_float(v[0]), s_scale[0], s_shift[0]) + rf[jj];
+                            if (g.relu) a = fmaxf(a, 0.f);
+                            reinterpret_cast<float*>(y)[o0 + j * ostep] = a;
+                        }
+                    }
+                }
+            } else {
+                const size_t ostep = (size_t)(g.Ho + 2) * (g.Wo + 2) * g.Cout;     // one output plane
+                const size_t o0 = ((((size_t)item.b * (g.Do + 2) + item.z0 + 1) * (g.Ho + 2) + hp) * (g.Wo + 2) + wp) * (size_t)g.Cout;
+                const __nv_bfloat16* resb = reinterpret_cast<const __nv_bfloat16*>(residual);
+                uint4 rv[JJ][NV];
+#pragma unroll
+                for (int jj = 0; jj < JJ; ++jj) {
+                    const int j = 2 * jj + half;
+                    const bool ld = residual && valid && j < item.nb;
+#pragma unroll
+                    for (int c = 0; c < NV; ++c)
+                        rv[jj][c] = ld ? __ldg(reinterpret_cast<const uint4*>(resb + o0 + j * ostep) + c) : make_uint4(0u, 0u, 0u, 0u);
+                }
+                wait_bar(tfull_bar(acc), acc_ph);
+                __syncwarp();
+                ptx::tc_fence_after();
+                if (my_last < 0) { ptx::tc_fence_before(); __syncwarp(); if (lane == 0) ptx::mbar_arrive(tempty_bar(acc)); }
+#pragma unroll
+                for (int jj = 0; jj < JJ; ++jj) {
+                    const int j = 2 * jj + half;
+                    if (j < item.nb) {
+                        uint32_t v[NP];
+                        if (NP == 32) ptx::tmem_ld32(taddr0 + j * NP, v); else ptx::tmem_ld16(taddr0 + j * NP, v);
+                        ptx::tc_wait_ld();
+                        consume_tmem_load(v[0], scratch_smem);
+                        if (j == my_last) { ptx::tc_fence_before(); __syncwarp(); if (lane == 0) ptx::mbar_arrive(tempty_bar(acc)); }
+                        if (valid) {
+                            uint4* out = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y) + o0 + j * ostep);
+#pragma unroll
+                            for (int c = 0; c < NV; ++c) {
+                                const float4 s0 = sc4[2 * c], s1 = sc4[2 * c + 1], h0 = sh4[2 * c], h1 = sh4[2 * c + 1];
+                                const uint4 rr = rv[jj][c];
+                                float f[8];
+                                f[0] = fmaf(__uint_as_float(v[8 * c + 0]), s0.x, h0.x) + bf16_lo(rr.x);
+                                f[1] = fmaf(__uint_as_float(v[8 * c + 1]), s0.y, h0.y) + bf16_hi(rr.x);
+                                f[2] = fmaf(__uint_as_float(v[8 * c + 2]), s0.z, h0.z) + bf16_lo(rr.y);
+                                f[3] = fmaf(__uint_as_float(v[8 * c + 3]), s0.w, h0.w) + bf16_hi(rr.y);
+                                f[4] = fmaf(__uint_as_float(v[8 * c + 4]), s1.x, h1.x) + bf16_lo(rr.z);
+                                f[5] = fmaf(__uint_as_float(v[8 * c + 5]), s1.y, h1.y) + bf16_hi(rr.z);
+                                f[6] = fmaf(__uint_as_float(v[8 * c + 6]), s1.z, h1.z) + bf16_lo(rr.w);
+                                f[7] = fmaf(__uint_as_float(v[8 * c + 7]), s1.w, h1.w) + bf16_hi(rr.w);
+                                if (g.relu) {
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+                                }
+                                uint4 ov;
+                                ov.x = pack_bf16x2(f[0], f[1]); ov.y = pack_bf16x2(f[2], f[3]);
+                                ov.z = pack_bf16x2(f[4], f[5]); ov.w = pack_bf16x2(f[6], f[7]);
+                                out[c] = ov;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem, C::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -413,6 +745,20 @@ int launch_mode(int KC, int NP, const ConvMaps& maps, const ConvGeom& g, dim3 gr
     return DSM_EUNSUPPORTED;
 }
 
+template <int KC, int NP>
+int launch_rs(const CUtensorMap& map_a, const CUtensorMap& map_w, const RsGeom& g, const float* scale, const float* shift,
+              const void* residual, void* y, cudaStream_t st) {
+    using C = RsCfg<KC, NP>;
+    auto kern = conv3d_rs_kernel<KC, NP>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    int nsm = DSM_NUM_SMS_B200, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    const int nblocks = g.nitems < nsm ? g.nitems : nsm;        // persistent: one CTA per SM
+    kern<<<nblocks, C::THREADS, C::SMEM, st>>>(map_a, map_w, g, scale, shift, residual, y);
+    return dsm_launch_status();
+}
+
 int conv3d_dispatch(const void* x, const void* w, const float* scale, const float* shift, const void* residual, void* y,
                     int B, int Cin, int Cout, int D, int H, int W, int stride, int transposed, int relu, int y_dtype,
                     int Do, int Ho, int Wo, int variant, void* stream) {
@@ -454,6 +800,30 @@ int conv3d_dispatch(const void* x, const void* w, const float* scale, const floa
         cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
         cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)NP};
         if (!encode_map(&maps.w, w, 2, dims, strides, box, row_bytes)) return DSM_EDRIVER;
+    }
+    // stride-1, Cout <= 32: the plane-sharing kernel (variant bit3 set = keep the per-tile kernels, for A/B runs)
+    if (!transposed && stride == 1 && NP <= 32 && Cin <= 64 && !(variant & 8)) {
+        CUtensorMap map_a;
+        cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)P};
+        cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
+        cuuint32_t box[2] = {(cuuint32_t)KC, 130u};
+        if (!encode_map(&map_a, x, 2, dims, strides, box, row_bytes)) return DSM_EDRIVER;
+        RsGeom rg;
+        memset(&rg, 0, sizeof(rg));
+        rg.B = B; rg.D = D; rg.H = H; rg.W = W; rg.Do = Do; rg.Ho = Ho; rg.Wo = Wo;
+        rg.Cout = Cout; rg.relu = relu; rg.y_f32 = (y_dtype == DSM_F32);
+        rg.plane_tiles = dsm_ceil_div(Hp * Wp, 128);
+        rg.nbands = dsm_ceil_div(Do, 8);
+        const long long ni = (long long)B * rg.nbands * rg.plane_tiles;
+        if (ni > 0x7fffffffLL) return DSM_EUNSUPPORTED;
+        rg.nitems = (int)ni;
+        for (int t = 0; t < 27; ++t) rg.w_row[t] = t * NP;
+        cudaStream_t st = (cudaStream_t)stream;
+        if (KC == 32 && NP == 16) return launch_rs<32, 16>(map_a, maps.w, rg, scale, shift, residual, y, st);
+        if (KC == 32 && NP == 32) return launch_rs<32, 32>(map_a, maps.w, rg, scale, shift, residual, y, st);
+        if (KC == 64 && NP == 16) return launch_rs<64, 16>(map_a, maps.w, rg, scale, shift, residual, y, st);
+        if (KC == 64 && NP == 32) return launch_rs<64, 32>(map_a, maps.w, rg, scale, shift, residual, y, st);
+        return DSM_EUNSUPPORTED;
     }
     dim3 grid;
     if (mode == MODE_BOX) {

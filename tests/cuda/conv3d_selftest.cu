@@ -209,6 +209,15 @@ int main(int argc, char** argv) {
             {1, 128, 128, 3, 4, 9, 1, 0, 1, 0, 1, 0, 0, "s1 128->128 (2 K chunks)"},
             {1, 64, 128, 6, 8, 18, 2, 0, 1, 0, 1, 0, 0, "s2 64->128"},
             {1, 128, 64, 3, 4, 9, 2, 1, 1, 1, 1, 0, 0, "deconv 128->64"},
+            // plane-sharing kernel: several bands, a partial last band, single / two planes
+            {1, 32, 32, 11, 6, 20, 1, 0, 1, 1, 1, 0, 0, "s1 32->32 D=11 (8+3 planes)"},
+            {2, 32, 32, 17, 5, 33, 1, 0, 1, 0, 1, 0, 0, "s1 32->32 B=2 D=17"},
+            {1, 64, 32, 9, 5, 23, 1, 0, 1, 1, 1, 0, 0, "s1 64->32 D=9"},
+            {1, 32, 1, 10, 7, 21, 1, 0, 0, 1, 0, 1, 0, "s1 32->1 fp32 D=10"},
+            {1, 32, 32, 1, 5, 9, 1, 0, 0, 0, 0, 0, 0, "s1 32->32 D=1"},
+            {1, 32, 32, 2, 5, 9, 1, 0, 0, 0, 1, 0, 0, "s1 32->32 D=2"},
+            {1, 32, 16, 8, 9, 40, 1, 0, 1, 0, 1, 0, 0, "s1 32->16 D=8"},
+            {1, 32, 32, 24, 20, 150, 1, 0, 1, 1, 1, 0, 0, "s1 32->32 24x20x150 (many tiles)"},
         };
         { int idx = 0; for (auto& c : cases) { if (g_only < 0 || g_only == idx) { Case cc = c; cc.variant |= g_level << 8; fails += run_case(cc, false, 0); } ++idx; } }
     }
@@ -218,8 +227,10 @@ int main(int argc, char** argv) {
             {1, 32, 32, 4, 6, 20, 1, 0, 1, 1, 1, 0, 2, "s1 32->32 per-tap"},
             {1, 64, 32, 5, 7, 19, 1, 0, 1, 0, 1, 0, 2, "s1 64->32 per-tap"},
             {1, 64, 64, 4, 6, 20, 1, 0, 1, 1, 1, 0, 2, "s1 64->64 per-tap"},
-            
-            
+            // variant bit3: the per-tile row-shifted-descriptor kernel instead of the plane-sharing kernel
+            {1, 32, 32, 4, 6, 20, 1, 0, 1, 1, 1, 0, 8, "s1 32->32 per-tile shift"},
+            {1, 64, 32, 5, 7, 19, 1, 0, 1, 0, 1, 0, 8, "s1 64->32 per-tile shift"},
+            {1, 32, 1, 4, 6, 20, 1, 0, 0, 1, 0, 1, 8, "s1 32->1 per-tile shift"},
         };
         { int idx = 0; for (auto& c : cases) { if (g_only < 0 || g_only == idx) { Case cc = c; cc.variant |= g_level << 8; fails += run_case(cc, false, 0); } ++idx; } }
     }
@@ -242,6 +253,9 @@ int main(int argc, char** argv) {
             {1, 64, 32, 48, 96, 312, 1, 0, 1, 0, 1, 0, 2, "dres0.0 64->32 per-tap"},
             {1, 32, 32, 48, 96, 312, 1, 0, 1, 1, 1, 0, 2, "32->32 per-tap"},
             {1, 64, 64, 24, 48, 156, 1, 0, 1, 1, 1, 0, 2, "conv2 64->64 per-tap"},
+            {1, 64, 32, 48, 96, 312, 1, 0, 1, 0, 1, 0, 8, "dres0.0 64->32 per-tile shift"},
+            {1, 32, 32, 48, 96, 312, 1, 0, 1, 1, 1, 0, 8, "32->32 per-tile shift"},
+            {1, 32, 1, 48, 96, 312, 1, 0, 0, 1, 0, 1, 8, "classif 32->1 per-tile shift"},
         };
         { int idx = 0; for (auto& c : cases) { if (g_only < 0 || g_only == idx) { Case cc = c; cc.variant |= g_level << 8; fails += run_case(cc, true, 10); } ++idx; } }
     }

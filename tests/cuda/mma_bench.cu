@@ -1,16 +1,33 @@
-// Micro-benchmark: how many SM cycles does one tcgen05.mma (cta_group::1, kind::f16, M=128, K=16,
-// bf16 K-major operands from shared memory) take as a function of N, of the swizzle mode (row
-// bytes 64 / 128) and of the number of CTAs issuing concurrently on an SM?  Answers SURVEY.md
-// hard part 1 ("micro-benchmark tcgen05 throughput vs N first").  Operand contents are garbage
-// (uninitialised smem): only the issue/retire rate is measured.
+// Micro-benchmark (answers SURVEY.md hard part 1): issue/retire rate of tcgen05.mma
+// (cta_group::1, kind::f16, M=128, K=16, bf16) as a function of N, for
+//   SS : A and B from shared memory (K-major, swizzled rows of 64/128 bytes)
+//   TS : A from tensor memory, B from shared memory
+// and of tcgen05.cp 128x256b (shared -> tensor memory, one 128x16 bf16 A slab).
+// The issue loop is unrolled x8 with pre-built descriptors so that the single issuing thread is not
+// the limit.  Operand contents are garbage: only rates are measured.
 //   build: make tests/cuda/mma_bench ; run: tests/cuda/mma_bench
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
 #include "../../dsmnet_b200/csrc/ptx.cuh"
 
-template <int N, int ROWB>
-__global__ void __launch_bounds__(64) mma_rate_kernel(long long* cycles, int n_mma, int distinct) {
+namespace {
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t sdesc) {
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" :: "r"(taddr), "l"(sdesc) : "memory");
+}
+}
+
+enum { SS = 0, TS = 1, CP = 2, TS_CP = 3 };
+
+template <int N, int ROWB, int MODE>
+__global__ void __launch_bounds__(64) rate_kernel(long long* cycles, int n_iter) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = ptx::smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -18,22 +35,37 @@ __global__ void __launch_bounds__(64) mma_rate_kernel(long long* cycles, int n_m
     __shared__ uint32_t slot;
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) { ptx::mbar_init(ptx::smem_u32(&bar), 1); ptx::fence_mbar_init(); }
-    if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(&slot), 256);
+    if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(&slot), 512);
     ptx::tc_fence_before(); __syncthreads(); ptx::tc_fence_after();
     const uint32_t tmem = slot;
     if (warp == 0) {
         constexpr uint32_t idesc = ptx::make_idesc_bf16(N);
-        const uint32_t a_bytes = 128 * ROWB, b_bytes = N * ROWB;
+        constexpr uint32_t a_bytes = 128 * ROWB, b_bytes = N * ROWB;
+        const uint32_t sa = base, sb = base + 2 * a_bytes;
+        // 8 operand variants: 2 tiles x (ROWB/32) K-slabs, cycled
+        uint64_t ad[8], bd[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const uint32_t tile = (u >> 1) & 1, slab = u % (ROWB / 32);
+            ad[u] = ptx::make_kmajor_desc(sa + tile * a_bytes + slab * 32, ROWB, 0u);
+            bd[u] = ptx::make_kmajor_desc(sb + tile * b_bytes + slab * 32, ROWB, 0u);
+        }
         long long t0 = 0, t1 = 0;
         __syncwarp();
         t0 = clock64();
         if (ptx::elect_one_sync()) {
-            for (int i = 0; i < n_mma; ++i) {
-                // `distinct` operand tiles are cycled so that reads do not all hit the same smem lines
-                const uint32_t sa = base + (i % distinct) * (a_bytes + b_bytes);
-                const uint64_t ad = ptx::make_kmajor_desc(sa + (i & ((ROWB / 32) - 1)) * 32, ROWB, 0u);
-                const uint64_t bd = ptx::make_kmajor_desc(sa + a_bytes + (i & ((ROWB / 32) - 1)) * 32, ROWB, 0u);
-                ptx::umma_bf16(tmem + (i & 1) * N % 256, ad, bd, idesc, 1u);
+            for (int i = 0; i < n_iter; ++i) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t d = tmem + (u & 1) * 256;            // two accumulators, alternating
+                    if (MODE == SS) ptx::umma_bf16(d, ad[u], bd[u], idesc, 1u);
+                    if (MODE == TS) umma_bf16_ts(d, tmem + 480 + (u & 1) * 8, bd[u], idesc, 1u);
+                    if (MODE == CP) tmem_cp_128x256b(tmem + 448 + (u & 3) * 8, ad[u]);
+                    if (MODE == TS_CP) {                                // one cp feeds three MMAs (the intended reuse)
+                        if (u % 3 == 0) tmem_cp_128x256b(tmem + 448 + ((u / 3) & 3) * 8, ad[u]);
+                        umma_bf16_ts(d, tmem + 448 + ((u / 3) & 3) * 8, bd[u], idesc, 1u);
+                    }
+                }
             }
             ptx::umma_commit(ptx::smem_u32(&bar));
         }
@@ -43,35 +75,40 @@ __global__ void __launch_bounds__(64) mma_rate_kernel(long long* cycles, int n_m
         if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
     }
     ptx::tc_fence_before(); __syncthreads();
-    if (warp == 1) ptx::tmem_dealloc(tmem, 256);
+    if (warp == 1) ptx::tmem_dealloc(tmem, 512);
 }
 
-template <int N, int ROWB>
-void run(int ctas_per_sm, int distinct) {
-    const int n_mma = 4096;
+template <int N, int ROWB, int MODE>
+void run(const char* what) {
+    const int n_iter = 512;
     int nsm = 148; cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
-    const int grid = nsm * ctas_per_sm;
-    const size_t smem = (size_t)distinct * (128 * ROWB + N * ROWB) + 2048;
-    auto k = mma_rate_kernel<N, ROWB>;
+    const size_t smem = (size_t)2 * (128 * ROWB + N * ROWB) + 2048;
+    auto k = rate_kernel<N, ROWB, MODE>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    long long* d; cudaMalloc(&d, grid * sizeof(long long));
-    k<<<grid, 64, smem>>>(d, n_mma, distinct);
-    k<<<grid, 64, smem>>>(d, n_mma, distinct);
+    long long* d; cudaMalloc(&d, nsm * sizeof(long long));
+    k<<<nsm, 64, smem>>>(d, n_iter);
+    k<<<nsm, 64, smem>>>(d, n_iter);
     cudaError_t e = cudaDeviceSynchronize();
-    long long h[1024]; cudaMemcpy(h, d, grid * sizeof(long long), cudaMemcpyDeviceToHost);
-    double mx = 0; for (int i = 0; i < grid; ++i) mx = h[i] > mx ? h[i] : mx;
-    const double cyc = mx / n_mma;                         // per MMA per CTA
-    const double flop_per_clk_sm = 2.0 * 128 * N * 16 * ctas_per_sm / cyc;
-    printf("N=%3d rowB=%3d ctas/SM=%d distinct=%d : %6.1f cyc/MMA/CTA  -> %6.0f flop/clk/SM (%s)\n", N, ROWB, ctas_per_sm, distinct,
-           cyc, flop_per_clk_sm, cudaGetErrorString(e));
+    long long h[1024]; cudaMemcpy(h, d, nsm * sizeof(long long), cudaMemcpyDeviceToHost);
+    double mx = 0; for (int i = 0; i < nsm; ++i) mx = h[i] > mx ? h[i] : mx;
+    const double cyc = mx / (n_iter * 8.0);
+    const double flop = (MODE == CP) ? 0.0 : 2.0 * 128 * N * 16 / cyc;
+    printf("%-6s N=%3d rowB=%3d : %6.1f cyc/op -> %6.0f flop/clk/SM (%s)\n", what, N, ROWB, cyc, flop, cudaGetErrorString(e));
     cudaFree(d);
 }
 
-int main() {
+int main(int argc, char** argv) {
     setvbuf(stdout, nullptr, _IONBF, 0);
-    run<16, 64>(1, 2);  run<32, 64>(1, 2);  run<32, 128>(1, 2); run<64, 128>(1, 2); run<96, 128>(1, 2);
-    run<128, 128>(1, 2); run<192, 128>(1, 2); run<256, 128>(1, 2);
-    run<32, 64>(2, 2);  run<32, 128>(2, 2); run<64, 128>(2, 2); run<96, 128>(2, 2); run<128, 128>(2, 2); run<256, 128>(2, 2);
-    run<32, 128>(1, 1); run<32, 128>(1, 4); run<96, 64>(1, 2); run<96, 64>(2, 2);
+    const int what = argc > 1 ? atoi(argv[1]) : 0;
+    if (what == 0 || what == 1) {
+        run<32, 64, SS>("SS");   run<64, 64, SS>("SS");   run<96, 64, SS>("SS");  run<128, 64, SS>("SS");
+        run<32, 128, SS>("SS");  run<48, 64, SS>("SS");   run<64, 128, SS>("SS");  run<96, 128, SS>("SS"); run<128, 128, SS>("SS");
+        run<192, 128, SS>("SS"); run<256, 128, SS>("SS");
+    }
+    if (what == 0 || what == 2) {
+        run<32, 64, TS>("TS");   run<64, 64, TS>("TS");   run<96, 64, TS>("TS");   run<32, 128, TS>("TS"); run<128, 128, TS>("TS");
+    }
+    if (what == 0 || what == 3) { run<32, 64, CP>("CP");  run<32, 128, CP>("CP"); }
+    if (what == 0 || what == 4) { run<32, 64, TS_CP>("TS+CP"); run<32, 128, TS_CP>("TS+CP"); run<64, 128, TS_CP>("TS+CP"); }
     return 0;
 }
