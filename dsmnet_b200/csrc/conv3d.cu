@@ -377,6 +377,11 @@ conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
 // 32->32, 110 KB for 64->32); only 130-row activation tiles (the three kw taps are row-shifted
 // descriptors into the same tile) stream through the TMA ring: (R+2)*3 tile loads per R*128
 // output voxels instead of 27 (or 9) per 128.
+// Issue rate: these MMAs are short (56 cycles at N=96), and one warp cannot prepare descriptors and
+// issue faster than ~76 cycles per MMA (measured), so THREE warps issue, one per kh tap.  MMAs from
+// different threads are not ordered against each other; that is harmless because every MMA
+// accumulates — the epilogue warps hand each accumulator block back zero-filled (tcgen05.st), so
+// there is no "first MMA overwrites" case and the sum commutes.
 // ---------------------------------------------------------------------------------------------
 struct RsGeom {
     int B, D, H, W;          // extent (stride 1: input == natural output extent)
@@ -385,6 +390,7 @@ struct RsGeom {
     int plane_tiles;         // ceil(Hp*Wp / 128)
     int nbands;              // ceil(Do / R)
     int nitems;              // B * nbands * plane_tiles
+    int dbg;                 // timing experiments only (variant bits 4..6): 1 = no epilogue work, 2 = no TMA traffic, 4 = no MMAs
     int w_row[27];           // first row of tap (kd*3+kh)*3+kw in the packed weights
 };
 
@@ -406,7 +412,7 @@ struct RsCfg {
     static constexpr int ACC_COLS = R * NP;
     static constexpr int TMEM_COLS = 2 * ACC_COLS;                // 256 (NP=16) or 512 (NP=32)
     static constexpr int SMEM = W_BYTES + STAGES * STAGE_BYTES + 1024 + BAR_BYTES + 2 * NP * 4;
-    static constexpr int THREADS = 320;                           // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+    static constexpr int THREADS = 384;                           // warp 0 TMA, warps 1-3 MMA (kh = 0,1,2), warps 4-11 epilogue
     static_assert(STAGES >= 4, "activation ring too shallow");
     static_assert((W_TILE % 1024) == 0 && ((NP * ROWB) % 1024) == 0, "weight sub-tiles must keep the swizzle phase");
 };
@@ -423,7 +429,7 @@ __device__ __forceinline__ RsItem rs_decode(const RsGeom& g, int t, int R) {
 }
 
 template <int KC, int NP>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(384, 1)
 conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                  const __grid_constant__ RsGeom g, const float* __restrict__ scale, const float* __restrict__ shift,
                  const void* __restrict__ residual, void* __restrict__ y) {
@@ -458,8 +464,8 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_w);
         ptx::prefetch_tensormap(&map_a);
-        for (int s = 0; s < C::STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; ++a) { ptx::mbar_init(tfull_bar(a), 1); ptx::mbar_init(tempty_bar(a), 8); }
+        for (int s = 0; s < C::STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), C::KHS); }
+        for (int a = 0; a < 2; ++a) { ptx::mbar_init(tfull_bar(a), 3); ptx::mbar_init(tempty_bar(a), 8); }
         ptx::mbar_init(wfull_bar, 1);
         ptx::fence_mbar_init();
     }
@@ -490,19 +496,24 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 for (int khs = 0; khs < 3 / C::KHS; ++khs) {
                     wait_bar(empty_bar(s), ph ^ 1u);
                     if (ptx::elect_one_sync()) {
-                        ptx::mbar_arrive_expect_tx(full_bar(s), C::TX_BYTES);
+                        if (g.dbg & 2) {
+                            ptx::mbar_arrive(full_bar(s));
+                        } else {
+                            ptx::mbar_arrive_expect_tx(full_bar(s), C::TX_BYTES);
 #pragma unroll
-                        for (int kk = 0; kk < C::KHS; ++kk)
-                            ptx::tma_load_2d(ring + s * C::STAGE_BYTES + kk * C::A_BYTES, &map_a, full_bar(s), 0,
-                                             row0 + (khs * C::KHS + kk) * Wp);
+                            for (int kk = 0; kk < C::KHS; ++kk)
+                                ptx::tma_load_2d(ring + s * C::STAGE_BYTES + kk * C::A_BYTES, &map_a, full_bar(s), 0,
+                                                 row0 + (khs * C::KHS + kk) * Wp);
+                        }
                     }
                     __syncwarp();
                     if (++s == C::STAGES) { s = 0; ph ^= 1u; }
                 }
             }
         }
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
+    } else if (warp <= 3) {
+        // ================= MMA issuers: warp w issues the taps with kh = w-1 =================
+        const int my_kh = warp - 1;
         constexpr uint32_t idesc0 = ptx::make_idesc_bf16(0);
         wait_bar(wfull_bar, 0);
         ptx::tc_fence_after();
@@ -510,18 +521,18 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const uint64_t dsc = ptx::make_kmajor_desc(0u, C::ROWB, 0u);
         const uint32_t desc_hi = (uint32_t)(dsc >> 32);
         const uint32_t ring_lo = (uint32_t)dsc | (ring >> 4);
-        const uint32_t w_lo = (uint32_t)dsc | (wsm >> 4);
+        const uint32_t w_lo = ((uint32_t)dsc | (wsm >> 4)) + (uint32_t)((my_kh * 3 * C::W_TILE) >> 4);
+        const uint32_t a_tile = (C::KHS == 3) ? (uint32_t)((my_kh * C::A_BYTES) >> 4) : 0u;
         int s = 0; uint32_t ph = 0;
         int tcount = 0;
         for (int t = blockIdx.x; t < g.nitems; t += gridDim.x) {
             const RsItem item = rs_decode(g, t, C::R);
             const int acc = tcount & 1;
-            const uint32_t acc_ph = (uint32_t)(tcount >> 1) & 1u;
+            const uint32_t use_ph = (uint32_t)(tcount >> 1) & 1u;
             ++tcount;
-            wait_bar(tempty_bar(acc), acc_ph ^ 1u);
+            wait_bar(tempty_bar(acc), use_ph);                   // drained AND zero-filled by the epilogue warps
             ptx::tc_fence_after();
             const uint32_t d_tmem = tmem + acc * C::ACC_COLS;
-            int nt = 0;                                          // accumulator blocks [0, nt) already hold data
             int last_i = item.nb;
             if (item.z0 + 1 + last_i >= Dp - 1) --last_i;        // trailing rim plane is skipped
             for (int i = -1; i <= item.nb; ++i) {
@@ -531,46 +542,30 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 const int brow = (2 - (i - jlo + 1)) * NP;        // weight row of block jlo's tap (kd = i-jlo+1)
                 const uint32_t d_lo = d_tmem + jlo * NP;
                 const uint32_t idesc = idesc0 | ((uint32_t)((jhi - jlo + 1) * NP >> 3) << 17);
-                const uint32_t b_lo_plane = w_lo + ((uint32_t)(brow * C::ROWB) >> 4);
+                const uint32_t b_lo0 = w_lo + ((uint32_t)(brow * C::ROWB) >> 4);
 #pragma unroll
                 for (int khs = 0; khs < 3 / C::KHS; ++khs) {
-                    wait_bar(full_bar(s), ph);
-                    ptx::tc_fence_after();
-                    if (ptx::elect_one_sync()) {
-                        const uint32_t a_lo0 = ring_lo + (uint32_t)s * (C::STAGE_BYTES >> 4);
+                    if (C::KHS == 3 || khs == my_kh) {
+                        wait_bar(full_bar(s), ph);
+                        ptx::tc_fence_after();
+                        if (ptx::elect_one_sync()) {
+                            const uint32_t a_lo0 = ring_lo + (uint32_t)s * (C::STAGE_BYTES >> 4) + a_tile;
+                            if (!(g.dbg & 4)) {
 #pragma unroll
-                        for (int kk = 0; kk < C::KHS; ++kk) {
-                            const int kh = khs * C::KHS + kk;
+                                for (int kw = 0; kw < 3; ++kw) {
 #pragma unroll
-                            for (int kw = 0; kw < 3; ++kw) {
-#pragma unroll
-                                for (int k = 0; k < KC / 16; ++k) {
-                                    const uint32_t a_lo = a_lo0 + ((kk * C::A_BYTES + kw * C::ROWB + k * 32) >> 4);
-                                    const uint32_t b_lo = b_lo_plane + (((kh * 3 + kw) * C::W_TILE + k * 32) >> 4);
-                                    if (kh == 0 && kw == 0 && k == 0) {
-                                        if (jhi >= nt) {
-                                            // first touch of block(s) [max(nt,jlo), jhi]: overwrite instead of accumulate
-                                            if (jlo < nt)
-                                                ptx::umma_bf16_lohi(d_lo, a_lo, b_lo, desc_hi, idesc0 | ((uint32_t)((nt - jlo) * NP >> 3) << 17), 1u);
-                                            const int f0 = max(nt, jlo);
-                                            ptx::umma_bf16_lohi(d_tmem + f0 * NP, a_lo, b_lo + ((uint32_t)((f0 - jlo) * NP * C::ROWB) >> 4), desc_hi,
-                                                                idesc0 | ((uint32_t)((jhi - f0 + 1) * NP >> 3) << 17), 0u);
-                                        } else {
-                                            ptx::umma_bf16_lohi(d_lo, a_lo, b_lo, desc_hi, idesc, 1u);
-                                        }
-                                    } else {
-                                        ptx::umma_bf16_lohi(d_lo, a_lo, b_lo, desc_hi, idesc, 1u);
-                                    }
+                                    for (int k = 0; k < KC / 16; ++k)
+                                        ptx::umma_bf16_lohi(d_lo, a_lo0 + ((kw * C::ROWB + k * 32) >> 4),
+                                                            b_lo0 + ((kw * C::W_TILE + k * 32) >> 4), desc_hi, idesc, 1u);
                                 }
                             }
+                            ptx::umma_commit(empty_bar(s));
+                            if (i == last_i) ptx::umma_commit(tfull_bar(acc));
                         }
-                        ptx::umma_commit(empty_bar(s));
-                        if (i == last_i && khs == 3 / C::KHS - 1) ptx::umma_commit(tfull_bar(acc));
+                        __syncwarp();
                     }
-                    __syncwarp();
                     if (++s == C::STAGES) { s = 0; ph ^= 1u; }
                 }
-                nt = max(nt, jhi + 1);
             }
         }
     } else {
@@ -579,9 +574,23 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // output planes of the band.  Residual rows are fetched BEFORE waiting for the accumulator so
         // that their DRAM latency hides behind the MMAs of this item.
         const int q = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int half = (warp - 4) >> 2;
         const int r = q * 32 + lane;
         constexpr int JJ = C::R / 2;                              // planes per warp
+        {   // both accumulator buffers start zero-filled; arriving completes phase 0 of their "free" barriers
+#pragma unroll
+            for (int a2 = 0; a2 < 2; ++a2) {
+#pragma unroll
+                for (int jj = 0; jj < JJ; ++jj) {
+                    const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + a2 * C::ACC_COLS + (2 * jj + half) * NP;
+                    if (NP == 32) ptx::tmem_zero32(ta); else ptx::tmem_zero16(ta);
+                }
+            }
+            ptx::tc_wait_st();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { ptx::mbar_arrive(tempty_bar(0)); ptx::mbar_arrive(tempty_bar(1)); }
+        }
         constexpr int NV = NP / 8;                                // uint4 per bf16 output row
         const float4* sc4 = reinterpret_cast<const float4*>(s_scale);
         const float4* sh4 = reinterpret_cast<const float4*>(s_shift);
@@ -597,6 +606,19 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const uint32_t taddr0 = tmem + ((uint32_t)(q * 32) << 16) + acc * C::ACC_COLS;
             int my_last = -1;                                     // my last plane of this band (-1: none)
             for (int jj = 0; jj < JJ; ++jj) if (2 * jj + half < item.nb) my_last = 2 * jj + half;
+            if (g.dbg & 1) {
+                wait_bar(tfull_bar(acc), acc_ph);
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+                continue;
+            }
+            // hand the buffer back: my blocks are in registers and zero-filled again
+            auto release = [&]() {
+                ptx::tc_wait_st();
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+            };
 
             if (g.y_f32) {
                 // single output channel: fp32, unpadded [B][Do][Ho][Wo]
@@ -611,7 +633,7 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 wait_bar(tfull_bar(acc), acc_ph);
                 __syncwarp();
                 ptx::tc_fence_after();
-                if (my_last < 0) { ptx::tc_fence_before(); __syncwarp(); if (lane == 0) ptx::mbar_arrive(tempty_bar(acc)); }
+                if (my_last < 0) release();
 #pragma unroll
                 for (int jj = 0; jj < JJ; ++jj) {
                     const int j = 2 * jj + half;
@@ -620,7 +642,8 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         ptx::tmem_ld16(taddr0 + j * NP, v);
                         ptx::tc_wait_ld();
                         consume_tmem_load(v[0], scratch_smem);
-                        if (j == my_last) { ptx::tc_fence_before(); __syncwarp(); if (lane == 0) ptx::mbar_arrive(tempty_bar(acc)); }
+                        ptx::tmem_zero16(taddr0 + j * NP);
+                        if (j == my_last) release();
                         if (valid) {
                             float a = fmaf(__uint_as_float(v[0]), s_scale[0], s_shift[0]) + rf[jj];
                             if (g.relu) a = fmaxf(a, 0.f);
@@ -644,7 +667,7 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 wait_bar(tfull_bar(acc), acc_ph);
                 __syncwarp();
                 ptx::tc_fence_after();
-                if (my_last < 0) { ptx::tc_fence_before(); __syncwarp(); if (lane == 0) ptx::mbar_arrive(tempty_bar(acc)); }
+                if (my_last < 0) release();
 #pragma unroll
                 for (int jj = 0; jj < JJ; ++jj) {
                     const int j = 2 * jj + half;
@@ -653,7 +676,8 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         if (NP == 32) ptx::tmem_ld32(taddr0 + j * NP, v); else ptx::tmem_ld16(taddr0 + j * NP, v);
                         ptx::tc_wait_ld();
                         consume_tmem_load(v[0], scratch_smem);
-                        if (j == my_last) { ptx::tc_fence_before(); __syncwarp(); if (lane == 0) ptx::mbar_arrive(tempty_bar(acc)); }
+                        if (NP == 32) ptx::tmem_zero32(taddr0 + j * NP); else ptx::tmem_zero16(taddr0 + j * NP);
+                        if (j == my_last) release();
                         if (valid) {
                             uint4* out = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y) + o0 + j * ostep);
 #pragma unroll
@@ -817,6 +841,7 @@ int conv3d_dispatch(const void* x, const void* w, const float* scale, const floa
         const long long ni = (long long)B * rg.nbands * rg.plane_tiles;
         if (ni > 0x7fffffffLL) return DSM_EUNSUPPORTED;
         rg.nitems = (int)ni;
+        rg.dbg = (variant >> 4) & 7;
         for (int t = 0; t < 27; ++t) rg.w_row[t] = t * NP;
         cudaStream_t st = (cudaStream_t)stream;
         if (KC == 32 && NP == 16) return launch_rs<32, 16>(map_a, maps.w, rg, scale, shift, residual, y, st);

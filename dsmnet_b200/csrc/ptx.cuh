@@ -121,6 +121,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
         : "r"(taddr));
 }
 
+// zero 32 lanes x 32 consecutive columns (the accumulator block this warp just drained)
+__device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
+    const uint32_t z = 0u;
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};"
+        :: "r"(taddr), "r"(z) : "memory");
+}
+__device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
+    const uint32_t z = 0u;
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};"
+        :: "r"(taddr), "r"(z) : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // ---- descriptors --------------------------------------------------------------------------
 // Shared-memory matrix descriptor, K-major operand, rows of `row_bytes` (64 -> SWIZZLE_64B,
 // 128 -> SWIZZLE_128B), 8-row groups densely packed (SBO = 8*row_bytes).  Field layout as in

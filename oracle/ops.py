@@ -410,7 +410,7 @@ def calibrate_bn_(params: Dict[str, torch.Tensor], cost: torch.Tensor) -> None:
         cb(c + ".0", x, relu=True)
 
 
-def psmnet_matcher_params(seed: int = 0, noise: float = 0.3, sharpness: float = 0.5) -> Dict[str, torch.Tensor]:
+def psmnet_matcher_params(seed: int = 0, noise: float = 0.15, sharpness: float = 1.0) -> Dict[str, torch.Tensor]:
     """Synthetic parameters that make the PSMNet 3-D stack an actual (crude) stereo matcher, so that
     an end-point error against a known disparity is a meaningful number (the north_star's bf16
     tolerance is stated on mean EPE; with purely random weights the EPE is tens of pixels and

@@ -259,6 +259,15 @@ int main(int argc, char** argv) {
         };
         { int idx = 0; for (auto& c : cases) { if (g_only < 0 || g_only == idx) { Case cc = c; cc.variant |= g_level << 8; fails += run_case(cc, true, 10); } ++idx; } }
     }
+    if (!strcmp(what, "dbg")) {
+        // timing experiments on the plane-sharing kernel (results are garbage): which part of the pipeline bounds it?
+        for (int v : {0, 16, 32, 64, 48, 80, 96, 112}) {
+            Case c = {1, 32, 32, 48, 96, 312, 1, 0, 1, 1, 1, 0, v, "32->32 dbg"};
+            run_case(c, true, 10);
+            Case c2 = {1, 64, 32, 48, 96, 312, 1, 0, 1, 0, 1, 0, v, "64->32 dbg"};
+            run_case(c2, true, 10);
+        }
+    }
     printf("SELFTEST %s: %d failing case(s), timeouts=%d\n", what, fails, dsm_debug_conv_timeouts());
     return fails ? 1 : 0;
 }

@@ -26,7 +26,7 @@ __device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t sdesc)
 
 enum { SS = 0, TS = 1, CP = 2, TS_CP = 3 };
 
-template <int N, int ROWB, int MODE>
+template <int N, int ROWB, int MODE, int ASHIFT = 0>
 __global__ void __launch_bounds__(64) rate_kernel(long long* cycles, int n_iter) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = ptx::smem_u32(smem_raw);
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(64) rate_kernel(long long* cycles, int n_iter)
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const uint32_t tile = (u >> 1) & 1, slab = u % (ROWB / 32);
-            ad[u] = ptx::make_kmajor_desc(sa + tile * a_bytes + slab * 32, ROWB, 0u);
+            ad[u] = ptx::make_kmajor_desc(sa + tile * a_bytes + slab * 32 + (ASHIFT % 100) * ROWB, ROWB, 0u);   // ASHIFT rows into the swizzle atom
             bd[u] = ptx::make_kmajor_desc(sb + tile * b_bytes + slab * 32, ROWB, 0u);
         }
         long long t0 = 0, t1 = 0;
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(64) rate_kernel(long long* cycles, int n_iter)
             for (int i = 0; i < n_iter; ++i) {
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const uint32_t d = tmem + (u & 1) * 256;            // two accumulators, alternating
+                    const uint32_t d = tmem + ((ASHIFT >= 100) ? 0 : (u & 1) * 256);   // two accumulators, alternating (ASHIFT>=100: one)
                     if (MODE == SS) ptx::umma_bf16(d, ad[u], bd[u], idesc, 1u);
                     if (MODE == TS) umma_bf16_ts(d, tmem + 480 + (u & 1) * 8, bd[u], idesc, 1u);
                     if (MODE == CP) tmem_cp_128x256b(tmem + 448 + (u & 3) * 8, ad[u]);
@@ -78,12 +78,12 @@ __global__ void __launch_bounds__(64) rate_kernel(long long* cycles, int n_iter)
     if (warp == 1) ptx::tmem_dealloc(tmem, 512);
 }
 
-template <int N, int ROWB, int MODE>
+template <int N, int ROWB, int MODE, int ASHIFT = 0>
 void run(const char* what) {
     const int n_iter = 512;
     int nsm = 148; cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
-    const size_t smem = (size_t)2 * (128 * ROWB + N * ROWB) + 2048;
-    auto k = rate_kernel<N, ROWB, MODE>;
+    const size_t smem = (size_t)2 * (128 * ROWB + N * ROWB) + 2048 + 8 * ROWB;
+    auto k = rate_kernel<N, ROWB, MODE, ASHIFT>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     long long* d; cudaMalloc(&d, nsm * sizeof(long long));
     k<<<nsm, 64, smem>>>(d, n_iter);
@@ -109,6 +109,14 @@ int main(int argc, char** argv) {
         run<32, 64, TS>("TS");   run<64, 64, TS>("TS");   run<96, 64, TS>("TS");   run<32, 128, TS>("TS"); run<128, 128, TS>("TS");
     }
     if (what == 0 || what == 3) { run<32, 64, CP>("CP");  run<32, 128, CP>("CP"); }
+    if (what == 0 || what == 5) {   // A tile read through a descriptor that starts 1 / 2 / 4 rows into a swizzle atom
+        run<96, 64, SS, 1>("SS+1r"); run<96, 64, SS, 2>("SS+2r"); run<96, 64, SS, 4>("SS+4r"); run<32, 64, SS, 1>("SS+1r");
+        run<96, 128, SS, 1>("SS+1r"); run<96, 128, SS, 2>("SS+2r"); run<96, 128, SS, 4>("SS+4r");
+    }
+    if (what == 0 || what == 6) {   // every MMA accumulates into the SAME columns (dependent chain), as in a real K loop
+        run<32, 64, SS, 100>("SS-dep"); run<64, 64, SS, 100>("SS-dep"); run<96, 64, SS, 100>("SS-dep"); run<128, 128, SS, 100>("SS-dep");
+        run<256, 128, SS, 100>("SS-dep"); run<32, 64, TS, 100>("TS-dep"); run<96, 64, TS, 100>("TS-dep");
+    }
     if (what == 0 || what == 4) { run<32, 64, TS_CP>("TS+CP"); run<32, 128, TS_CP>("TS+CP"); run<64, 128, TS_CP>("TS+CP"); }
     return 0;
 }
