@@ -168,7 +168,7 @@ def run_native(args, rank, world, local_rank):
     host_R = torch.randn(B, C_FEAT, h, w, generator=g).pin_memory()
     fL = host_L.to(device); fR = host_R.to(device)
     host_out = [torch.empty(B, H_IMG, W_IMG).pin_memory() for _ in range(3)]
-    launches_per_step = 1 + 28 + 3              # concat volume, 28 conv blocks, 3 heads
+    launches_per_step = 1 + 28 + 1              # concat volume, 28 conv blocks, one launch for the three heads
 
     def step():
         with torch.no_grad():
@@ -244,7 +244,7 @@ def run_native(args, rank, world, local_rank):
     ms_k = time_kernel_alone(lambda: layer(ws["a"], ws["c0"]))
     flops = 2.0 * 27 * 32 * 32 * B * (MAXDISP // 4) * h * w
     achieved = flops / (ms_k * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "conv3d_igemm_kernel<KC=32,N=32> (Conv3d 32->32 k3 s1 @48x96x312, 7 launches/step)",
+    roofline = {"bound": "tensor", "kernel": "conv3d_rs_kernel<KC=32,NP=32> (Conv3d 32->32 k3 s1 + BN + ReLU @48x96x312, 7 launches/step)",
                 "achieved": achieved, "peak": tf_burst, "unit": "TFLOP/s", "frac": achieved / tf_burst,
                 "peak_source": which + " bf16 burst (kernel timed alone)", "ms_per_launch": ms_k, "traffic": None}
 
@@ -256,8 +256,11 @@ def run_native(args, rank, world, local_rank):
                          (SAMPLE_ROWS, H_IMG, dt, H_IMG // SAMPLE_ROWS)}
 
     pairs = B * world * args.steps
-    act_bytes = sum(v.data.numel() * 2 for k, v in ws.items() if hasattr(v, "data") and not isinstance(v, list)) + \
-        sum(x.data.numel() * 2 for k in ("out", "pre", "post") for x in ws[k])
+    def nbytes(v):
+        t = v if isinstance(v, torch.Tensor) else v.data
+        return t.numel() * t.element_size()
+    act_bytes = sum(nbytes(v) for k, v in ws.items() if not isinstance(v, list)) + \
+        sum(nbytes(x) for k in ("out", "pre", "post") for x in ws[k])
     line = {"metric": METRIC, "value": pairs / (t_ms / 1e3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",

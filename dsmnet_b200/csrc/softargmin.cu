@@ -130,60 +130,85 @@ __device__ __forceinline__ void src_index(int dst, float scale, int in_size, int
     i1 = min(i0 + 1, in_size - 1);
 }
 
-// MAXDL: the low-res depth extent is kept in registers (template bound), D-axis source index and
-// weight come from a per-CTA shared table.  Since a linear interpolation never exceeds its end
-// points, max_d of the upsampled column <= max_dl of the bilinearly interpolated low-res column:
-// that maximum is known before the D loop, so the softmax is a single pass with one ex2 per d.
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// One CTA = 128 consecutive output pixels of one output row.  MAXDL bounds the low-res depth so
+// that the interpolated column lives in registers.
+//  1. tables (shared): l1[d] = D-axis interpolation weight of output plane d, cnt[dl] = how many
+//     output planes have low-res source plane dl (they are consecutive in d);
+//  2. the low-res row pair (h0,h1) the output row falls between is blended ONCE per CTA into shared
+//     memory: row[dl][j] for the ~0.25*128+2 low-res columns the CTA touches (coalesced reads);
+//  3. each thread blends its two columns -> c[dl] (registers), takes the max (a linear interpolation
+//     never exceeds its end points, so max_d of the upsampled column <= max_dl c[dl]: the softmax is a
+//     single pass), pre-scales by log2(e), and walks the D planes: one FMA + one ex2 + two
+//     accumulations per plane.
 template <int MAXDL>
 __global__ void __launch_bounds__(128)
 upsample_softargmin_kernel(const float* __restrict__ cost, float* __restrict__ disp,
                            int Dl, int Hl, int Wl, int D, int H, int W,
-                           float sd, float sh, float sw, int align_corners) {
-    extern __shared__ __align__(8) unsigned char smem_raw[];
-    int* s_d0 = reinterpret_cast<int*>(smem_raw);            // [D]
-    float* s_l1 = reinterpret_cast<float*>(s_d0 + D);        // [D]
-    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+                           float sd, float sh, float sw, int align_corners, int rw) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* s_l1 = reinterpret_cast<float*>(smem_raw);        // [D]
+    int* s_cnt = reinterpret_cast<int*>(s_l1 + D);           // [MAXDL]
+    float* s_row = reinterpret_cast<float*>(s_cnt + MAXDL);  // [Dl][rw]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < MAXDL; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+    for (int d = tid; d < D; d += blockDim.x) {
         int d0, d1; float l1;
         src_index(d, sd, Dl, align_corners, d0, d1, l1);
-        s_d0[d] = d0; s_l1[d] = (d1 == d0) ? 0.f : l1;       // clamped top: both taps are the same plane
+        s_l1[d] = (d1 == d0) ? 0.f : l1;                     // clamped top: both taps are the same plane
+        atomicAdd(&s_cnt[d0], 1);
     }
-    __syncthreads();
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int x0 = blockIdx.x * blockDim.x;
     const int y = blockIdx.y, b = blockIdx.z;
-    if (x >= W) return;
-    int h0, h1, w0, w1; float lh1, lw1;
+    int h0, h1, wb, wb1; float lh1, lwb;
     src_index(y, sh, Hl, align_corners, h0, h1, lh1);
-    src_index(x, sw, Wl, align_corners, w0, w1, lw1);
-    const float lh0 = 1.f - lh1, lw0 = 1.f - lw1;
+    src_index(x0, sw, Wl, align_corners, wb, wb1, lwb);      // first low-res column of this CTA
+    const float lh0 = 1.f - lh1;
     const float* base = cost + (size_t)b * Dl * Hl * Wl;
     const size_t pl = (size_t)Hl * Wl;
-    const int o00 = h0 * Wl + w0, o01 = h0 * Wl + w1, o10 = h1 * Wl + w0, o11 = h1 * Wl + w1;
+    for (int idx = tid; idx < Dl * rw; idx += blockDim.x) {
+        const int dl = idx / rw, j = idx - dl * rw;
+        const int wl = min(wb + j, Wl - 1);
+        const float* p = base + (size_t)dl * pl + wl;
+        s_row[idx] = lh0 * __ldg(p + (size_t)h0 * Wl) + lh1 * __ldg(p + (size_t)h1 * Wl);
+    }
+    __syncthreads();
+    const int x = x0 + tid;
+    if (x >= W) return;
+    int w0, w1; float lw1;
+    src_index(x, sw, Wl, align_corners, w0, w1, lw1);
+    const float lw0 = 1.f - lw1;
+    const int j0 = w0 - wb, j1 = w1 - wb;
     float c[MAXDL + 1];
     float m = -INFINITY;
 #pragma unroll
     for (int dl = 0; dl < MAXDL; ++dl) {
         if (dl < Dl) {
-            const float* p = base + (size_t)dl * pl;
-            c[dl] = lh0 * (lw0 * __ldg(p + o00) + lw1 * __ldg(p + o01)) + lh1 * (lw0 * __ldg(p + o10) + lw1 * __ldg(p + o11));
+            c[dl] = lw0 * s_row[dl * rw + j0] + lw1 * s_row[dl * rw + j1];
             m = fmaxf(m, c[dl]);
         } else c[dl] = 0.f;
     }
     c[MAXDL] = 0.f;
     constexpr float LOG2E = 1.4426950408889634f;
     const float ml = m * LOG2E;
-    float s = 0.f, t = 0.f;
-    // walk the low-res intervals; the table tells which output planes fall into each
+#pragma unroll
+    for (int dl = 0; dl <= MAXDL; ++dl) c[dl] = fmaf(c[dl], LOG2E, -ml);
+    float s = 0.f, t = 0.f, fd = 0.f;
     int d = 0;
 #pragma unroll
     for (int dl = 0; dl < MAXDL; ++dl) {
         if (dl < Dl) {
-            const float a0 = c[dl], a1 = c[dl + 1];
-            while (d < D && s_d0[d] == dl) {
-                const float l1 = s_l1[d];
-                const float v = (1.f - l1) * a0 + l1 * a1;
-                const float e = exp2f(fmaf(v, LOG2E, -ml));
-                s += e; t = fmaf((float)d, e, t);
-                ++d;
+            const float a0 = c[dl], da = c[dl + 1] - a0;
+            const int n = s_cnt[dl];
+            for (int k = 0; k < n; ++k, ++d) {
+                const float e = ex2_approx(fmaf(s_l1[d], da, a0));
+                s += e; t = fmaf(fd, e, t); fd += 1.f;
             }
         }
     }
@@ -240,12 +265,15 @@ extern "C" int dsm_upsample_softargmin_fwd(const float* cost_lr, float* disp, in
         if (align_corners) return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
         return (float)in / (float)out;
     };
-    const size_t smem = (size_t)D * (sizeof(int) + sizeof(float));
+    const float sw = scale(Wl, W);
+    const int rw = (int)(sw * 127.f) + 3;                    // low-res columns one 128-pixel CTA can touch
+    const int maxdl = Dl <= 16 ? 16 : (Dl <= 48 ? 48 : 96);
+    const size_t smem = (size_t)D * sizeof(float) + (size_t)maxdl * sizeof(int) + (size_t)Dl * rw * sizeof(float);
     if (smem > 48 * 1024) return DSM_EUNSUPPORTED;
     const dim3 grid(dsm_ceil_div(W, 128), H, B);
     cudaStream_t st = (cudaStream_t)stream;
 #define DSM_UPS(MAXDL) upsample_softargmin_kernel<MAXDL><<<grid, 128, smem, st>>>( \
-        cost_lr, disp, Dl, Hl, Wl, D, H, W, scale(Dl, D), scale(Hl, H), scale(Wl, W), align_corners)
+        cost_lr, disp, Dl, Hl, Wl, D, H, W, scale(Dl, D), scale(Hl, H), sw, align_corners, rw)
     if (Dl <= 16) DSM_UPS(16); else if (Dl <= 48) DSM_UPS(48); else if (Dl <= 96) DSM_UPS(96);
     else return DSM_EUNSUPPORTED;
 #undef DSM_UPS

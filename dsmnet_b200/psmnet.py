@@ -135,8 +135,10 @@ class PSMNetHotPath(nn.Module):
             pre=[P(B, 64, D2, H2, W2, device) for _ in range(3)],
             post=[P(B, 64, D2, H2, W2, device) for _ in range(3)],
             h3=P(B, 64, D4, H4, W4, device), h4=P(B, 64, D4, H4, W4, device),
-            cost=[torch.empty(B, D, H, W, device=device, dtype=torch.float32) for _ in range(3)],
+            # the three classifier outputs in head order (cost3, cost2, cost1): one head launch reads all of them
+            cost_all=torch.empty(3, B, D, H, W, device=device, dtype=torch.float32),
         )
+        ws["cost"] = [ws["cost_all"][2 - i] for i in range(3)]      # cost[i] = cost_{i+1}
         self._ws[key] = ws
         return ws
 
@@ -180,8 +182,13 @@ class PSMNetHotPath(nn.Module):
 
     def forward(self, fL, fR, out_hw):
         c1, c2, c3 = self.aggregate(fL, fR)
+        B, _, H, W = fL.shape
+        ws = self._workspace(B, self.maxdisp // 4, H, W, fL.device)
         size = (self.maxdisp, out_hw[0], out_hw[1])
-        return [upsample_softargmin(c, size, self.align_corners) for c in (c3, c2, c1)]
+        # heads of stackhourglass.py:152-166 for (cost3, cost2, cost1) in ONE launch over the stacked costs
+        stacked = ws["cost_all"].view(3 * B, *ws["cost_all"].shape[2:])
+        preds = upsample_softargmin(stacked, size, self.align_corners).view(3, B, out_hw[0], out_hw[1])
+        return [preds[0], preds[1], preds[2]]
 
 
 # --------------------------------------------------------------------------------------------
