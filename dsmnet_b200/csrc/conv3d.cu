@@ -437,6 +437,8 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Dp = g.D + 2, Hp = g.H + 2, Wp = g.W + 2;
     const int plane = Hp * Wp;
+    long long dbg_c0 = 0; unsigned long long dbg_t0 = 0;
+    if (g_conv_progress && blockIdx.x == 0 && tid == 0) { dbg_c0 = clock64(); dbg_t0 = globaltimer_ns(); }
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = ptx::smem_u32(smem_raw);
@@ -712,6 +714,297 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 1) ptx::tmem_dealloc(tmem, C::TMEM_COLS);
+    if (g_conv_progress && blockIdx.x == 0 && tid == 0) {      // diagnostic: SM cycles and wall ns of CTA 0 -> MHz
+        g_conv_progress[0] = (int)((clock64() - dbg_c0) >> 4);
+        g_conv_progress[1] = (int)((globaltimer_ns() - dbg_t0) >> 4);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Class-sharing kernel for transposed convolutions (k3, s2, p1, output_padding 1) with Cout <= 32.
+//
+// out[2j+p] along each axis takes (p=0) tap k=1 of input j, or (p=1) tap k=2 of input j and tap k=0
+// of input j+1, so the 8 output parity classes are 8 small stride-1 convolutions over the SAME input
+// voxels with 1/2/4/8 taps (27 (class,tap) pairs in all).  The per-class kernel above runs them as
+// 27 N=Cout MMAs per K step, each re-reading a 4 KB A slab.  Here a CTA owns one 128-voxel input tile
+// and ALL 8 classes (8 x NP accumulator columns, two buffers): the input tile at offset
+// (od,oh,ow) in {0,1}^3 is the A operand of every class with p >= o component-wise, and with the
+// classes laid out in Gray-code order (000,001,011,010,110,111,101,100) those sets are 1 or 2
+// contiguous column runs, so the 27 pairs become 10 MMAs per K step with N = 256,128,128,64,64,
+// 64,64,32,32,32 -> 568 cycles instead of 27 x 40.  The four (od,oh) tiles stream through TMA (ow is
+// a row-shifted descriptor); all 27 weight blocks stay resident in shared memory in MMA order.
+// ---------------------------------------------------------------------------------------------
+struct DcOp { short tile, ow, brow, n, dcol, pad; };          // one MMA (per K step)
+
+struct DcGeom {
+    int B, D, H, W;          // INPUT extent
+    int Do, Ho, Wo;          // output buffer extent (<= 2D, 2H, 2W)
+    int Cout, relu, y_f32;
+    int ntiles;              // ceil(P / 128), P = B*Dp*Hp*Wp
+    long long P;
+    int nops;
+    short op_begin[6];       // MMAs of tile a are ops[op_begin[a] .. op_begin[a+1])
+    DcOp ops[12];
+    short w_dst[27], w_src[27];   // weight block -> first smem row, first packed-weight row
+};
+
+__constant__ const int kDcPosClass[8] = {0, 1, 3, 2, 6, 7, 5, 4};   // accumulator block -> parity class (pd<<2|ph<<1|pw)
+
+template <int KC, int NP>
+struct DcCfg {
+    static constexpr int ROWB = KC * 2;
+    static constexpr int A_ROWS = 130;
+    static constexpr int A_BYTES = ((A_ROWS * ROWB + 1023) / 1024) * 1024;
+    static constexpr int W_BYTES = 27 * NP * ROWB;
+    static constexpr int BAR_BYTES = 512;
+    static constexpr int BUDGET = 225 * 1024 - W_BYTES - 1024 - BAR_BYTES - 2 * NP * 4;
+    static constexpr int S_RAW = BUDGET / A_BYTES;
+    static constexpr int STAGES = S_RAW > 8 ? 8 : S_RAW;
+    static constexpr int TX_BYTES = A_ROWS * ROWB;
+    static constexpr int ACC_COLS = 8 * NP;
+    static constexpr int TMEM_COLS = 2 * ACC_COLS;
+    static constexpr int SMEM = W_BYTES + STAGES * A_BYTES + 1024 + BAR_BYTES + 2 * NP * 4;
+    static constexpr int THREADS = 320;                          // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+    static_assert(STAGES >= 4, "activation ring too shallow");
+    static_assert(((NP * ROWB) % 1024) == 0, "weight blocks must keep the swizzle phase");
+};
+
+// tiles that lie completely inside a rim plane (d' = 0 or D+1) read only zeros and store nothing
+__device__ __forceinline__ bool dc_skip(long long p0, long long P, long long plane, long long vol, int Dp) {
+    const long long pl = min(p0 + 127, P - 1);
+    const long long b0 = p0 / vol, b1 = pl / vol;
+    const int dp0 = (int)((p0 - b0 * vol) / plane), dp1 = (int)((pl - b1 * vol) / plane);
+    return b0 == b1 && dp0 == dp1 && (dp0 == 0 || dp0 == Dp - 1);
+}
+
+template <int KC, int NP>
+__global__ void __launch_bounds__(320, 1)
+conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                 const __grid_constant__ DcGeom g, const float* __restrict__ scale, const float* __restrict__ shift,
+                 const void* __restrict__ residual, void* __restrict__ y) {
+    using C = DcCfg<KC, NP>;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int Dp = g.D + 2, Hp = g.H + 2, Wp = g.W + 2;
+    const long long plane = (long long)Hp * Wp, vol = plane * Dp;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = ptx::smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - raw);
+    const uint32_t wsm = base;
+    const uint32_t ring = base + C::W_BYTES;
+    constexpr int RING_END = C::W_BYTES + C::STAGES * C::A_BYTES;
+    const uint32_t bars = base + RING_END;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
+    auto tfull_bar = [&](int a) { return bars + 8u * (2 * C::STAGES + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (2 * C::STAGES + 2 + a); };
+    const uint32_t wfull_bar = bars + 8u * (2 * C::STAGES + 4);
+    constexpr int NBARS = 2 * C::STAGES + 5;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + RING_END + 8 * NBARS);
+    const uint32_t scratch_smem = bars + 8u * NBARS + 8u;
+    float* s_scale = reinterpret_cast<float*>(base_ptr + RING_END + C::BAR_BYTES);
+    float* s_shift = s_scale + NP;
+
+    if (tid < NP) {
+        s_scale[tid] = scale ? __ldg(scale + tid) : 1.f;
+        s_shift[tid] = shift ? __ldg(shift + tid) : 0.f;
+    }
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&map_w);
+        ptx::prefetch_tensormap(&map_a);
+        for (int s = 0; s < C::STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { ptx::mbar_init(tfull_bar(a), 1); ptx::mbar_init(tempty_bar(a), 8); }
+        ptx::mbar_init(wfull_bar, 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), C::TMEM_COLS);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (ptx::elect_one_sync()) {
+            ptx::mbar_arrive_expect_tx(wfull_bar, C::W_BYTES);
+            for (int i = 0; i < 27; ++i)
+                ptx::tma_load_2d(wsm + g.w_dst[i] * C::ROWB, &map_w, wfull_bar, 0, g.w_src[i]);
+        }
+        __syncwarp();
+        int s = 0; uint32_t ph = 0;
+        for (int t = blockIdx.x; t < g.ntiles; t += gridDim.x) {
+            const long long p0 = (long long)t * 128;
+            if (dc_skip(p0, g.P, plane, vol, Dp)) continue;
+#pragma unroll 1
+            for (int a = 0; a < 4; ++a) {                        // (od, oh) = (a>>1, a&1)
+                wait_bar(empty_bar(s), ph ^ 1u);
+                if (ptx::elect_one_sync()) {
+                    ptx::mbar_arrive_expect_tx(full_bar(s), C::TX_BYTES);
+                    ptx::tma_load_2d(ring + s * C::A_BYTES, &map_a, full_bar(s), 0, (int)(p0 + ((a >> 1) * Hp + (a & 1)) * Wp));
+                }
+                __syncwarp();
+                if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        constexpr uint32_t idesc0 = ptx::make_idesc_bf16(0);
+        wait_bar(wfull_bar, 0);
+        ptx::tc_fence_after();
+        const uint64_t dsc = ptx::make_kmajor_desc(0u, C::ROWB, 0u);
+        const uint32_t desc_hi = (uint32_t)(dsc >> 32);
+        const uint32_t ring_lo = (uint32_t)dsc | (ring >> 4);
+        const uint32_t w_lo = (uint32_t)dsc | (wsm >> 4);
+        int s = 0; uint32_t ph = 0;
+        int tcount = 0;
+        for (int t = blockIdx.x; t < g.ntiles; t += gridDim.x) {
+            const long long p0 = (long long)t * 128;
+            if (dc_skip(p0, g.P, plane, vol, Dp)) continue;
+            const int acc = tcount & 1;
+            const uint32_t acc_ph = (uint32_t)(tcount >> 1) & 1u;
+            ++tcount;
+            wait_bar(tempty_bar(acc), acc_ph ^ 1u);
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem + acc * C::ACC_COLS;
+#pragma unroll 1
+            for (int a = 0; a < 4; ++a) {
+                wait_bar(full_bar(s), ph);
+                ptx::tc_fence_after();
+                if (ptx::elect_one_sync()) {
+                    const uint32_t a_lo0 = ring_lo + (uint32_t)s * (C::A_BYTES >> 4);
+                    for (int op = g.op_begin[a]; op < g.op_begin[a + 1]; ++op) {
+                        const DcOp o = g.ops[op];
+                        const uint32_t a_lo = a_lo0 + (uint32_t)((o.ow * C::ROWB) >> 4);
+                        const uint32_t b_lo = w_lo + (uint32_t)((o.brow * C::ROWB) >> 4);
+                        const uint32_t idesc = idesc0 | ((uint32_t)(o.n >> 3) << 17);
+#pragma unroll
+                        for (int k = 0; k < KC / 16; ++k)        // the very first MMA (offset 000 covers all 8 classes) overwrites
+                            ptx::umma_bf16_lohi(d_tmem + o.dcol, a_lo + ((k * 32) >> 4), b_lo + ((k * 32) >> 4), desc_hi, idesc,
+                                                (op | k) ? 1u : 0u);
+                    }
+                    ptx::umma_commit(empty_bar(s));
+                    if (a == 3) ptx::umma_commit(tfull_bar(acc));
+                }
+                __syncwarp();
+                if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else {
+        // ================= epilogue: 8 warps, two per TMEM lane quadrant, 4 classes each =================
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int r = q * 32 + lane;
+        constexpr int NV = NP / 8;
+        const float4* sc4 = reinterpret_cast<const float4*>(s_scale);
+        const float4* sh4 = reinterpret_cast<const float4*>(s_shift);
+        int tcount = 0;
+        for (int t = blockIdx.x; t < g.ntiles; t += gridDim.x) {
+            const long long p0 = (long long)t * 128;
+            if (dc_skip(p0, g.P, plane, vol, Dp)) continue;
+            const long long p = p0 + r;
+            bool interior = false;
+            int ob = 0, dz = 0, hy = 0, wx = 0;
+            if (p < g.P) {
+                const long long b = p / vol, rem = p - b * vol;
+                const int dp = (int)(rem / plane);
+                const int rem2 = (int)(rem - (long long)dp * plane);
+                const int hp = rem2 / Wp, wp = rem2 - hp * Wp;
+                interior = dp >= 1 && dp <= g.D && hp >= 1 && hp <= g.H && wp >= 1 && wp <= g.W;
+                ob = (int)b; dz = 2 * (dp - 1); hy = 2 * (hp - 1); wx = 2 * (wp - 1);
+            }
+            const int acc = tcount & 1;
+            const uint32_t acc_ph = (uint32_t)(tcount >> 1) & 1u;
+            ++tcount;
+            const uint32_t taddr0 = tmem + ((uint32_t)(q * 32) << 16) + acc * C::ACC_COLS;
+            bool valid[4]; size_t off[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int c = kDcPosClass[2 * jj + half];
+                const int od = dz + ((c >> 2) & 1), oh = hy + ((c >> 1) & 1), ow = wx + (c & 1);
+                valid[jj] = interior && od < g.Do && oh < g.Ho && ow < g.Wo;
+                off[jj] = g.y_f32 ? (((size_t)ob * g.Do + od) * g.Ho + oh) * g.Wo + ow
+                                  : ((((size_t)ob * (g.Do + 2) + od + 1) * (g.Ho + 2) + oh + 1) * (g.Wo + 2) + ow + 1) * (size_t)g.Cout;
+            }
+            auto release = [&]() {
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+            };
+            if (g.y_f32) {
+                float rf[4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj)
+                    rf[jj] = (residual && valid[jj]) ? __ldg(reinterpret_cast<const float*>(residual) + off[jj]) : 0.f;
+                wait_bar(tfull_bar(acc), acc_ph);
+                __syncwarp();
+                ptx::tc_fence_after();
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    uint32_t v[16];
+                    ptx::tmem_ld16(taddr0 + (2 * jj + half) * NP, v);
+                    ptx::tc_wait_ld();
+                    consume_tmem_load(v[0], scratch_smem);
+                    if (jj == 3) release();
+                    if (valid[jj]) {
+                        float a = fmaf(__uint_as_float(v[0]), s_scale[0], s_shift[0]) + rf[jj];
+                        if (g.relu) a = fmaxf(a, 0.f);
+                        reinterpret_cast<float*>(y)[off[jj]] = a;
+                    }
+                }
+            } else {
+                const __nv_bfloat16* resb = reinterpret_cast<const __nv_bfloat16*>(residual);
+                uint4 rv[4][NV];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const bool ld = residual && valid[jj];
+#pragma unroll
+                    for (int c = 0; c < NV; ++c)
+                        rv[jj][c] = ld ? __ldg(reinterpret_cast<const uint4*>(resb + off[jj]) + c) : make_uint4(0u, 0u, 0u, 0u);
+                }
+                wait_bar(tfull_bar(acc), acc_ph);
+                __syncwarp();
+                ptx::tc_fence_after();
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    uint32_t v[NP];
+                    if (NP == 32) ptx::tmem_ld32(taddr0 + (2 * jj + half) * NP, v); else ptx::tmem_ld16(taddr0 + (2 * jj + half) * NP, v);
+                    ptx::tc_wait_ld();
+                    consume_tmem_load(v[0], scratch_smem);
+                    if (jj == 3) release();
+                    if (valid[jj]) {
+                        uint4* out = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y) + off[jj]);
+#pragma unroll
+                        for (int c = 0; c < NV; ++c) {
+                            const float4 s0 = sc4[2 * c], s1 = sc4[2 * c + 1], h0 = sh4[2 * c], h1 = sh4[2 * c + 1];
+                            const uint4 rr = rv[jj][c];
+                            float f[8];
+                            f[0] = fmaf(__uint_as_float(v[8 * c + 0]), s0.x, h0.x) + bf16_lo(rr.x);
+                            f[1] = fmaf(__uint_as_float(v[8 * c + 1]), s0.y, h0.y) + bf16_hi(rr.x);
+                            f[2] = fmaf(__uint_as_float(v[8 * c + 2]), s0.z, h0.z) + bf16_lo(rr.y);
+                            f[3] = fmaf(__uint_as_float(v[8 * c + 3]), s0.w, h0.w) + bf16_hi(rr.y);
+                            f[4] = fmaf(__uint_as_float(v[8 * c + 4]), s1.x, h1.x) + bf16_lo(rr.z);
+                            f[5] = fmaf(__uint_as_float(v[8 * c + 5]), s1.y, h1.y) + bf16_hi(rr.z);
+                            f[6] = fmaf(__uint_as_float(v[8 * c + 6]), s1.z, h1.z) + bf16_lo(rr.w);
+                            f[7] = fmaf(__uint_as_float(v[8 * c + 7]), s1.w, h1.w) + bf16_hi(rr.w);
+                            if (g.relu) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+                            }
+                            uint4 ov;
+                            ov.x = pack_bf16x2(f[0], f[1]); ov.y = pack_bf16x2(f[2], f[3]);
+                            ov.z = pack_bf16x2(f[4], f[5]); ov.w = pack_bf16x2(f[6], f[7]);
+                            out[c] = ov;
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem, C::TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -783,6 +1076,57 @@ int launch_rs(const CUtensorMap& map_a, const CUtensorMap& map_w, const RsGeom& 
     return dsm_launch_status();
 }
 
+template <int KC, int NP>
+int launch_dc(const CUtensorMap& map_a, const CUtensorMap& map_w, const DcGeom& g, const float* scale, const float* shift,
+              const void* residual, void* y, cudaStream_t st) {
+    using C = DcCfg<KC, NP>;
+    auto kern = conv3d_dc_kernel<KC, NP>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    int nsm = DSM_NUM_SMS_B200, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    const int nblocks = g.ntiles < nsm ? g.ntiles : nsm;
+    kern<<<nblocks, C::THREADS, C::SMEM, st>>>(map_a, map_w, g, scale, shift, residual, y);
+    return dsm_launch_status();
+}
+
+// MMA schedule of the class-sharing transposed conv: for every input offset o in {0,1}^3 (grouped by the
+// (od,oh) tile that is loaded, ow is a descriptor shift) the accumulator blocks (Gray-code class order) whose
+// class needs that offset, split into contiguous runs; weight blocks are laid out in the same order.
+void build_dc_schedule(DcGeom& g, int NP) {
+    static const int pos_class[8] = {0, 1, 3, 2, 6, 7, 5, 4};
+    int nops = 0, nblk = 0;
+    for (int a = 0; a < 4; ++a) for (int ow = 0; ow < 2; ++ow) {
+        const int od = a >> 1, oh = a & 1;
+        if (ow == 0) g.op_begin[a] = (short)nops;
+        int pos = 0;
+        while (pos < 8) {
+            auto uses = [&](int ps) {
+                const int c = pos_class[ps];
+                return ((c >> 2) & 1) >= od && ((c >> 1) & 1) >= oh && (c & 1) >= ow;
+            };
+            if (!uses(pos)) { ++pos; continue; }
+            int end = pos;
+            while (end + 1 < 8 && uses(end + 1)) ++end;
+            DcOp& op = g.ops[nops++];
+            op.tile = (short)a; op.ow = (short)ow; op.brow = (short)(nblk * NP); op.n = (short)((end - pos + 1) * NP);
+            op.dcol = (short)(pos * NP); op.pad = 0;
+            for (int ps = pos; ps <= end; ++ps) {
+                const int c = pos_class[ps];
+                // per axis: parity 0 -> tap 1 (offset 0); parity 1 -> tap 0 at offset 1, tap 2 at offset 0
+                auto tap = [](int par, int off) { return par == 0 ? 1 : (off == 1 ? 0 : 2); };
+                const int kd = tap((c >> 2) & 1, od), kh = tap((c >> 1) & 1, oh), kw = tap(c & 1, ow);
+                g.w_dst[nblk] = (short)(nblk * NP);
+                g.w_src[nblk] = (short)(((kd * 3 + kh) * 3 + kw) * NP);
+                ++nblk;
+            }
+            pos = end + 1;
+        }
+    }
+    g.nops = nops;      // 10 MMAs, 27 weight blocks
+    g.op_begin[4] = (short)nops;
+}
+
 int conv3d_dispatch(const void* x, const void* w, const float* scale, const float* shift, const void* residual, void* y,
                     int B, int Cin, int Cout, int D, int H, int W, int stride, int transposed, int relu, int y_dtype,
                     int Do, int Ho, int Wo, int variant, void* stream) {
@@ -824,6 +1168,26 @@ int conv3d_dispatch(const void* x, const void* w, const float* scale, const floa
         cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
         cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)NP};
         if (!encode_map(&maps.w, w, 2, dims, strides, box, row_bytes)) return DSM_EDRIVER;
+    }
+    // transposed, Cout <= 32: the class-sharing kernel (variant bit3 set = keep the per-class kernel, for A/B runs)
+    if (transposed && NP <= 32 && Cin <= 64 && !(variant & 8)) {
+        CUtensorMap map_a;
+        cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)P};
+        cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
+        cuuint32_t box[2] = {(cuuint32_t)KC, 130u};
+        if (!encode_map(&map_a, x, 2, dims, strides, box, row_bytes)) return DSM_EDRIVER;
+        DcGeom dg;
+        memset(&dg, 0, sizeof(dg));
+        dg.B = B; dg.D = D; dg.H = H; dg.W = W; dg.Do = Do; dg.Ho = Ho; dg.Wo = Wo;
+        dg.Cout = Cout; dg.relu = relu; dg.y_f32 = (y_dtype == DSM_F32);
+        dg.P = P; dg.ntiles = (int)dsm_ceil_div_ll(P, 128);
+        build_dc_schedule(dg, NP);
+        cudaStream_t st = (cudaStream_t)stream;
+        if (KC == 32 && NP == 16) return launch_dc<32, 16>(map_a, maps.w, dg, scale, shift, residual, y, st);
+        if (KC == 32 && NP == 32) return launch_dc<32, 32>(map_a, maps.w, dg, scale, shift, residual, y, st);
+        if (KC == 64 && NP == 16) return launch_dc<64, 16>(map_a, maps.w, dg, scale, shift, residual, y, st);
+        if (KC == 64 && NP == 32) return launch_dc<64, 32>(map_a, maps.w, dg, scale, shift, residual, y, st);
+        return DSM_EUNSUPPORTED;
     }
     // stride-1, Cout <= 32: the plane-sharing kernel (variant bit3 set = keep the per-tile kernels, for A/B runs)
     if (!transposed && stride == 1 && NP <= 32 && Cin <= 64 && !(variant & 8)) {

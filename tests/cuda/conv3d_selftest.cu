@@ -165,7 +165,10 @@ static int run_case(const Case& c, bool timing, int reps) {
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= reps;
         const double vox = (double)c.B * (c.transposed ? (double)c.D * c.H * c.W : (double)Do * Ho * Wo);
         const double flops = 2.0 * 27 * c.Cin * c.Cout * vox;
-        printf("TIME %-34s v%d : %.3f ms  %.1f TFLOP/s (algorithmic) timeouts=%d\n", c.name, c.variant, ms, flops / ms * 1e-9, dsm_debug_conv_timeouts());
+        printf("TIME %-34s v%d : %.3f ms  %.1f TFLOP/s (algorithmic) timeouts=%d", c.name, c.variant, ms, flops / ms * 1e-9, dsm_debug_conv_timeouts());
+        if (g_prog && g_prog[1] > 0) printf("  [CTA0: %.1f us at %.0f MHz]", g_prog[1] * 16e-3, 1e3 * g_prog[0] / (double)g_prog[1]);
+        printf("\n");
+        if (g_prog) g_prog[0] = g_prog[1] = 0;
     }
     cudaFree(dx); cudaFree(dw); cudaFree(dscale); cudaFree(dshift); cudaFree(dref); cudaFree(dgot);
     if (dyb) cudaFree(dyb); if (dyf) cudaFree(dyf); if (dresb) cudaFree(dresb); if (dresf) cudaFree(dresf);
@@ -218,6 +221,12 @@ int main(int argc, char** argv) {
             {1, 32, 32, 2, 5, 9, 1, 0, 0, 0, 1, 0, 0, "s1 32->32 D=2"},
             {1, 32, 16, 8, 9, 40, 1, 0, 1, 0, 1, 0, 0, "s1 32->16 D=8"},
             {1, 32, 32, 24, 20, 150, 1, 0, 1, 1, 1, 0, 0, "s1 32->32 24x20x150 (many tiles)"},
+            // class-sharing transposed-conv kernel
+            {2, 64, 32, 5, 6, 21, 2, 1, 1, 1, 1, 0, 0, "deconv 64->32 B=2 5x6x21"},
+            {1, 32, 32, 4, 9, 40, 2, 1, 0, 0, 0, 0, 0, "deconv 32->32 plain"},
+            {1, 32, 16, 6, 7, 30, 2, 1, 1, 1, 1, 0, 0, "deconv 32->16"},
+            {1, 64, 1, 4, 6, 17, 2, 1, 0, 1, 1, 1, 0, "deconv 64->1 fp32 +res"},
+            {1, 64, 32, 12, 24, 78, 2, 1, 0, 1, 1, 0, 0, "deconv 64->32 12x24x78 (many tiles)"},
         };
         { int idx = 0; for (auto& c : cases) { if (g_only < 0 || g_only == idx) { Case cc = c; cc.variant |= g_level << 8; fails += run_case(cc, false, 0); } ++idx; } }
     }
@@ -231,6 +240,8 @@ int main(int argc, char** argv) {
             {1, 32, 32, 4, 6, 20, 1, 0, 1, 1, 1, 0, 8, "s1 32->32 per-tile shift"},
             {1, 64, 32, 5, 7, 19, 1, 0, 1, 0, 1, 0, 8, "s1 64->32 per-tile shift"},
             {1, 32, 1, 4, 6, 20, 1, 0, 0, 1, 0, 1, 8, "s1 32->1 per-tile shift"},
+            {1, 64, 32, 3, 5, 10, 2, 1, 0, 1, 1, 0, 8, "deconv 64->32 per-class"},
+            {1, 32, 1, 3, 5, 10, 2, 1, 0, 0, 0, 1, 8, "deconv 32->1 per-class"},
         };
         { int idx = 0; for (auto& c : cases) { if (g_only < 0 || g_only == idx) { Case cc = c; cc.variant |= g_level << 8; fails += run_case(cc, false, 0); } ++idx; } }
     }
@@ -256,6 +267,7 @@ int main(int argc, char** argv) {
             {1, 64, 32, 48, 96, 312, 1, 0, 1, 0, 1, 0, 8, "dres0.0 64->32 per-tile shift"},
             {1, 32, 32, 48, 96, 312, 1, 0, 1, 1, 1, 0, 8, "32->32 per-tile shift"},
             {1, 32, 1, 48, 96, 312, 1, 0, 0, 1, 0, 1, 8, "classif 32->1 per-tile shift"},
+            {1, 64, 32, 24, 48, 156, 2, 1, 0, 1, 1, 0, 8, "conv6 deconv 64->32 per-class"},
         };
         { int idx = 0; for (auto& c : cases) { if (g_only < 0 || g_only == idx) { Case cc = c; cc.variant |= g_level << 8; fails += run_case(cc, true, 10); } ++idx; } }
     }
