@@ -187,7 +187,7 @@ def run_native(args, rank, world, local_rank):
     if not args.no_graph:
         try:
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):    # NCCL's watchdog thread may touch CUDA meanwhile
                 static_out = step()
         except Exception as e:                  # eager launches are still the same kernels
             graph = None

@@ -27,8 +27,18 @@ inline bool encode(CUtensorMap* m, CUtensorMapDataType dt, const void* base, int
     EncodeTiledFn enc = get_encode_tiled();
     if (!enc) return false;
     // The driver call needs a current context.  A host thread that has not issued a runtime call yet (autograd's
-    // worker thread running a backward as its first CUDA work) has none: bind the primary context first.
-    cudaFree(nullptr);
+    // worker thread running a backward as its first CUDA work) has none: bind the primary context then — and only
+    // then, because cudaFree is not allowed while a stream capture is in progress (a capturing thread has one).
+    typedef CUresult (*CtxGetCurrentFn)(CUcontext*);
+    static CtxGetCurrentFn ctx_get = []() -> CtxGetCurrentFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuCtxGetCurrent", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<CtxGetCurrentFn>(p);
+    }();
+    CUcontext cur = nullptr;
+    if (!ctx_get || ctx_get(&cur) != CUDA_SUCCESS || cur == nullptr) cudaFree(nullptr);
     cuuint32_t ones[5] = {1, 1, 1, 1, 1};
     return enc(m, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
                sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
