@@ -65,7 +65,8 @@ class FusedConv3d:
     """One fused layer with device-resident packed weights."""
 
     def __init__(self, weight, bn=None, bias=None, stride=1, transposed=False, relu=False, device=None, variant=0):
-        self.transposed, self.stride, self.relu = bool(transposed), int(stride), bool(relu)
+        # relu: False/0 none, True/1 after the residual add (PSMNet), 2 before it (GC-Net skip adds)
+        self.transposed, self.stride, self.relu = bool(transposed), int(stride), int(relu)
         if self.transposed:
             self.cin, self.cout = weight.shape[0], weight.shape[1]
             self.stride = 2

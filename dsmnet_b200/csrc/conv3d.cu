@@ -64,6 +64,15 @@ __device__ __forceinline__ void consume_tmem_load(uint32_t v0, uint32_t scratch_
         :: "r"(v0), "r"(scratch_smem) : "memory");
 }
 
+// epilogue activation: relu 0 = none, 1 = ReLU AFTER the residual add (PSMNet: stackhourglass.py:46-58),
+// 2 = ReLU BEFORE it (GC-Net: myAdd3d(l33(x), x29) adds to an already-activated deconv, gcnet.py:78-96)
+__device__ __forceinline__ float fuse_act(float a, float r, int relu) {
+    if (relu == 2) a = fmaxf(a, 0.f);
+    a += r;
+    if (relu == 1) a = fmaxf(a, 0.f);
+    return a;
+}
+
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -310,9 +319,8 @@ conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
                 if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
                 if (valid) {
                     const size_t o = (((size_t)ob * g.Do + od) * g.Ho + oh) * g.Wo + ow;
-                    float a = fmaf(__uint_as_float(v[0]), s_scale[0], s_shift[0]);
-                    if (residual) a += __ldg(reinterpret_cast<const float*>(residual) + o);
-                    if (g.relu) a = fmaxf(a, 0.f);
+                    const float a = fuse_act(fmaf(__uint_as_float(v[0]), s_scale[0], s_shift[0]),
+                                             residual ? __ldg(reinterpret_cast<const float*>(residual) + o) : 0.f, g.relu);
                     reinterpret_cast<float*>(y)[o] = a;
                 }
             } else {
@@ -338,15 +346,11 @@ conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
 #pragma unroll
                             for (int i = 0; i < 8; ++i)
                                 f[i] = fmaf(__uint_as_float(v[qq * 8 + i]), s_scale[c0 + qq * 8 + i], s_shift[c0 + qq * 8 + i]);
-                            if (res) {
-                                const uint4 rv = __ldg(res + (c0 / 8) + qq);
-                                f[0] += bf16_lo(rv.x); f[1] += bf16_hi(rv.x); f[2] += bf16_lo(rv.y); f[3] += bf16_hi(rv.y);
-                                f[4] += bf16_lo(rv.z); f[5] += bf16_hi(rv.z); f[6] += bf16_lo(rv.w); f[7] += bf16_hi(rv.w);
-                            }
-                            if (g.relu) {
+                            const uint4 rv = res ? __ldg(res + (c0 / 8) + qq) : make_uint4(0u, 0u, 0u, 0u);
+                            const float rr[8] = {bf16_lo(rv.x), bf16_hi(rv.x), bf16_lo(rv.y), bf16_hi(rv.y),
+                                                 bf16_lo(rv.z), bf16_hi(rv.z), bf16_lo(rv.w), bf16_hi(rv.w)};
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
-                            }
+                            for (int i = 0; i < 8; ++i) f[i] = fuse_act(f[i], rr[i], g.relu);
                             uint4 ov;
                             ov.x = pack_bf16x2(f[0], f[1]); ov.y = pack_bf16x2(f[2], f[3]);
                             ov.z = pack_bf16x2(f[4], f[5]); ov.w = pack_bf16x2(f[6], f[7]);
@@ -648,9 +652,8 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         ptx::tmem_zero16(taddr0 + j * NP);
                         if (j == my_last) release();
                         if (valid) {
-                            float a = fmaf(__uint_as_float(v[0]), s_scale[0], s_shift[0]) + rf[jj];
-                            if (g.relu) a = fmaxf(a, 0.f);
-                            reinterpret_cast<float*>(y)[o0 + j * ostep] = a;
+                            reinterpret_cast<float*>(y)[o0 + j * ostep] =
+                                fuse_act(fmaf(__uint_as_float(v[0]), s_scale[0], s_shift[0]), rf[jj], g.relu);
                         }
                     }
                 }
@@ -688,18 +691,14 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                 const float4 s0 = sc4[2 * c], s1 = sc4[2 * c + 1], h0 = sh4[2 * c], h1 = sh4[2 * c + 1];
                                 const uint4 rr = rv[jj][c];
                                 float f[8];
-                                f[0] = fmaf(__uint_as_float(v[8 * c + 0]), s0.x, h0.x) + bf16_lo(rr.x);
-                                f[1] = fmaf(__uint_as_float(v[8 * c + 1]), s0.y, h0.y) + bf16_hi(rr.x);
-                                f[2] = fmaf(__uint_as_float(v[8 * c + 2]), s0.z, h0.z) + bf16_lo(rr.y);
-                                f[3] = fmaf(__uint_as_float(v[8 * c + 3]), s0.w, h0.w) + bf16_hi(rr.y);
-                                f[4] = fmaf(__uint_as_float(v[8 * c + 4]), s1.x, h1.x) + bf16_lo(rr.z);
-                                f[5] = fmaf(__uint_as_float(v[8 * c + 5]), s1.y, h1.y) + bf16_hi(rr.z);
-                                f[6] = fmaf(__uint_as_float(v[8 * c + 6]), s1.z, h1.z) + bf16_lo(rr.w);
-                                f[7] = fmaf(__uint_as_float(v[8 * c + 7]), s1.w, h1.w) + bf16_hi(rr.w);
-                                if (g.relu) {
-#pragma unroll
-                                    for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
-                                }
+                                f[0] = fuse_act(fmaf(__uint_as_float(v[8 * c + 0]), s0.x, h0.x), bf16_lo(rr.x), g.relu);
+                                f[1] = fuse_act(fmaf(__uint_as_float(v[8 * c + 1]), s0.y, h0.y), bf16_hi(rr.x), g.relu);
+                                f[2] = fuse_act(fmaf(__uint_as_float(v[8 * c + 2]), s0.z, h0.z), bf16_lo(rr.y), g.relu);
+                                f[3] = fuse_act(fmaf(__uint_as_float(v[8 * c + 3]), s0.w, h0.w), bf16_hi(rr.y), g.relu);
+                                f[4] = fuse_act(fmaf(__uint_as_float(v[8 * c + 4]), s1.x, h1.x), bf16_lo(rr.z), g.relu);
+                                f[5] = fuse_act(fmaf(__uint_as_float(v[8 * c + 5]), s1.y, h1.y), bf16_hi(rr.z), g.relu);
+                                f[6] = fuse_act(fmaf(__uint_as_float(v[8 * c + 6]), s1.z, h1.z), bf16_lo(rr.w), g.relu);
+                                f[7] = fuse_act(fmaf(__uint_as_float(v[8 * c + 7]), s1.w, h1.w), bf16_hi(rr.w), g.relu);
                                 uint4 ov;
                                 ov.x = pack_bf16x2(f[0], f[1]); ov.y = pack_bf16x2(f[2], f[3]);
                                 ov.z = pack_bf16x2(f[4], f[5]); ov.w = pack_bf16x2(f[6], f[7]);
@@ -948,9 +947,7 @@ conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     consume_tmem_load(v[0], scratch_smem);
                     if (jj == 3) release();
                     if (valid[jj]) {
-                        float a = fmaf(__uint_as_float(v[0]), s_scale[0], s_shift[0]) + rf[jj];
-                        if (g.relu) a = fmaxf(a, 0.f);
-                        reinterpret_cast<float*>(y)[off[jj]] = a;
+                        reinterpret_cast<float*>(y)[off[jj]] = fuse_act(fmaf(__uint_as_float(v[0]), s_scale[0], s_shift[0]), rf[jj], g.relu);
                     }
                 }
             } else {
@@ -980,18 +977,14 @@ conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             const float4 s0 = sc4[2 * c], s1 = sc4[2 * c + 1], h0 = sh4[2 * c], h1 = sh4[2 * c + 1];
                             const uint4 rr = rv[jj][c];
                             float f[8];
-                            f[0] = fmaf(__uint_as_float(v[8 * c + 0]), s0.x, h0.x) + bf16_lo(rr.x);
-                            f[1] = fmaf(__uint_as_float(v[8 * c + 1]), s0.y, h0.y) + bf16_hi(rr.x);
-                            f[2] = fmaf(__uint_as_float(v[8 * c + 2]), s0.z, h0.z) + bf16_lo(rr.y);
-                            f[3] = fmaf(__uint_as_float(v[8 * c + 3]), s0.w, h0.w) + bf16_hi(rr.y);
-                            f[4] = fmaf(__uint_as_float(v[8 * c + 4]), s1.x, h1.x) + bf16_lo(rr.z);
-                            f[5] = fmaf(__uint_as_float(v[8 * c + 5]), s1.y, h1.y) + bf16_hi(rr.z);
-                            f[6] = fmaf(__uint_as_float(v[8 * c + 6]), s1.z, h1.z) + bf16_lo(rr.w);
-                            f[7] = fmaf(__uint_as_float(v[8 * c + 7]), s1.w, h1.w) + bf16_hi(rr.w);
-                            if (g.relu) {
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
-                            }
+                            f[0] = fuse_act(fmaf(__uint_as_float(v[8 * c + 0]), s0.x, h0.x), bf16_lo(rr.x), g.relu);
+                            f[1] = fuse_act(fmaf(__uint_as_float(v[8 * c + 1]), s0.y, h0.y), bf16_hi(rr.x), g.relu);
+                            f[2] = fuse_act(fmaf(__uint_as_float(v[8 * c + 2]), s0.z, h0.z), bf16_lo(rr.y), g.relu);
+                            f[3] = fuse_act(fmaf(__uint_as_float(v[8 * c + 3]), s0.w, h0.w), bf16_hi(rr.y), g.relu);
+                            f[4] = fuse_act(fmaf(__uint_as_float(v[8 * c + 4]), s1.x, h1.x), bf16_lo(rr.z), g.relu);
+                            f[5] = fuse_act(fmaf(__uint_as_float(v[8 * c + 5]), s1.y, h1.y), bf16_hi(rr.z), g.relu);
+                            f[6] = fuse_act(fmaf(__uint_as_float(v[8 * c + 6]), s1.z, h1.z), bf16_lo(rr.w), g.relu);
+                            f[7] = fuse_act(fmaf(__uint_as_float(v[8 * c + 7]), s1.w, h1.w), bf16_hi(rr.w), g.relu);
                             uint4 ov;
                             ov.x = pack_bf16x2(f[0], f[1]); ov.y = pack_bf16x2(f[2], f[3]);
                             ov.z = pack_bf16x2(f[4], f[5]); ov.w = pack_bf16x2(f[6], f[7]);
@@ -1112,6 +1105,7 @@ int conv3d_dispatch(const void* x, const void* w, const float* scale, const floa
                     int Do, int Ho, int Wo, int variant, void* stream) {
     if (!x || !w || !y || B <= 0 || Cin <= 0 || Cout <= 0 || D <= 0 || H <= 0 || W <= 0) return DSM_EINVAL;
     if (stride != 1 && stride != 2) return DSM_EINVAL;
+    if (relu < 0 || relu > 2) return DSM_EINVAL;
     if (transposed && stride != 2) return DSM_EUNSUPPORTED;
     if (y_dtype != DSM_BF16 && y_dtype != DSM_F32) return DSM_EINVAL;
     if (Cin != 32 && Cin != 64 && Cin != 128) return DSM_EUNSUPPORTED;

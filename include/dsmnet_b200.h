@@ -80,7 +80,9 @@ int dsm_concat_volume_bwd(const void* gout, float* gL, float* gR,
  *              the ConvTranspose3d kernel index (weight[ci][co][kd][kh][kw]).
  *   scale,shift : fp32 [CoutP] per-channel affine applied to the accumulator (folded
  *              BatchNorm + bias), either may be NULL (1 / 0)
- *   residual : same dtype/geometry as y, added before ReLU; NULL for none
+ *   residual : same dtype/geometry as y; NULL for none
+ *   relu     : 0 = none, 1 = ReLU after the residual add (PSMNet hourglass, stackhourglass.py:46-58),
+ *              2 = ReLU before it (GC-Net: myAdd3d(l33(x32), x29) adds to an activated deconv, gcnet.py:78-96)
  *   y        : y_dtype DSM_BF16 -> bf16 DSM_NDHWC_PADDED [B][Do+2][Ho+2][Wo+2][Cout] (only the
  *              interior is written: the rim must have been zeroed once by the caller);
  *              y_dtype DSM_F32 (Cout==1 only) -> fp32 [B][Do][Ho][Wo]

@@ -151,11 +151,11 @@ def crop_add(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 def conv3d_block(x: torch.Tensor, weight: torch.Tensor, scale: Optional[torch.Tensor] = None,
                  shift: Optional[torch.Tensor] = None, stride: int = 1, transposed: bool = False,
-                 residual: Optional[torch.Tensor] = None, relu: bool = False,
+                 residual: Optional[torch.Tensor] = None, relu=False,
                  operand_dtype: Optional[torch.dtype] = None,
                  storage_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
     """Conv3d(k3,p1,stride) or ConvTranspose3d(k3,s2,p1,output_padding=1), then the folded
-    BatchNorm affine, then optional crop-add of `residual`, then optional ReLU.
+    BatchNorm affine, then optional crop-add of `residual`, then optional ReLU (`relu=2`: ReLU first, then the add).
 
     Restates convbn_3d (submodule.py:16-19), the hourglass wiring (stackhourglass.py:26-41,45-60)
     and conv3d_bn/deconv3d_bn (util_conv.py:150-179).  `operand_dtype=torch.bfloat16` rounds the
@@ -173,9 +173,11 @@ def conv3d_block(x: torch.Tensor, weight: torch.Tensor, scale: Optional[torch.Te
         y = y * scale.view(1, -1, 1, 1, 1)
     if shift is not None:
         y = y + shift.view(1, -1, 1, 1, 1)
+    if relu == 2:          # GC-Net: the block is activated first, the skip is added afterwards (gcnet.py:78-96)
+        y = F.relu(y)
     if residual is not None:
         y = crop_add(y, residual)
-    if relu:
+    if relu == 1 or relu is True:
         y = F.relu(y)
     if storage_dtype is not None:
         y = y.to(storage_dtype).float()
@@ -474,3 +476,96 @@ def synthetic_stereo_features(H: int, W: int, C: int = 32, d_lo: float = 10.0, d
     xprime = (xl - d_lo) / (1 + a)
     disp = (xl - xprime).view(1, 1, W).expand(1, H, W).contiguous()
     return fL, fR, disp
+
+
+# ------------------------------------------------------------------------------------------
+# GC-Net 3-D path: concat volume -> feature3d enc-dec -> soft-argmin of MINUS the cost
+# ------------------------------------------------------------------------------------------
+
+GC_LAYERS = [  # name, Cin, Cout, stride, transposed  (gcnet.py:38-61)
+    ("l19", 64, 32, 1, False), ("l20", 32, 32, 1, False),
+    ("l21", 64, 64, 2, False), ("l22", 64, 64, 1, False), ("l23", 64, 64, 1, False),
+    ("l24", 64, 64, 2, False), ("l25", 64, 64, 1, False), ("l26", 64, 64, 1, False),
+    ("l27", 64, 64, 2, False), ("l28", 64, 64, 1, False), ("l29", 64, 64, 1, False),
+    ("l30", 64, 128, 2, False), ("l31", 128, 128, 1, False), ("l32", 128, 128, 1, False),
+    ("l33", 128, 64, 2, True), ("l34", 64, 64, 2, True), ("l35", 64, 64, 2, True), ("l36", 64, 32, 2, True),
+    ("l37", 32, 1, 2, True),
+]
+
+
+def _gc_block(params, name, x, stride=1, transposed=False, residual=None, operand_dtype=None):
+    """conv3d_bn / deconv3d_bn (util_conv.py:150-179): conv(+bias) -> BatchNorm3d (eval) -> ReLU; a skip,
+    when there is one, is added AFTER the activation (myAdd3d at gcnet.py:78,84,90,96).  l37 has neither
+    BatchNorm nor activation and is a bare module (`l37.weight`), the others are Sequentials (`l19.0.weight`)."""
+    bare = (name + ".weight") in params
+    w = params[name + (".weight" if bare else ".0.weight")]
+    b = params.get(name + (".bias" if bare else ".0.bias"))
+    cout = w.shape[1] if transposed else w.shape[0]
+    bn = None if bare else _bn(params, name + ".1")
+    scale, shift = fold_bn(cout, bn, b)
+    od, sd = operand_dtype if isinstance(operand_dtype, tuple) else (operand_dtype, None)
+    if bare:
+        sd = None                                     # the single-channel output stays fp32
+    return conv3d_block(x, w, scale, shift, stride, transposed, residual, 0 if bare else 2, od, sd)
+
+
+def gcnet_aggregate(params: Dict[str, torch.Tensor], cost: torch.Tensor, operand_dtype=None) -> torch.Tensor:
+    """feature3d.forward up to x37 (gcnet.py:65-101), eval-mode BatchNorm.  cost: [B,64,D,H,W] ->
+    [B,1,2D,2H,2W]."""
+    od = operand_dtype
+    g = lambda n, x, s=1, t=False, r=None: _gc_block(params, n, x, s, t, r, od)
+    x21 = g("l21", cost, 2); x24 = g("l24", x21, 2); x27 = g("l27", x24, 2); x30 = g("l30", x27, 2)
+    x32 = g("l32", g("l31", x30))
+    x29 = g("l29", g("l28", x27))
+    x33 = g("l33", x32, 2, True, x29)
+    x26 = g("l26", g("l25", x24))
+    x34 = g("l34", x33, 2, True, x26)
+    x23 = g("l23", g("l22", x21))
+    x35 = g("l35", x34, 2, True, x23)
+    x20 = g("l20", g("l19", cost))
+    x36 = g("l36", x35, 2, True, x20)
+    return g("l37", x36, 2, True)
+
+
+def gcnet_hotpath(params: Dict[str, torch.Tensor], fL: torch.Tensor, fR: torch.Tensor, maxdisp: int, operand_dtype=None):
+    """gcnet.forward from the feature maps on (gcnet.py:129-137, feature3d :65-111): GC volume with
+    D = maxdisp/2, 3-D enc-dec, softmax over MINUS the cost, regression.  Returns [B,1,2H,2W]."""
+    cost = concat_volume(fL, fR, maxdisp // 2, "gc")
+    if isinstance(operand_dtype, tuple) and operand_dtype[1] is not None:
+        cost = cost.to(operand_dtype[1]).float()
+    x37 = gcnet_aggregate(params, cost, operand_dtype)
+    return softargmin(x37.squeeze(1), -1.0).unsqueeze(1)
+
+
+def gcnet_random_params(seed: int = 0, calibrate_on: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    """Synthetic parameters of GC-Net's feature3d with the reference's names (`l19.0.weight`, `l19.0.bias`,
+    `l19.1.running_var`, ..., bare `l37.weight/bias`); He-normal weights, small biases; with `calibrate_on`
+    (a GC cost volume) the BatchNorm running statistics are set to the batch statistics layer by layer."""
+    rs = np.random.RandomState(seed)
+    params: Dict[str, torch.Tensor] = {}
+    for name, cin, cout, stride, transposed in GC_LAYERS:
+        shape = (cin, cout, 3, 3, 3) if transposed else (cout, cin, 3, 3, 3)
+        taps = 27.0 / 8.0 if transposed else 27.0          # taps that reach one output voxel on average
+        w = rs.standard_normal(size=shape).astype(np.float32) * np.float32(math.sqrt(2.0 / (taps * cin)))
+        b = rs.standard_normal(size=(cout,)).astype(np.float32) * np.float32(0.05)
+        if name == "l37":
+            params[name + ".weight"] = torch.from_numpy(w); params[name + ".bias"] = torch.from_numpy(b)
+            continue
+        params[name + ".0.weight"] = torch.from_numpy(w); params[name + ".0.bias"] = torch.from_numpy(b)
+        params[name + ".1.weight"] = torch.ones(cout); params[name + ".1.bias"] = torch.zeros(cout)
+        params[name + ".1.running_mean"] = torch.zeros(cout); params[name + ".1.running_var"] = torch.ones(cout)
+    if calibrate_on is not None:
+        def cal(name, x, stride=1, transposed=False, residual=None):
+            w = params[name + ".0.weight"]; b = params[name + ".0.bias"]
+            raw = conv3d_block(x, w, None, b, stride, transposed)
+            params[name + ".1.running_mean"] = raw.mean(dim=(0, 2, 3, 4))
+            params[name + ".1.running_var"] = raw.var(dim=(0, 2, 3, 4), unbiased=False) + 1e-3
+            return _gc_block(params, name, x, stride, transposed, residual)
+        c = calibrate_on
+        x21 = cal("l21", c, 2); x24 = cal("l24", x21, 2); x27 = cal("l27", x24, 2); x30 = cal("l30", x27, 2)
+        x32 = cal("l32", cal("l31", x30))
+        x29 = cal("l29", cal("l28", x27)); x33 = cal("l33", x32, 2, True, x29)
+        x26 = cal("l26", cal("l25", x24)); x34 = cal("l34", x33, 2, True, x26)
+        x23 = cal("l23", cal("l22", x21)); x35 = cal("l35", x34, 2, True, x23)
+        x20 = cal("l20", cal("l19", c)); cal("l36", x35, 2, True, x20)
+    return params

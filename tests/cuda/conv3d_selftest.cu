@@ -53,9 +53,10 @@ __global__ void ref_conv(const __nv_bfloat16* x, const __nv_bfloat16* w, const f
         for (int ci = 0; ci < Cin; ++ci) acc += __bfloat162float(xr[ci]) * __bfloat162float(wr[ci]);
     }
     float v = acc * (scale ? scale[co] : 1.f) + (shift ? shift[co] : 0.f);
+    if (relu == 2) v = fmaxf(v, 0.f);
     if (res_b) v += __bfloat162float(res_b[((((size_t)b * (Do + 2) + od + 1) * (Ho + 2) + oh + 1) * (Wo + 2) + ow + 1) * Cout + co]);
     if (res_f) v += res_f[(((size_t)b * Do + od) * Ho + oh) * Wo + ow];
-    if (relu) v = fmaxf(v, 0.f);
+    if (relu == 1) v = fmaxf(v, 0.f);
     out[i] = v;
 }
 
@@ -221,6 +222,10 @@ int main(int argc, char** argv) {
             {1, 32, 32, 2, 5, 9, 1, 0, 0, 0, 1, 0, 0, "s1 32->32 D=2"},
             {1, 32, 16, 8, 9, 40, 1, 0, 1, 0, 1, 0, 0, "s1 32->16 D=8"},
             {1, 32, 32, 24, 20, 150, 1, 0, 1, 1, 1, 0, 0, "s1 32->32 24x20x150 (many tiles)"},
+            // ReLU before the residual add (GC-Net skip connections)
+            {1, 64, 32, 3, 5, 10, 2, 1, 2, 1, 1, 0, 0, "deconv 64->32 relu-then-add"},
+            {1, 128, 64, 3, 4, 9, 2, 1, 2, 1, 1, 0, 0, "deconv 128->64 relu-then-add"},
+            {1, 32, 32, 4, 6, 20, 1, 0, 2, 1, 1, 0, 0, "s1 32->32 relu-then-add"},
             // class-sharing transposed-conv kernel
             {2, 64, 32, 5, 6, 21, 2, 1, 1, 1, 1, 0, 0, "deconv 64->32 B=2 5x6x21"},
             {1, 32, 32, 4, 9, 40, 2, 1, 0, 0, 0, 0, 0, "deconv 32->32 plain"},

@@ -111,6 +111,21 @@ def main():
     save("psmnet_hotpath", fL=fL, fR=fR, maxdisp=maxdisp, H=H, W=W, seed=7, params_sha256=params_digest(params),
          cost1=c1, cost2=c2, cost3=c3, pred1=p1, pred2=p2, pred3=p3)
 
+    # ---- GC-Net 3-D path: the reference's own feature3d (eval-mode BatchNorm) on a GC volume -----------
+    maxdisp = 16                                                      # D = maxdisp/2 = 8 (gcnet.py:117)
+    rs = np.random.RandomState(2025)
+    gfL = torch.from_numpy(rs.standard_normal((1, 32, 16, 24)).astype(np.float32))
+    gfR = torch.from_numpy(rs.standard_normal((1, 32, 16, 24)).astype(np.float32))
+    gvol = R.gc_volume(gfL, gfR, maxdisp // 2)
+    gparams = O.gcnet_random_params(seed=9, calibrate_on=gvol)
+    gnet = R.make_gcnet(maxdisp, seed=0).eval()
+    gmissing = gnet.load_state_dict({"layer3d." + k: v for k, v in gparams.items()}, strict=False)
+    assert not gmissing.unexpected_keys, gmissing.unexpected_keys
+    assert all(k.startswith("layer2d") or k.endswith("num_batches_tracked") for k in gmissing.missing_keys)
+    with torch.no_grad(), R.pinned_torch():
+        gdisp = gnet.layer3d(gvol, "test")                            # [1,1,32,48]
+    save("gcnet_hotpath", fL=gfL, fR=gfR, maxdisp=maxdisp, seed=9, params_sha256=params_digest(gparams), disp=gdisp)
+
     # single reference layers (GC-Net style: bias + BN + ReLU; stride 2; transposed with BN3d swap)
     uc = mods["util_conv"]
     torch.manual_seed(77)

@@ -166,6 +166,52 @@ def test_psmnet_hotpath_vs_oracle(B, H, W, maxdisp):
         assert float((mine.cpu() - r).abs().mean()) < 0.25               # gate (2)
 
 
+def _gc_module(params, maxdisp):
+    from dsmnet_b200.gcnet import GCNetHotPath
+    m = GCNetHotPath(maxdisp)
+    missing = m.load_state_dict({"layer3d." + k: v for k, v in params.items()}, strict=False)
+    assert not missing.unexpected_keys
+    assert all(k.endswith("num_batches_tracked") for k in missing.missing_keys), missing.missing_keys
+    return m.cuda().eval()
+
+
+def test_gcnet_hotpath_golden():
+    """GC-Net's 3-D path (gcnet.py:65-111 run by the reference itself) vs the CUDA path."""
+    g = load_golden("gcnet_hotpath")
+    cost = O.concat_volume(g["fL"], g["fR"], g["maxdisp"] // 2, "gc")
+    params = O.gcnet_random_params(seed=g["seed"], calibrate_on=cost)
+    m = _gc_module(params, g["maxdisp"])
+    with torch.no_grad():
+        disp = m(g["fL"].cuda(), g["fR"].cuda()).cpu()
+    emu = O.gcnet_hotpath(params, g["fL"], g["fR"], g["maxdisp"], operand_dtype=BF16)
+    assert disp.shape == g["disp"].shape
+    d_emu = float((disp - emu).abs().mean()); d_fmt = float((emu - g["disp"]).abs().mean()); d_ref = float((disp - g["disp"]).abs().mean())
+    print("gcnet: mean |ours-emu| %.4f, |emu-ref| %.4f, |ours-ref| %.4f px" % (d_emu, d_fmt, d_ref))
+    assert d_emu < max(0.5 * d_fmt, 0.02)             # gate (1): the kernels add little beyond the operand format
+    assert d_ref < 2.0 * d_fmt + 0.02                 # gate (2)
+
+
+@pytest.mark.parametrize("B,H,W,maxdisp", [(1, 20, 28, 24), (2, 16, 16, 16)])
+def test_gcnet_hotpath_vs_oracle(B, H, W, maxdisp):
+    """odd level sizes exercise the myAdd3d crop of the skip connections (util_fun.py:41-51)"""
+    torch.manual_seed(6)
+    fL = torch.randn(B, 32, H, W); fR = torch.randn(B, 32, H, W)
+    cost = O.concat_volume(fL, fR, maxdisp // 2, "gc")
+    params = O.gcnet_random_params(seed=13, calibrate_on=cost)
+    ref = O.gcnet_hotpath(params, fL, fR, maxdisp)
+    emu = O.gcnet_hotpath(params, fL, fR, maxdisp, operand_dtype=BF16)
+    m = _gc_module(params, maxdisp)
+    with torch.no_grad():
+        disp = m(fL.cuda(), fR.cuda()).cpu()
+    from dsmnet_b200.conv3d import conv_timeouts
+    assert conv_timeouts() == 0
+    assert disp.shape == ref.shape
+    d_emu = float((disp - emu).abs().mean()); d_fmt = float((emu - ref).abs().mean())
+    print("gcnet %s: mean |ours-emu| %.4f, |emu-ref| %.4f px" % ((B, H, W, maxdisp), d_emu, d_fmt))
+    assert d_emu < max(0.5 * d_fmt, 0.02)
+    assert float((disp - ref).abs().mean()) < 2.0 * d_fmt + 0.02
+
+
 def test_training_mode_raises():
     from dsmnet_b200 import _lib
     from dsmnet_b200.psmnet import PSMNetHotPath

@@ -76,6 +76,21 @@ def test_psmnet_hotpath():
         assert (mine - ref).abs().mean() < 1e-4
 
 
+def test_gcnet_hotpath():
+    """the reference's feature3d (19-layer 3-D enc-dec + soft-argmin of -cost) vs the oracle restatement"""
+    g = load_golden("gcnet_hotpath")
+    cost = O.concat_volume(g["fL"], g["fR"], g["maxdisp"] // 2, "gc")
+    params = O.gcnet_random_params(seed=g["seed"], calibrate_on=cost)
+    h = hashlib.sha256()
+    for k in sorted(params):
+        if params[k].dim() == 5:
+            h.update(k.encode()); h.update(params[k].numpy().tobytes())
+    assert h.hexdigest() == g["params_sha256"], "synthetic weights are not the ones the fixture was made with"
+    disp = O.gcnet_hotpath(params, g["fL"], g["fR"], g["maxdisp"])
+    assert disp.shape == g["disp"].shape
+    assert (disp - g["disp"]).abs().max() < 2e-3 and (disp - g["disp"]).abs().mean() < 1e-4
+
+
 @pytest.mark.parametrize("name,transposed,stride", [("gc_conv_s2", False, 2), ("gc_deconv", True, 2)])
 def test_gc_layers(name, transposed, stride):
     g = load_golden(name)
