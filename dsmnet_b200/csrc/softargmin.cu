@@ -68,6 +68,71 @@ softargmin_fwd_kernel(const float* __restrict__ cost, float* __restrict__ disp,
     }
 }
 
+// D-split variant for small images: a CTA is 32 pixel-quads x DSPLIT warps; the 8-plane chunks are dealt
+// round-robin to the warps (warp w takes chunks w, w+DSPLIT, ...: all warps of the GPU still sweep the
+// volume front to back together, which keeps DRAM pages open — a contiguous D range per warp measured 35%
+// slower), each with the same chunked online softmax, and the DSPLIT partial (m, s, t) triples are merged
+// through shared memory (m = max; s, t rescaled by e^(m_i - m)).  DSPLIT x more threads put DSPLIT x more
+// independent 128-bit loads in flight: one thread per pixel-quad only reaches ~16% of HBM bandwidth at
+// GC-Net's 256x512 (0.13 M pixels are too few threads).
+constexpr int DSPLIT = 4;
+
+__global__ void __launch_bounds__(32 * DSPLIT)
+softargmin_fwd_split_kernel(const float* __restrict__ cost, float* __restrict__ disp,
+                            int D, long long HW, long long nq, float sign) {
+    __shared__ float4 s_m[DSPLIT][32], s_s[DSPLIT][32], s_t[DSPLIT][32];
+    const int lane = threadIdx.x, w = threadIdx.y;
+    const long long q = (long long)blockIdx.x * 32 + lane;
+    const int b = blockIdx.y;
+    Online o[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) o[p].init();
+    if (q < nq) {
+        const float* c = cost + (size_t)b * D * HW + q * 4;
+        // software pipeline: the next chunk's eight 128-bit loads are issued before the current chunk is consumed
+        float4 nxt[DCH];
+        auto fetch = [&](int d0) {
+#pragma unroll
+            for (int i = 0; i < DCH; ++i)
+                nxt[i] = (d0 + i < D) ? ld_stream_f4(reinterpret_cast<const float4*>(c + (size_t)(d0 + i) * HW)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        int d0 = w * DCH;
+        if (d0 < D) fetch(d0);
+        for (; d0 < D; d0 += DSPLIT * DCH) {
+            const int n = min(DCH, D - d0);
+            float v[4][DCH];
+#pragma unroll
+            for (int i = 0; i < DCH; ++i) {
+                v[0][i] = sign * nxt[i].x; v[1][i] = sign * nxt[i].y; v[2][i] = sign * nxt[i].z; v[3][i] = sign * nxt[i].w;
+            }
+            if (d0 + DSPLIT * DCH < D) fetch(d0 + DSPLIT * DCH);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) o[p].chunk(v[p], n, d0);
+        }
+    }
+    s_m[w][lane] = make_float4(o[0].m, o[1].m, o[2].m, o[3].m);
+    s_s[w][lane] = make_float4(o[0].s, o[1].s, o[2].s, o[3].s);
+    s_t[w][lane] = make_float4(o[0].t, o[1].t, o[2].t, o[3].t);
+    __syncthreads();
+    if (w == 0 && q < nq) {
+        float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < DSPLIT; ++i) {
+            const float4 a = s_m[i][lane];
+            m[0] = fmaxf(m[0], a.x); m[1] = fmaxf(m[1], a.y); m[2] = fmaxf(m[2], a.z); m[3] = fmaxf(m[3], a.w);
+        }
+        float ss[4] = {0.f, 0.f, 0.f, 0.f}, tt[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < DSPLIT; ++i) {
+            const float4 a = s_m[i][lane], sv = s_s[i][lane], tv = s_t[i][lane];
+            const float e0 = __expf(a.x - m[0]), e1 = __expf(a.y - m[1]), e2 = __expf(a.z - m[2]), e3 = __expf(a.w - m[3]);
+            ss[0] = fmaf(sv.x, e0, ss[0]); ss[1] = fmaf(sv.y, e1, ss[1]); ss[2] = fmaf(sv.z, e2, ss[2]); ss[3] = fmaf(sv.w, e3, ss[3]);
+            tt[0] = fmaf(tv.x, e0, tt[0]); tt[1] = fmaf(tv.y, e1, tt[1]); tt[2] = fmaf(tv.z, e2, tt[2]); tt[3] = fmaf(tv.w, e3, tt[3]);
+        }
+        *reinterpret_cast<float4*>(disp + (size_t)b * HW + q * 4) = make_float4(tt[0] / ss[0], tt[1] / ss[1], tt[2] / ss[2], tt[3] / ss[3]);
+    }
+}
+
 // backward: gcost[b,d,y,x] = sign * p_d * (d - disp) * gdisp,  p = softmax_d(sign*cost)
 // pass 1 recomputes (m, s); pass 2 writes.  One thread per pixel (scalar, coalesced along x).
 __global__ void __launch_bounds__(256)
@@ -224,7 +289,10 @@ extern "C" int dsm_softargmin_fwd(const float* cost, float* disp, int B, int D, 
     cudaStream_t st = (cudaStream_t)stream;
     if ((HW & 3) == 0 && dsm_aligned16(cost) && dsm_aligned16(disp)) {
         const long long nq = HW / 4;
-        softargmin_fwd_kernel<true><<<dim3((unsigned)dsm_ceil_div_ll(nq, 128), B), 128, 0, st>>>(cost, disp, D, HW, nq, sign);
+        if (D >= 2 * DSPLIT * DCH)
+            softargmin_fwd_split_kernel<<<dim3((unsigned)dsm_ceil_div_ll(nq, 32), B), dim3(32, DSPLIT), 0, st>>>(cost, disp, D, HW, nq, sign);
+        else
+            softargmin_fwd_kernel<true><<<dim3((unsigned)dsm_ceil_div_ll(nq, 128), B), 128, 0, st>>>(cost, disp, D, HW, nq, sign);
     } else {
         softargmin_fwd_kernel<false><<<dim3((unsigned)dsm_ceil_div_ll(HW, 128), B), 128, 0, st>>>(cost, disp, D, HW, HW, sign);
     }

@@ -80,15 +80,26 @@ concat_ndhwc_bf16_kernel(const float* __restrict__ fL, const float* __restrict__
     const int half = cpv / 2;
     const bool yrim = (yp == 0 || yp == H + 1);
 
+    // 16-byte chunk k of voxel x lives at chunk (k ^ swz(x)): conflict-free 128-bit shared stores by 8 consecutive x
+    const int swz_mask = (half >= 4 && (half & (half - 1)) == 0) ? 3 : 0;
+    uint4* wA = reinterpret_cast<uint4*>(sA);
+    uint4* wB = reinterpret_cast<uint4*>(sB);
     if (!yrim) {
         const int y = yp - 1;
         const float* a = (mode == DSM_VOL_GC_RIGHT ? fR : fL) + ((size_t)b * C * H + y) * W;
         const float* r = (mode == DSM_VOL_GC_RIGHT ? fL : fR) + ((size_t)b * C * H + y) * W;
         const size_t plane = (size_t)H * W;
-        for (int i = threadIdx.x; i < C * W; i += blockDim.x) {
-            const int c = i / W, x = i - c * W;
-            sA[x * C + c] = __float2bfloat16_rn(__ldg(a + c * plane + x));
-            sB[x * C + c] = __float2bfloat16_rn(__ldg(r + c * plane + x));
+        // thread = (x, group of 8 channels): 8 coalesced-along-x loads per source, one 128-bit shared store each
+        for (int i = threadIdx.x; i < W * half; i += blockDim.x) {
+            const int kq = i / W, x = i - kq * W;
+            const float* pa = a + (size_t)(kq * 8) * plane + x;
+            const float* pr = r + (size_t)(kq * 8) * plane + x;
+            float fa[8], fr[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { fa[c] = __ldg(pa + c * plane); fr[c] = __ldg(pr + c * plane); }
+            const int dst = x * half + (kq ^ ((x >> 1) & swz_mask));
+            wA[dst] = make_uint4(pack_bf16x2(fa[0], fa[1]), pack_bf16x2(fa[2], fa[3]), pack_bf16x2(fa[4], fa[5]), pack_bf16x2(fa[6], fa[7]));
+            wB[dst] = make_uint4(pack_bf16x2(fr[0], fr[1]), pack_bf16x2(fr[2], fr[3]), pack_bf16x2(fr[4], fr[5]), pack_bf16x2(fr[6], fr[7]));
         }
     }
     __syncthreads();
@@ -97,26 +108,33 @@ concat_ndhwc_bf16_kernel(const float* __restrict__ fL, const float* __restrict__
     const uint4* vA = reinterpret_cast<const uint4*>(sA);
     const uint4* vB = reinterpret_cast<const uint4*>(sB);
     const int row_chunks = Wp * cpv;
-    for (int dp = dp0; dp < dp1; ++dp) {
-        uint4* orow = out + (((size_t)b * (D + 2) + dp) * Hp + yp) * (size_t)row_chunks;
-        const bool rim = yrim || dp == 0 || dp == D + 1;
-        const int d = dp - 1;
-        for (int i = threadIdx.x; i < row_chunks; i += blockDim.x) {
+    const size_t plane_chunks = (size_t)Hp * row_chunks;
+    uint4* obase = out + (((size_t)b * (D + 2) + dp0) * Hp + yp) * (size_t)row_chunks;
+    // a thread keeps its chunk positions and walks the planes of the slab: the (voxel, chunk) decode is done once
+    for (int i = threadIdx.x; i < row_chunks; i += blockDim.x) {
+        const int xp = i / cpv, k = i - xp * cpv;
+        const int x = xp - 1;
+        const bool inside = !yrim && xp >= 1 && xp <= W;
+        const bool first = k < half;
+        const int kk = first ? k : k - half;
+        uint4 va = zero;
+        if (inside && first) va = vA[x * half + (kk ^ ((x >> 1) & swz_mask))];
+        uint4* o = obase + i;
+        for (int dp = dp0; dp < dp1; ++dp, o += plane_chunks) {
             uint4 v = zero;
-            if (!rim) {
-                const int xp = i / cpv, k = i - xp * cpv;
-                const int x = xp - 1;
-                if (xp >= 1 && xp <= W) {
-                    if (k < half) {
-                        if (mode != DSM_VOL_PSM || x >= d) v = vA[x * half + k];
-                    } else if (mode == DSM_VOL_GC_RIGHT) {
-                        if (x + d < W) v = vB[(x + d) * half + (k - half)];
-                    } else {
-                        if (x >= d) v = vB[(x - d) * half + (k - half)];
-                    }
+            if (inside && dp >= 1 && dp <= D) {
+                const int d = dp - 1;
+                if (first) {
+                    if (mode != DSM_VOL_PSM || x >= d) v = va;
+                } else if (mode == DSM_VOL_GC_RIGHT) {
+                    const int xs = x + d;
+                    if (xs < W) v = vB[xs * half + (kk ^ ((xs >> 1) & swz_mask))];
+                } else {
+                    const int xs = x - d;
+                    if (xs >= 0) v = vB[xs * half + (kk ^ ((xs >> 1) & swz_mask))];
                 }
             }
-            st_stream_u4(orow + i, v);
+            st_stream_u4(o, v);
         }
     }
 }

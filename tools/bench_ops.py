@@ -152,6 +152,22 @@ def main():
     conv_case("deconv 64->32 +res (conv6)", 64, 32, 24, 48, 156, 2, True, True)
     conv_case("conv 32->1 s1 fp32 +res (classif.2)", 32, 1, 48, 96, 312, 1, False, True)
 
+    # ---- whole hot paths (CUDA graph, inputs resident) ----------------------------------------------
+    from dsmnet_b200.gcnet import GCNetHotPath
+    from dsmnet_b200.psmnet import PSMNetHotPath
+    with torch.no_grad():
+        gc = GCNetHotPath(192).to(dev).eval()
+        for mod in gc.modules():                     # O(1) activations with random weights: unit-variance-ish BN
+            if isinstance(mod, torch.nn.BatchNorm3d):
+                mod.running_var.fill_(2.0)
+        gl = torch.randn(1, 32, 128, 256, device=dev); gr = torch.randn(1, 32, 128, 256, device=dev)
+        t = timeit(lambda i: gc(gl, gr), reps=10)
+        tens("GC-Net hot path fwd 256x512 maxdisp 192 (volume + 19 convs + head)", 882.6e9, t)
+        psm = PSMNetHotPath(192).to(dev).eval()
+        pl = torch.randn(1, 32, 96, 312, device=dev); pr = torch.randn(1, 32, 96, 312, device=dev)
+        t = timeit(lambda i: psm(pl, pr, (384, 1248)), reps=10)
+        tens("PSMNet hot path fwd 384x1248 maxdisp 192 (volume + 28 convs + 3 heads)", 926.7e9, t)
+
     if args.json:
         json.dump({"peaks": {"hbm_gbs": hbm, "bf16_tflops": tf, "source": which}, "rows": rows}, open(args.json, "w"), indent=1)
 
