@@ -396,6 +396,7 @@ struct RsGeom {
     int nbands;              // ceil(Do / R)
     int nitems;              // B * nbands * plane_tiles
     int dbg;                 // timing experiments only (variant bits 4..6): 1 = no epilogue work, 2 = no TMA traffic, 4 = no MMAs
+    int ngroups;             // output-channel groups of NP channels (Cout = ngroups*NP when > 1): CTA c owns group c % ngroups
     int w_row[27];           // first row of tap (kd*3+kh)*3+kw in the packed weights
 };
 
@@ -444,6 +445,11 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int plane = Hp * Wp;
     long long dbg_c0 = 0; unsigned long long dbg_t0 = 0;
     if (g_conv_progress && blockIdx.x == 0 && tid == 0) { dbg_c0 = clock64(); dbg_t0 = globaltimer_ns(); }
+    // Cout > NP (64->64 layers): the output channels are split into groups of NP; a CTA keeps the weights of ONE group
+    // resident and walks the items with the CTAs of its group (the activation tiles are read once per group, from L2)
+    const int grp = (int)blockIdx.x % g.ngroups;
+    const int item0 = (int)blockIdx.x / g.ngroups, item_step = (int)gridDim.x / g.ngroups;
+    const int ch0 = grp * NP;                                  // first output channel of this CTA
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = ptx::smem_u32(smem_raw);
@@ -465,8 +471,8 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     float* s_shift = s_scale + NP;
 
     if (tid < NP) {
-        s_scale[tid] = scale ? __ldg(scale + tid) : 1.f;
-        s_shift[tid] = shift ? __ldg(shift + tid) : 0.f;
+        s_scale[tid] = scale ? __ldg(scale + ch0 + tid) : 1.f;
+        s_shift[tid] = shift ? __ldg(shift + ch0 + tid) : 0.f;
     }
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_w);
@@ -490,11 +496,11 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 for (int kh = 0; kh < 3; ++kh)
                     for (int kw = 0; kw < 3; ++kw)
                         ptx::tma_load_2d(wsm + (kh * 3 + kw) * C::W_TILE + (2 - kd) * NP * C::ROWB, &map_w, wfull_bar, 0,
-                                         g.w_row[(kd * 3 + kh) * 3 + kw]);
+                                         g.w_row[(kd * 3 + kh) * 3 + kw] + ch0);
         }
         __syncwarp();
         int s = 0; uint32_t ph = 0;                              // ring slot and its phase
-        for (int t = blockIdx.x; t < g.nitems; t += gridDim.x) {
+        for (int t = item0; t < g.nitems; t += item_step) {
             const RsItem item = rs_decode(g, t, C::R);
             for (int i = -1; i <= item.nb; ++i) {
                 const int zp = item.z0 + 1 + i;                  // padded input plane
@@ -532,7 +538,7 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const uint32_t a_tile = (C::KHS == 3) ? (uint32_t)((my_kh * C::A_BYTES) >> 4) : 0u;
         int s = 0; uint32_t ph = 0;
         int tcount = 0;
-        for (int t = blockIdx.x; t < g.nitems; t += gridDim.x) {
+        for (int t = item0; t < g.nitems; t += item_step) {
             const RsItem item = rs_decode(g, t, C::R);
             const int acc = tcount & 1;
             const uint32_t use_ph = (uint32_t)(tcount >> 1) & 1u;
@@ -602,7 +608,7 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const float4* sc4 = reinterpret_cast<const float4*>(s_scale);
         const float4* sh4 = reinterpret_cast<const float4*>(s_shift);
         int tcount = 0;
-        for (int t = blockIdx.x; t < g.nitems; t += gridDim.x) {
+        for (int t = item0; t < g.nitems; t += item_step) {
             const RsItem item = rs_decode(g, t, C::R);
             const int pq = item.tile * 128 + r;                   // position in the padded (h,w) plane
             const int hp = pq / Wp, wp = pq - hp * Wp;
@@ -659,7 +665,7 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 }
             } else {
                 const size_t ostep = (size_t)(g.Ho + 2) * (g.Wo + 2) * g.Cout;     // one output plane
-                const size_t o0 = ((((size_t)item.b * (g.Do + 2) + item.z0 + 1) * (g.Ho + 2) + hp) * (g.Wo + 2) + wp) * (size_t)g.Cout;
+                const size_t o0 = ((((size_t)item.b * (g.Do + 2) + item.z0 + 1) * (g.Ho + 2) + hp) * (g.Wo + 2) + wp) * (size_t)g.Cout + ch0;
                 const __nv_bfloat16* resb = reinterpret_cast<const __nv_bfloat16*>(residual);
                 uint4 rv[JJ][NV];
 #pragma unroll
@@ -1044,7 +1050,9 @@ int launch_rs(const CUtensorMap& map_a, const CUtensorMap& map_w, const RsGeom& 
     if (e != cudaSuccess) return (int)e;
     int nsm = DSM_NUM_SMS_B200, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    const int nblocks = g.nitems < nsm ? g.nitems : nsm;        // persistent: one CTA per SM
+    int per_group = nsm / g.ngroups;                            // persistent: one CTA per SM, split evenly over the channel groups
+    if (per_group > g.nitems) per_group = g.nitems;
+    const int nblocks = per_group * g.ngroups;
     kern<<<nblocks, C::THREADS, C::SMEM, st>>>(map_a, map_w, g, scale, shift, residual, y);
     return dsm_launch_status();
 }
@@ -1164,7 +1172,12 @@ int conv3d_dispatch(const void* x, const void* w, const float* scale, const floa
         return DSM_EUNSUPPORTED;
     }
     // stride-1, Cout <= 32: the plane-sharing kernel (variant bit3 set = keep the per-tile kernels, for A/B runs)
-    if (!transposed && stride == 1 && NP <= 32 && Cin <= 64 && !(variant & 8)) {
+    // 64->64: two groups of 32 channels — only when there is enough work to fill the machine twice over (each CTA pays a
+    // 110 KB weight prologue; the 12x24x78 hourglass bottom is faster on the per-tile kernel)
+    const bool rs_grouped = (y_dtype == DSM_BF16 && Cout > 32 && Cout % 32 == 0 && Cout <= 128) &&
+                            (long long)B * dsm_ceil_div(Do > 0 ? Do : D, 8) * dsm_ceil_div(Hp * Wp, 128) * (Cout / 32) >= 2LL * DSM_NUM_SMS_B200;
+    if (!transposed && stride == 1 && (NP <= 32 || rs_grouped) && Cin <= 64 && !(variant & 8)) {
+        const int NPk = rs_grouped ? 32 : NP;
         CUtensorMap map_a;
         cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)P};
         cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
@@ -1180,12 +1193,20 @@ int conv3d_dispatch(const void* x, const void* w, const float* scale, const floa
         if (ni > 0x7fffffffLL) return DSM_EUNSUPPORTED;
         rg.nitems = (int)ni;
         rg.dbg = (variant >> 4) & 7;
-        for (int t = 0; t < 27; ++t) rg.w_row[t] = t * NP;
+        rg.ngroups = rs_grouped ? Cout / 32 : 1;
+        for (int t = 0; t < 27; ++t) rg.w_row[t] = t * NP;          // packed weights are [27][NP = CoutP][Cin]
+        CUtensorMap map_w = maps.w;
+        if (rs_grouped) {                                            // weight boxes of 32 rows instead of CoutP
+            cuuint64_t wdims[2] = {(cuuint64_t)Cin, (cuuint64_t)27 * NP};
+            cuuint64_t wstrides[1] = {(cuuint64_t)Cin * 2};
+            cuuint32_t wbox[2] = {(cuuint32_t)KC, 32u};
+            if (!encode_map(&map_w, w, 2, wdims, wstrides, wbox, row_bytes)) return DSM_EDRIVER;
+        }
         cudaStream_t st = (cudaStream_t)stream;
-        if (KC == 32 && NP == 16) return launch_rs<32, 16>(map_a, maps.w, rg, scale, shift, residual, y, st);
-        if (KC == 32 && NP == 32) return launch_rs<32, 32>(map_a, maps.w, rg, scale, shift, residual, y, st);
-        if (KC == 64 && NP == 16) return launch_rs<64, 16>(map_a, maps.w, rg, scale, shift, residual, y, st);
-        if (KC == 64 && NP == 32) return launch_rs<64, 32>(map_a, maps.w, rg, scale, shift, residual, y, st);
+        if (KC == 32 && NPk == 16) return launch_rs<32, 16>(map_a, map_w, rg, scale, shift, residual, y, st);
+        if (KC == 32 && NPk == 32) return launch_rs<32, 32>(map_a, map_w, rg, scale, shift, residual, y, st);
+        if (KC == 64 && NPk == 16) return launch_rs<64, 16>(map_a, map_w, rg, scale, shift, residual, y, st);
+        if (KC == 64 && NPk == 32) return launch_rs<64, 32>(map_a, map_w, rg, scale, shift, residual, y, st);
         return DSM_EUNSUPPORTED;
     }
     dim3 grid;

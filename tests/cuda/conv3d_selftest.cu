@@ -276,6 +276,12 @@ int main(int argc, char** argv) {
         };
         { int idx = 0; for (auto& c : cases) { if (g_only < 0 || g_only == idx) { Case cc = c; cc.variant |= g_level << 8; fails += run_case(cc, true, 10); } ++idx; } }
     }
+    if (!strcmp(what, "dbg48")) {
+        Case c = {1, 32, 32, 48, 96, 312, 1, 0, 1, 1, 1, 0, 48, "32->32 dbg48"};
+        run_case(c, true, 10);
+        Case c2 = {1, 32, 32, 48, 96, 312, 1, 0, 1, 1, 1, 0, 32, "32->32 dbg32 (no TMA)"};
+        run_case(c2, true, 10);
+    }
     if (!strcmp(what, "dbg")) {
         // timing experiments on the plane-sharing kernel (results are garbage): which part of the pipeline bounds it?
         for (int v : {0, 16, 32, 64, 48, 80, 96, 112}) {

@@ -78,6 +78,74 @@ __global__ void __launch_bounds__(64) rate_kernel(long long* cycles, int n_iter)
     if (warp == 1) ptx::tmem_dealloc(tmem, 512);
 }
 
+// The plane-sharing conv's exact MMA stream (32->32: rows of 64 B, N=96): per "plane" 3 A tiles (kh) x 3 row shifts (kw)
+// x 2 K slabs against 9 distinct 96-row weight tiles, all accumulating into the same 96 columns; NISS warps issue
+// (warp w takes kh = w when NISS == 3), one commit per plane per issuer onto a barrier nobody waits for.
+template <int NISS>
+__global__ void __launch_bounds__(32 * (NISS + 1)) rs_stream_kernel(long long* cycles, int n_planes) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = ptx::smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    __shared__ __align__(8) uint64_t bar[4];
+    __shared__ uint32_t slot;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { for (int i = 0; i < 4; ++i) ptx::mbar_init(ptx::smem_u32(&bar[i]), 1); ptx::fence_mbar_init(); }
+    if (warp == NISS) ptx::tmem_alloc(ptx::smem_u32(&slot), 512);
+    ptx::tc_fence_before(); __syncthreads(); ptx::tc_fence_after();
+    const uint32_t tmem = slot;
+    constexpr uint32_t A_BYTES = 9216, W_TILE = 6144, STAGE = 3 * A_BYTES;
+    const uint32_t wsm = base, ring = base + 9 * W_TILE;
+    if (warp < NISS) {
+        const uint64_t dsc = ptx::make_kmajor_desc(0u, 64, 0u);
+        const uint32_t desc_hi = (uint32_t)(dsc >> 32);
+        const uint32_t ring_lo = (uint32_t)dsc | (ring >> 4), w_lo = (uint32_t)dsc | (wsm >> 4);
+        constexpr uint32_t idesc = ptx::make_idesc_bf16(96);
+        __syncwarp();
+        const long long t0 = clock64();
+        if (ptx::elect_one_sync()) {
+            int s = 0;
+            for (int pl = 0; pl < n_planes; ++pl) {
+                const uint32_t d = tmem + (uint32_t)((pl % 6) * 32);
+                for (int kh = (NISS == 3 ? warp : 0); kh < 3; kh += (NISS == 3 ? 3 : 1)) {
+                    const uint32_t a0 = ring_lo + (uint32_t)s * (STAGE >> 4) + (uint32_t)((kh * A_BYTES) >> 4);
+                    const uint32_t b0 = w_lo + (uint32_t)((kh * 3 * W_TILE) >> 4);
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+                        for (int k = 0; k < 2; ++k)
+                            ptx::umma_bf16_lohi(d, a0 + ((kw * 64 + k * 32) >> 4), b0 + ((kw * W_TILE + k * 32) >> 4), desc_hi, idesc, 1u);
+                }
+                ptx::umma_commit(ptx::smem_u32(&bar[1]));
+                if (++s == 6) s = 0;
+            }
+            ptx::umma_commit(ptx::smem_u32(&bar[0]) + 8u * 2 + 8u * (warp ? 1 : 0) * 0);
+        }
+        __syncwarp();
+        if (warp == 0) { while (!ptx::mbar_try_wait(ptx::smem_u32(&bar[2]), 0)) {} }
+        const long long t1 = clock64();
+        if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+    }
+    ptx::tc_fence_before(); __syncthreads();
+    if (warp == NISS) ptx::tmem_dealloc(tmem, 512);
+}
+
+template <int NISS>
+void run_rs(const char* what) {
+    const int n_planes = 400;
+    int nsm = 148; cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
+    const size_t smem = 9 * 6144 + 6 * 3 * 9216 + 2048;
+    auto k = rs_stream_kernel<NISS>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    long long* d; cudaMalloc(&d, nsm * sizeof(long long));
+    k<<<nsm, 32 * (NISS + 1), smem>>>(d, n_planes);
+    k<<<nsm, 32 * (NISS + 1), smem>>>(d, n_planes);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long h[1024]; cudaMemcpy(h, d, nsm * sizeof(long long), cudaMemcpyDeviceToHost);
+    double mx = 0; for (int i = 0; i < nsm; ++i) mx = h[i] > mx ? h[i] : mx;
+    printf("%-22s : %7.1f cyc/plane (18 MMAs N=96) = %5.1f cyc/MMA (%s)\n", what, mx / n_planes, mx / n_planes / 18.0, cudaGetErrorString(e));
+    cudaFree(d);
+}
+
 template <int N, int ROWB, int MODE, int ASHIFT = 0>
 void run(const char* what) {
     const int n_iter = 512;
@@ -117,6 +185,7 @@ int main(int argc, char** argv) {
         run<32, 64, SS, 100>("SS-dep"); run<64, 64, SS, 100>("SS-dep"); run<96, 64, SS, 100>("SS-dep"); run<128, 128, SS, 100>("SS-dep");
         run<256, 128, SS, 100>("SS-dep"); run<32, 64, TS, 100>("TS-dep"); run<96, 64, TS, 100>("TS-dep");
     }
+    if (what == 0 || what == 7) { run_rs<1>("RS stream, 1 issuer"); run_rs<3>("RS stream, 3 issuers"); }
     if (what == 0 || what == 4) { run<32, 64, TS_CP>("TS+CP"); run<32, 128, TS_CP>("TS+CP"); run<64, 128, TS_CP>("TS+CP"); }
     return 0;
 }
