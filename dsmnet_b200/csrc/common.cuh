@@ -38,6 +38,17 @@ __device__ __forceinline__ float ld_stream_f1(const float* p) {
     return r;
 }
 
+// 256-bit global accesses (sm_100: LDG.256 / STG.256): one instruction per 32-byte sector, 32-byte aligned addresses
+__device__ __forceinline__ void ld_nc_v8(const void* p, uint4& a, uint4& b) {
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+__device__ __forceinline__ void st_v8(void* p, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+static inline bool dsm_aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);   // .x = lo (low 16 bits)
     return *reinterpret_cast<uint32_t*>(&v);

@@ -673,8 +673,10 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     const int j = 2 * jj + half;
                     const bool ld = residual && valid && j < item.nb;
 #pragma unroll
-                    for (int c = 0; c < NV; ++c)
-                        rv[jj][c] = ld ? __ldg(reinterpret_cast<const uint4*>(resb + o0 + j * ostep) + c) : make_uint4(0u, 0u, 0u, 0u);
+                    for (int c = 0; c < NV; c += 2) {
+                        rv[jj][c] = rv[jj][c + 1] = make_uint4(0u, 0u, 0u, 0u);
+                        if (ld) ld_nc_v8(resb + o0 + j * ostep + 8 * c, rv[jj][c], rv[jj][c + 1]);
+                    }
                 }
                 wait_bar(tfull_bar(acc), acc_ph);
                 __syncwarp();
@@ -692,6 +694,7 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         if (j == my_last) release();
                         if (valid) {
                             uint4* out = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y) + o0 + j * ostep);
+                            uint4 ovp = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
                             for (int c = 0; c < NV; ++c) {
                                 const float4 s0 = sc4[2 * c], s1 = sc4[2 * c + 1], h0 = sh4[2 * c], h1 = sh4[2 * c + 1];
@@ -708,7 +711,7 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                 uint4 ov;
                                 ov.x = pack_bf16x2(f[0], f[1]); ov.y = pack_bf16x2(f[2], f[3]);
                                 ov.z = pack_bf16x2(f[4], f[5]); ov.w = pack_bf16x2(f[6], f[7]);
-                                out[c] = ov;
+                                if (c & 1) st_v8(out + c - 1, ovp, ov); else ovp = ov;      // one 256-bit store per 16 channels
                             }
                         }
                     }
@@ -963,8 +966,10 @@ conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 for (int jj = 0; jj < 4; ++jj) {
                     const bool ld = residual && valid[jj];
 #pragma unroll
-                    for (int c = 0; c < NV; ++c)
-                        rv[jj][c] = ld ? __ldg(reinterpret_cast<const uint4*>(resb + off[jj]) + c) : make_uint4(0u, 0u, 0u, 0u);
+                    for (int c = 0; c < NV; c += 2) {
+                        rv[jj][c] = rv[jj][c + 1] = make_uint4(0u, 0u, 0u, 0u);
+                        if (ld) ld_nc_v8(resb + off[jj] + 8 * c, rv[jj][c], rv[jj][c + 1]);
+                    }
                 }
                 wait_bar(tfull_bar(acc), acc_ph);
                 __syncwarp();
@@ -978,6 +983,7 @@ conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     if (jj == 3) release();
                     if (valid[jj]) {
                         uint4* out = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y) + off[jj]);
+                        uint4 ovp = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
                         for (int c = 0; c < NV; ++c) {
                             const float4 s0 = sc4[2 * c], s1 = sc4[2 * c + 1], h0 = sh4[2 * c], h1 = sh4[2 * c + 1];
@@ -994,7 +1000,7 @@ conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             uint4 ov;
                             ov.x = pack_bf16x2(f[0], f[1]); ov.y = pack_bf16x2(f[2], f[3]);
                             ov.z = pack_bf16x2(f[4], f[5]); ov.w = pack_bf16x2(f[6], f[7]);
-                            out[c] = ov;
+                            if (c & 1) st_v8(out + c - 1, ovp, ov); else ovp = ov;      // one 256-bit store per 16 channels
                         }
                     }
                 }
@@ -1122,6 +1128,7 @@ int conv3d_dispatch(const void* x, const void* w, const float* scale, const floa
     if (y_dtype == DSM_F32) { if (Cout != 1) return DSM_EUNSUPPORTED; NP = 16; }
     else { if (Cout != 16 && Cout != 32 && Cout != 64 && Cout != 128) return DSM_EUNSUPPORTED; NP = Cout; }
     if (!dsm_aligned16(x) || !dsm_aligned16(w) || !dsm_aligned16(y) || (residual && !dsm_aligned16(residual))) return DSM_EALIGN;
+    const bool al32 = dsm_aligned32(y) && (!residual || dsm_aligned32(residual));     // the RS / DC epilogues use 256-bit accesses
     // natural output extent
     int nDo, nHo, nWo;
     if (transposed) { nDo = 2 * D; nHo = 2 * H; nWo = 2 * W; }
@@ -1152,7 +1159,7 @@ int conv3d_dispatch(const void* x, const void* w, const float* scale, const floa
         if (!encode_map(&maps.w, w, 2, dims, strides, box, row_bytes)) return DSM_EDRIVER;
     }
     // transposed, Cout <= 32: the class-sharing kernel (variant bit3 set = keep the per-class kernel, for A/B runs)
-    if (transposed && NP <= 32 && Cin <= 64 && !(variant & 8)) {
+    if (transposed && NP <= 32 && Cin <= 64 && al32 && !(variant & 8)) {
         CUtensorMap map_a;
         cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)P};
         cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
@@ -1176,7 +1183,7 @@ int conv3d_dispatch(const void* x, const void* w, const float* scale, const floa
     // 110 KB weight prologue; the 12x24x78 hourglass bottom is faster on the per-tile kernel)
     const bool rs_grouped = (y_dtype == DSM_BF16 && Cout > 32 && Cout % 32 == 0 && Cout <= 128) &&
                             (long long)B * dsm_ceil_div(Do > 0 ? Do : D, 8) * dsm_ceil_div(Hp * Wp, 128) * (Cout / 32) >= 2LL * DSM_NUM_SMS_B200;
-    if (!transposed && stride == 1 && (NP <= 32 || rs_grouped) && Cin <= 64 && !(variant & 8)) {
+    if (!transposed && stride == 1 && (NP <= 32 || rs_grouped) && Cin <= 64 && al32 && !(variant & 8)) {
         const int NPk = rs_grouped ? 32 : NP;
         CUtensorMap map_a;
         cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)P};
