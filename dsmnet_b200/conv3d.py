@@ -122,3 +122,95 @@ class FusedConv3d:
 def conv_timeouts() -> int:
     """Pipeline waits that timed out inside conv kernels since load (0 in a healthy run)."""
     return _lib.lib().dsm_debug_conv_timeouts()
+
+
+# ------------------------------------------------------------------------------------------------
+# Training path: a differentiable bare convolution on padded NDHWC bf16 volumes.
+#   forward : the same tcgen05 kernels as inference (identity affine, no activation)
+#   dgrad   : those kernels again with transformed weights (see include/dsmnet_b200.h, op 3 training)
+#   wgrad   : dsm_conv3d_wgrad
+# BatchNorm (batch statistics), ReLU and the skip adds of the training graph are stock PyTorch
+# elementwise/reduction ops on views of these volumes (dsmnet_b200/train3d.py) — as in the reference,
+# whose BatchNorm3d/ReLU are stock modules.
+# ------------------------------------------------------------------------------------------------
+
+def _dgrad_layer(weight: torch.Tensor, stride: int, transposed: bool, device) -> "FusedConv3d":
+    """The layer that maps gy to gx for y = conv(x, weight)."""
+    w = weight.detach()
+    if transposed:                    # y = conv_transpose(x, w[Cin][Cout]): gx = conv3d(gy, w, stride 2), w read as [out=Cin][in=Cout]
+        return FusedConv3d(w, None, None, 2, False, 0, device)
+    if stride == 1:                   # gx = conv3d(gy, w'), w'[ci][co][k] = w[co][ci][2-k]
+        return FusedConv3d(w.flip(2, 3, 4).transpose(0, 1).contiguous(), None, None, 1, False, 0, device)
+    # stride 2: gx = conv_transpose3d(gy, w) cropped to x's extent; w[Cout][Cin] is a ConvTranspose weight with in=Cout
+    return FusedConv3d(w, None, None, 2, True, 0, device)
+
+
+_wgrad_ws = {}
+
+
+def _wgrad_workspace(ca: int, cb: int, device) -> torch.Tensor:
+    key = (ca, cb, str(device))
+    ws = _wgrad_ws.get(key)
+    if ws is None:
+        n = _lib.lib().dsm_conv3d_wgrad_workspace_bytes(ca, cb)
+        ws = torch.empty(n // 4, device=device, dtype=torch.float32)
+        _wgrad_ws[key] = ws
+    return ws
+
+
+def conv3d_wgrad(anchor: PaddedVolume, partner: PaddedVolume, stride: int, ca_out: int, cb_out: int) -> torch.Tensor:
+    """dW[ca_out][cb_out][3][3][3] (fp32) from the padded volumes; see dsm_conv3d_wgrad for anchor/partner."""
+    dev = anchor.data.device
+    dw = torch.empty(ca_out, cb_out, 3, 3, 3, device=dev, dtype=torch.float32)
+    ws = _wgrad_workspace(anchor.C, partner.C, dev)
+    _lib.check(_lib.lib().dsm_conv3d_wgrad(
+        anchor.data.data_ptr(), partner.data.data_ptr(), dw.data_ptr(), anchor.B, anchor.C, partner.C,
+        anchor.D, anchor.H, anchor.W, partner.D, partner.H, partner.W, stride, ca_out, cb_out, 0, 0, 0,
+        ws.data_ptr(), ws.numel() * 4, _lib.stream_ptr(dev)), "dsm_conv3d_wgrad")
+    return dw
+
+
+class Conv3dFunction(torch.autograd.Function):
+    """ydata = conv(xdata, weight): k=3, pad=1; `geom` = (B, D, H, W, stride, transposed, (Do, Ho, Wo)).
+    xdata / ydata are the flat bf16 storages of PaddedVolumes (zero rims)."""
+
+    @staticmethod
+    def forward(ctx, xdata, weight, geom):
+        B, D, H, W, stride, transposed, odims = geom
+        cin = weight.shape[0] if transposed else weight.shape[1]
+        cout = weight.shape[1] if transposed else weight.shape[0]
+        x = PaddedVolume(xdata, B, cin, D, H, W)
+        layer = FusedConv3d(weight, None, None, stride, transposed, 0, xdata.device)
+        y = layer(x, PaddedVolume.empty(B, cout, *odims, xdata.device))
+        ctx.save_for_backward(xdata, weight)
+        ctx.geom = geom
+        return y.data
+
+    @staticmethod
+    def backward(ctx, gy):
+        xdata, weight = ctx.saved_tensors
+        B, D, H, W, stride, transposed, odims = ctx.geom
+        cin = weight.shape[0] if transposed else weight.shape[1]
+        cout = weight.shape[1] if transposed else weight.shape[0]
+        dev = xdata.device
+        g = PaddedVolume(gy.contiguous().to(torch.bfloat16), B, cout, *odims)
+        x = PaddedVolume(xdata, B, cin, D, H, W)
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = _dgrad_layer(weight, stride, transposed, dev)(g, PaddedVolume.empty(B, cin, D, H, W, dev)).data
+        if ctx.needs_input_grad[1]:
+            if transposed:
+                gw = conv3d_wgrad(x, g, 2, cin, cout)          # anchor = x (coarse), partner = gy
+            else:
+                gw = conv3d_wgrad(g, x, stride, cout, cin)     # anchor = gy, partner = x
+            gw = gw.to(weight.dtype)
+        return gx, gw, None
+
+
+def conv3d_train(x: PaddedVolume, weight: torch.Tensor, stride: int = 1, transposed: bool = False, out_dims=None) -> PaddedVolume:
+    """Differentiable y = conv(x, weight) on padded volumes (both channel counts in {32, 64, 128})."""
+    cout = weight.shape[1] if transposed else weight.shape[0]
+    nat = conv_out_dims(x.D, x.H, x.W, 2 if transposed else stride, transposed)
+    odims = tuple(out_dims) if out_dims is not None else nat
+    ydata = Conv3dFunction.apply(x.data, weight, (x.B, x.D, x.H, x.W, 2 if transposed else stride, bool(transposed), odims))
+    return PaddedVolume(ydata, x.B, cout, *odims)

@@ -96,6 +96,23 @@ int dsm_conv3d_fwd(const void* x, const void* w_packed, const float* scale, cons
                    int stride, int transposed, int relu, int y_dtype,
                    void* ws, size_t ws_bytes, void* stream);
 
+/* ---- op 3, training: filter gradient of the k=3 convolutions (autograd of the nn.Conv3d / nn.ConvTranspose3d
+ * modules cited above).  The INPUT gradient (dgrad) needs no entry point of its own: it is dsm_conv3d_fwd with
+ * transformed weights (stride-1 conv: flipped taps and swapped channels; stride-2 conv: the transposed conv of
+ * gy with the same filter; transposed conv: the stride-2 conv of gy) — see dsmnet_b200/conv3d.py.
+ *   anchor  : the coarser of (x, gy), padded NDHWC bf16 [B][Da+2][Ha+2][Wa+2][Ca]
+ *             (conv: gy, Ca = Cout;  transposed conv: x, Ca = Cin)
+ *   partner : the other one, [B][Dp+2][Hp+2][Wp+2][Cb]; partner voxel = stride*anchor + tap - 1 per axis
+ *   dw      : fp32 [Ca_out][Cb_out][3][3][3] = PyTorch's weight layout for both module types
+ *             (Ca_out <= Ca, Cb_out <= Cb: the tensors may carry zero-padded channels)
+ *   scale_a / scale_b : optional per-channel factors (the folded BatchNorm scale on the gy side), NULL = 1
+ *   accumulate : 0 overwrite dw, 1 add to it;   ws: dsm_conv3d_wgrad_workspace_bytes(Ca, Cb) bytes of scratch  */
+size_t dsm_conv3d_wgrad_workspace_bytes(int Ca, int Cb);
+int dsm_conv3d_wgrad(const void* anchor, const void* partner, float* dw,
+                     int B, int Ca, int Cb, int Da, int Ha, int Wa, int Dp, int Hp, int Wp, int stride,
+                     int Ca_out, int Cb_out, const float* scale_a, const float* scale_b, int accumulate,
+                     void* ws, size_t ws_bytes, void* stream);
+
 /* layout converters at the reference boundary (NCDHW fp32 <-> padded NDHWC bf16)             */
 int dsm_pack_ndhwc(const float* x_ncdhw, void* y_padded_bf16, int B, int C, int D, int H, int W, void* stream);
 int dsm_unpack_ndhwc(const void* x_padded_bf16, float* y_ncdhw, int B, int C, int D, int H, int W, void* stream);
