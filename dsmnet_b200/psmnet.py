@@ -11,8 +11,9 @@ path from the two feature maps on — concat volume (stackhourglass.py:124-133),
 (:135-149) and the three upsample+softmax+regression heads (:152-166) — runs as:
   concat_volume (padded NDHWC bf16)  ->  25 fused tcgen05 conv blocks  ->  3 fp32 Cout=1 convs
   ->  3 fused upsample+soft-argmin kernels.
-Inference (eval-mode BatchNorm folded into the conv epilogue).  Training the 3-D stack needs the
-conv backward kernels and is not part of this round: calling it in train mode raises.
+Inference: eval-mode BatchNorm folded into the conv epilogue, everything fused.  With gradients enabled
+(train mode, or eval-mode with parameters/inputs that require grad) the same graph runs through
+``aggregate_train``: convolutions forward/backward on the sm_100a kernels, BatchNorm/ReLU/adds as stock ops.
 """
 from __future__ import annotations
 
@@ -143,11 +144,44 @@ class PSMNetHotPath(nn.Module):
         return ws
 
     # -- the path -----------------------------------------------------------------------------
+    def aggregate_train(self, fL, fR):
+        """The same graph with autograd (stackhourglass.py:123-149): convolutions fwd/bwd on the sm_100a kernels,
+        BatchNorm with batch statistics / ReLU / adds as stock PyTorch ops (dsmnet_b200/train3d.py)."""
+        from . import train3d as T
+        D = self.maxdisp // 4
+        vol = T.volume_from_ncdhw(concat_volume(fL, fR, D, "psm"))
+
+        def cb(seq, x, relu=0, residual=None):
+            return T.conv_bn_act(x, seq[0], seq[1], relu, residual)
+
+        c0 = cb(self.dres0[0], vol, 1)
+        c0 = cb(self.dres0[2], c0, 1)
+        t = cb(self.dres1[0], c0, 1)
+        cost0 = cb(self.dres1[2], t, 0, c0)
+
+        def hg(h, x, presqu, postsqu):
+            out = cb(h.conv1[0], x, 1)
+            pre = cb(h.conv2, out, 1, postsqu)
+            out = cb(h.conv3[0], pre, 1)
+            out = cb(h.conv4[0], out, 1)
+            post = cb(h.conv5, out, 1, presqu if presqu is not None else pre)
+            return cb(h.conv6, post, 0, cost0), pre, post            # "+ cost0" of :139,142,145
+
+        out1, pre1, post1 = hg(self.dres2, cost0, None, None)
+        out2, pre2, post2 = hg(self.dres3, out1, pre1, post1)
+        out3, pre3, post3 = hg(self.dres4, out2, pre1, post2)        # pre1, as in :144
+        costs, prev = [], None
+        for c, x in ((self.classif1, out1), (self.classif2, out2), (self.classif3, out3)):
+            cur = T.conv_c1(cb(c[0], x, 1), c[2])
+            prev = cur if prev is None else cur + prev               # :148-149
+            costs.append(prev)
+        return costs
+
     def aggregate(self, fL, fR):
         """concat volume + dres0..classif3 -> (cost1, cost2, cost3), fp32 [B, D/4, H/4, W/4] each."""
-        if self.training:
-            raise _lib.DsmError("PSMNetHotPath: training-mode 3-D stack (conv backward, batch-stat BN) is not "
-                                "implemented on the sm_100a path yet; call .eval() — there is no fallback")
+        if self.training or torch.is_grad_enabled() and (fL.requires_grad or fR.requires_grad or
+                                                         any(p.requires_grad for p in self.parameters())):
+            return self.aggregate_train(fL, fR)
         B, C, H, W = fL.shape
         D = self.maxdisp // 4
         plan = self._get_plan(fL.device)
@@ -182,6 +216,12 @@ class PSMNetHotPath(nn.Module):
 
     def forward(self, fL, fR, out_hw):
         c1, c2, c3 = self.aggregate(fL, fR)
+        if c1.requires_grad:
+            # differentiable heads (stackhourglass.py:152-166): stock trilinear upsample + the soft-argmin op (fwd+bwd kernels)
+            from .softargmin import softargmin
+            size = [self.maxdisp, out_hw[0], out_hw[1]]
+            return [softargmin(F.interpolate(c.unsqueeze(1), size=size, mode="trilinear", align_corners=self.align_corners).squeeze(1), 1.0)
+                    for c in (c3, c2, c1)]
         B, _, H, W = fL.shape
         ws = self._workspace(B, self.maxdisp // 4, H, W, fL.device)
         size = (self.maxdisp, out_hw[0], out_hw[1])

@@ -569,3 +569,58 @@ def gcnet_random_params(seed: int = 0, calibrate_on: Optional[torch.Tensor] = No
         x23 = cal("l23", cal("l22", x21)); x35 = cal("l35", x34, 2, True, x23)
         x20 = cal("l20", cal("l19", c)); cal("l36", x35, 2, True, x20)
     return params
+
+
+# ------------------------------------------------------------------------------------------
+# training-mode restatement (BatchNorm with batch statistics), differentiable with torch autograd
+# ------------------------------------------------------------------------------------------
+
+def _convbn_train(params, prefix, x, stride=1, transposed=False, residual=None, relu=0, operand_dtype=None, eps=1e-5):
+    """convbn_3d in TRAIN mode (submodule.py:16-19 under model.train()): conv -> batch-stat BatchNorm -> [+res] -> [relu].
+    `operand_dtype=torch.bfloat16` rounds conv operands and the stored block output like the kernels do (straight-through
+    for autograd)."""
+    def rnd(t):
+        return t if operand_dtype is None else t + (t.to(operand_dtype).float() - t).detach()
+    w = params[prefix + ".0.weight"]
+    y = F.conv_transpose3d(rnd(x), rnd(w), None, stride=2, padding=1, output_padding=1) if transposed else \
+        F.conv3d(rnd(x), rnd(w), None, stride=stride, padding=1)
+    y = rnd(y)                                            # the conv kernel stores bf16
+    y = F.batch_norm(y, None, None, params[prefix + ".1.weight"], params[prefix + ".1.bias"], True, 0.1, eps)
+    if residual is not None:
+        y = crop_add(y, residual)
+    if relu:
+        y = F.relu(y)
+    return rnd(y)
+
+
+def psmnet_hotpath_train(params: Dict[str, torch.Tensor], fL: torch.Tensor, fR: torch.Tensor, maxdisp: int,
+                         out_hw: Tuple[int, int], align_corners: bool = True, operand_dtype=None):
+    """PSMNet.forward from the feature maps on in TRAIN mode (stackhourglass.py:123-168 under model.train()):
+    the graph of psmnet_hotpath with batch-statistics BatchNorm; every tensor in `params` / fL / fR may require grad."""
+    od = operand_dtype
+    cost = concat_volume(fL, fR, maxdisp // 4, "psm")
+    cb = lambda p, x, s=1, t=False, r=None, relu=0: _convbn_train(params, p, x, s, t, r, relu, od)
+    c0 = cb("dres0.0", cost, relu=1); c0 = cb("dres0.2", c0, relu=1)
+    t = cb("dres1.0", c0, relu=1); cost0 = cb("dres1.2", t, r=c0)
+
+    def hg(p, x, presqu, postsqu):
+        out = cb(p + ".conv1.0", x, 2, relu=1)
+        pre = cb(p + ".conv2", out, r=postsqu, relu=1)
+        out = cb(p + ".conv3.0", pre, 2, relu=1)
+        out = cb(p + ".conv4.0", out, relu=1)
+        post = cb(p + ".conv5", out, t=True, r=presqu if presqu is not None else pre, relu=1)
+        return cb(p + ".conv6", post, t=True, r=cost0), pre, post
+
+    out1, pre1, post1 = hg("dres2", cost0, None, None)
+    out2, pre2, post2 = hg("dres3", out1, pre1, post1)
+    out3, pre3, post3 = hg("dres4", out2, pre1, post2)
+
+    def classif(p, x):
+        t = cb(p + ".0", x, relu=1)
+        w = params[p + ".2.weight"]
+        if od is not None:
+            w = w + (w.to(od).float() - w).detach()
+        return F.conv3d(t, w, None, stride=1, padding=1)
+    cost1 = classif("classif1", out1); cost2 = classif("classif2", out2) + cost1; cost3 = classif("classif3", out3) + cost2
+    size = [maxdisp, out_hw[0], out_hw[1]]
+    return [upsample_softargmin(c.squeeze(1), size, align_corners) for c in (cost3, cost2, cost1)]

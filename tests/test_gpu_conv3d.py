@@ -212,9 +212,67 @@ def test_gcnet_hotpath_vs_oracle(B, H, W, maxdisp):
     assert float((disp - ref).abs().mean()) < 2.0 * d_fmt + 0.02
 
 
-def test_training_mode_raises():
+def test_gcnet_training_mode_raises():
+    """GC-Net's 3-D stack has no training graph yet: it must say so, not fall back"""
     from dsmnet_b200 import _lib
-    from dsmnet_b200.psmnet import PSMNetHotPath
-    m = PSMNetHotPath(32).cuda().train()
+    from dsmnet_b200.gcnet import GCNetHotPath
+    m = GCNetHotPath(16).cuda().train()
     with pytest.raises(_lib.DsmError):
-        m(torch.randn(1, 32, 8, 12, device="cuda"), torch.randn(1, 32, 8, 12, device="cuda"), (32, 48))
+        m(torch.randn(1, 32, 16, 16, device="cuda"), torch.randn(1, 32, 16, 16, device="cuda"))
+
+
+def test_psmnet_training_step_gradients():
+    """train-mode PSMNet 3-D stack (batch-stat BatchNorm): loss and gradients w.r.t. the feature maps and the
+    parameters vs torch autograd of the oracle's fp32 restatement (stackhourglass.py:123-168 under model.train())."""
+    from dsmnet_b200.psmnet import PSMNetHotPath
+    from dsmnet_b200.conv3d import conv_timeouts
+    torch.manual_seed(3)
+    B, h, w, maxdisp = 2, 8, 16, 32
+    fL = torch.randn(B, 32, h, w); fR = torch.randn(B, 32, h, w)
+    params = O.psmnet_random_params(seed=17)
+    gt = torch.rand(B, 4 * h, 4 * w) * maxdisp * 0.5
+
+    def loss_of(preds):
+        return sum(wt * (p - gt).abs().mean() for wt, p in zip((1.0, 0.7, 0.5), preds))     # the reference's weighted L1 pyramid
+
+    # oracle, fp32
+    pr = {k: v.clone().requires_grad_(v.dim() == 5 or k.endswith(".1.weight") or k.endswith(".1.bias")) for k, v in params.items()}
+    a = fL.clone().requires_grad_(); b = fR.clone().requires_grad_()
+    lref = loss_of(O.psmnet_hotpath_train(pr, a, b, maxdisp, (4 * h, 4 * w)))
+    lref.backward()
+    # oracle with bf16 operand / storage emulation (straight-through): the format-error yardstick
+    pe = {k: v.clone().requires_grad_(v.dim() == 5 or k.endswith(".1.weight") or k.endswith(".1.bias")) for k, v in params.items()}
+    ae = fL.clone().requires_grad_(); be = fR.clone().requires_grad_()
+    lemu = loss_of(O.psmnet_hotpath_train(pe, ae, be, maxdisp, (4 * h, 4 * w), operand_dtype=torch.bfloat16))
+    lemu.backward()
+    # CUDA path
+    m = PSMNetHotPath(maxdisp)
+    m.load_state_dict(params, strict=False)
+    m = m.cuda().train()
+    x = fL.cuda().requires_grad_(); y = fR.cuda().requires_grad_()
+    gtc = gt.cuda()
+    preds = m(x, y, (4 * h, 4 * w))
+    loss = sum(wt * (p - gtc).abs().mean() for wt, p in zip((1.0, 0.7, 0.5), preds))
+    loss.backward()
+    torch.cuda.synchronize()
+    assert conv_timeouts() == 0
+    print("loss: ours %.5f, oracle fp32 %.5f, oracle bf16-emulation %.5f" % (float(loss), float(lref), float(lemu)))
+    assert abs(float(loss) - float(lref)) < 0.02 * abs(float(lref))
+
+    def cos(u, v):
+        return float(torch.nn.functional.cosine_similarity(u.flatten().double(), v.flatten().double(), dim=0))
+
+    named = dict(m.named_parameters())
+    checks = [("fL", x.grad.cpu(), a.grad, ae.grad), ("fR", y.grad.cpu(), b.grad, be.grad)]
+    for k in ("dres0.0.0.weight", "dres0.2.0.weight", "dres1.2.0.weight", "dres2.conv1.0.0.weight", "dres2.conv2.0.weight",
+              "dres3.conv5.0.weight", "dres4.conv6.0.weight", "classif1.0.0.weight", "classif3.2.weight",
+              "dres2.conv2.1.weight", "dres4.conv6.1.bias"):
+        checks.append((k, named[k].grad.cpu(), pr[k].grad, pe[k].grad))
+    for name, mine, ref, emu in checks:
+        c_ref, c_emu, c_fmt = cos(mine, ref), cos(mine, emu), cos(emu, ref)
+        print("grad %-26s cos(ours,fp32) %.4f  cos(ours,emu) %.4f  cos(emu,fp32) %.4f  |ours|/|ref| %.3f" %
+              (name, c_ref, c_emu, c_fmt, float(mine.norm() / ref.norm())))
+        # direction and magnitude of every gradient; the yardstick is what the bf16 operand/storage format alone does to
+        # the fp32 gradient of this random, batch-normalised (hence noise-amplifying) network: cos(emu, fp32) ~ 0.97
+        assert c_ref > 0.9 and 0.85 < float(mine.norm() / ref.norm()) < 1.15
+        assert c_ref > c_fmt - 0.03                                             # no worse than the bf16 format itself
