@@ -4,9 +4,9 @@ soft-argmin of MINUS the cost (:104-111).
 
 ``feature3d`` keeps the reference's constructor and parameter names (``l19.0.weight``, ``l19.0.bias``,
 ``l19.1.running_var``, ..., bare ``l37.weight``) so that the ``layer3d.*`` part of a reference
-``state_dict`` loads unchanged.  Inference only (eval-mode BatchNorm folded into the conv epilogue);
-training-mode BatchNorm and the conv backward kernels are not built, and calling it in train mode
-raises — there is no fallback.  The 2-D trunk ``feature2d`` (:14-29) is a caller of the path and stays
+``state_dict`` loads unchanged.  Inference: eval-mode BatchNorm folded into the conv epilogue, everything
+fused.  With gradients enabled (train mode) the same graph runs with autograd: convolutions forward /
+backward on the sm_100a kernels, BatchNorm with batch statistics, ReLU and skip adds as stock ops.  The 2-D trunk ``feature2d`` (:14-29) is a caller of the path and stays
 stock PyTorch in the reference; ``GCNetHotPath`` therefore starts from the two feature maps.
 """
 from __future__ import annotations
@@ -98,11 +98,27 @@ class feature3d(nn.Module):
         self._ws[key] = ws
         return ws
 
+    def aggregate_train(self, vol: PaddedVolume) -> torch.Tensor:
+        """The same graph with autograd (gcnet.py:65-101 under model.train()): convolutions fwd/bwd on the sm_100a
+        kernels, BatchNorm with batch statistics / ReLU / skip adds as stock PyTorch ops (dsmnet_b200/train3d.py)."""
+        from . import train3d as T
+
+        def g(name, x, residual=None):
+            seq = getattr(self, name)
+            return T.conv_bn_act(x, seq[0], seq[1], 2, residual)       # conv+bias -> BN -> ReLU, then the skip add
+
+        x21 = g("l21", vol); x24 = g("l24", x21); x27 = g("l27", x24); x30 = g("l30", x27)
+        x32 = g("l32", g("l31", x30))
+        x29 = g("l29", g("l28", x27)); x33 = g("l33", x32, x29)
+        x26 = g("l26", g("l25", x24)); x34 = g("l34", x33, x26)
+        x23 = g("l23", g("l22", x21)); x35 = g("l35", x34, x23)
+        x20 = g("l20", g("l19", vol)); x36 = g("l36", x35, x20)
+        return T.conv_c1(x36, self.l37)
+
     def aggregate(self, vol: PaddedVolume) -> torch.Tensor:
         """x37 of gcnet.py:65-101 as fp32 [B, 2D, 2H, 2W]."""
-        if self.training:
-            raise _lib.DsmError("feature3d: training-mode BatchNorm / conv backward are not implemented on the sm_100a "
-                                "path; call .eval() — there is no fallback")
+        if self.training or torch.is_grad_enabled() and (vol.data.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return self.aggregate_train(vol)
         dev = vol.data.device
         p = self._get_plan(dev)
         ws = self._workspace(vol.B, vol.D, vol.H, vol.W, dev)
@@ -140,6 +156,11 @@ class GCNetHotPath(nn.Module):
         self.layer3d = feature3d(32)
 
     def forward(self, fL, fR):
-        vol = concat_volume(fL, fR, self.D, "gc", padded_bf16=True)
+        if self.training or torch.is_grad_enabled() and (fL.requires_grad or fR.requires_grad or
+                                                         any(p.requires_grad for p in self.parameters())):
+            from .train3d import volume_from_ncdhw
+            vol = volume_from_ncdhw(concat_volume(fL, fR, self.D, "gc"))     # differentiable NCDHW volume -> padded bf16
+        else:
+            vol = concat_volume(fL, fR, self.D, "gc", padded_bf16=True)
         x37 = self.layer3d.aggregate(vol)
         return softargmin(x37, -1.0).unsqueeze(1)

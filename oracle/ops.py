@@ -624,3 +624,33 @@ def psmnet_hotpath_train(params: Dict[str, torch.Tensor], fL: torch.Tensor, fR: 
     cost1 = classif("classif1", out1); cost2 = classif("classif2", out2) + cost1; cost3 = classif("classif3", out3) + cost2
     size = [maxdisp, out_hw[0], out_hw[1]]
     return [upsample_softargmin(c.squeeze(1), size, align_corners) for c in (cost3, cost2, cost1)]
+
+
+def gcnet_hotpath_train(params: Dict[str, torch.Tensor], fL: torch.Tensor, fR: torch.Tensor, maxdisp: int, operand_dtype=None,
+                        eps: float = 1e-5) -> torch.Tensor:
+    """gcnet.forward from the feature maps on in TRAIN mode (gcnet.py:129-137, feature3d :65-111 under model.train()):
+    conv+bias -> batch-stat BatchNorm -> ReLU, skip adds after the activation; differentiable with torch autograd."""
+    od = operand_dtype
+
+    def rnd(t):
+        return t if od is None else t + (t.to(od).float() - t).detach()
+
+    def g(name, x, stride=1, transposed=False, residual=None):
+        w, b = params[name + ".0.weight"], params[name + ".0.bias"]
+        y = F.conv_transpose3d(rnd(x), rnd(w), None, stride=2, padding=1, output_padding=1) if transposed else \
+            F.conv3d(rnd(x), rnd(w), None, stride=stride, padding=1)
+        y = rnd(y) + b.view(1, -1, 1, 1, 1)
+        y = F.relu(F.batch_norm(y, None, None, params[name + ".1.weight"], params[name + ".1.bias"], True, 0.1, eps))
+        if residual is not None:
+            y = crop_add(y, residual)
+        return rnd(y)
+
+    cost = concat_volume(fL, fR, maxdisp // 2, "gc")
+    x21 = g("l21", cost, 2); x24 = g("l24", x21, 2); x27 = g("l27", x24, 2); x30 = g("l30", x27, 2)
+    x32 = g("l32", g("l31", x30))
+    x29 = g("l29", g("l28", x27)); x33 = g("l33", x32, 2, True, x29)
+    x26 = g("l26", g("l25", x24)); x34 = g("l34", x33, 2, True, x26)
+    x23 = g("l23", g("l22", x21)); x35 = g("l35", x34, 2, True, x23)
+    x20 = g("l20", g("l19", cost)); x36 = g("l36", x35, 2, True, x20)
+    x37 = F.conv_transpose3d(rnd(x36), rnd(params["l37.weight"]), params["l37.bias"], stride=2, padding=1, output_padding=1)
+    return softargmin(x37.squeeze(1), -1.0).unsqueeze(1)
