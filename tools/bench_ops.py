@@ -168,6 +168,37 @@ def main():
         t = timeit(lambda i: psm(pl, pr, (384, 1248)), reps=10)
         tens("PSMNet hot path fwd 384x1248 maxdisp 192 (volume + 28 convs + 3 heads)", 926.7e9, t)
 
+    # ---- training steps (eager autograd; convolutions fwd/dgrad/wgrad on the sm_100a kernels) ------------------
+    def eager_time(fn, reps=3):
+        fn(); torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e-3
+
+    gc.train()
+    gtg = torch.rand(1, 1, 256, 512, device=dev) * 96
+
+    def gc_step():
+        gc.zero_grad(set_to_none=True)
+        (gc(gl, gr) - gtg).abs().mean().backward()
+    t = eager_time(gc_step)
+    tens("GC-Net 3-D path TRAIN step fwd+bwd 256x512 (cfg3; flops = 3x fwd)", 3 * 882.6e9, t)
+    print("    peak memory %.1f GB" % (torch.cuda.max_memory_allocated() / 1e9))
+    del gc
+    torch.cuda.empty_cache(); torch.cuda.reset_peak_memory_stats()
+    psm.train()
+    gtp = torch.rand(1, 384, 1248, device=dev) * 96
+
+    def psm_step():
+        psm.zero_grad(set_to_none=True)
+        sum((p - gtp).abs().mean() for p in psm(pl, pr, (384, 1248))).backward()
+    t = eager_time(psm_step)
+    tens("PSMNet 3-D path TRAIN step fwd+bwd 384x1248 (flops = 3x fwd)", 3 * 926.7e9, t)
+    print("    peak memory %.1f GB" % (torch.cuda.max_memory_allocated() / 1e9))
+
     if args.json:
         json.dump({"peaks": {"hbm_gbs": hbm, "bf16_tflops": tf, "source": which}, "rows": rows}, open(args.json, "w"), indent=1)
 
