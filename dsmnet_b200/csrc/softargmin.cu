@@ -201,27 +201,27 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
-// One CTA = 128 consecutive output pixels of one output row.  MAXDL bounds the low-res depth so
-// that the interpolated column lives in registers.
+// One CTA = 256 consecutive output pixels of one output row (two per thread).
 //  1. tables (shared): l1[d] = D-axis interpolation weight of output plane d, cnt[dl] = how many
 //     output planes have low-res source plane dl (they are consecutive in d);
 //  2. the low-res row pair (h0,h1) the output row falls between is blended ONCE per CTA into shared
-//     memory: row[dl][j] for the ~0.25*128+2 low-res columns the CTA touches (coalesced reads);
-//  3. each thread blends its two columns -> c[dl] (registers), takes the max (a linear interpolation
-//     never exceeds its end points, so max_d of the upsampled column <= max_dl c[dl]: the softmax is a
-//     single pass), pre-scales by log2(e), and walks the D planes: one FMA + one ex2 + two
-//     accumulations per plane.
-template <int MAXDL>
+//     memory: row[dl][j] for the ~0.25*128+2 low-res columns the CTA touches (warp = a group of planes,
+//     lanes = columns: no index division, eight independent loads in flight per thread);
+//  3. each thread blends its two columns per plane on the fly: a first sweep over the Dl planes finds the
+//     maximum (a linear interpolation never exceeds its end points, so max_d of the upsampled column
+//     <= max_dl c[dl] and the softmax is a single pass), a second sweep walks the D planes: one FMA + one
+//     ex2 + two accumulations per plane.  The loops are real loops (compact code: the first, fully
+//     unrolled version of this kernel spent a third of its time on instruction-cache misses).
 __global__ void __launch_bounds__(128)
 upsample_softargmin_kernel(const float* __restrict__ cost, float* __restrict__ disp,
                            int Dl, int Hl, int Wl, int D, int H, int W,
                            float sd, float sh, float sw, int align_corners, int rw) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* s_l1 = reinterpret_cast<float*>(smem_raw);        // [D]
-    int* s_cnt = reinterpret_cast<int*>(s_l1 + D);           // [MAXDL]
-    float* s_row = reinterpret_cast<float*>(s_cnt + MAXDL);  // [Dl][rw]
-    const int tid = threadIdx.x;
-    for (int i = tid; i < MAXDL; i += blockDim.x) s_cnt[i] = 0;
+    int* s_cnt = reinterpret_cast<int*>(s_l1 + D);           // [Dl]
+    float* s_row = reinterpret_cast<float*>(s_cnt + Dl);     // [Dl + 1][rw]   (one extra, zero, row: the clamped top interval)
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    for (int i = tid; i < Dl; i += blockDim.x) s_cnt[i] = 0;
     __syncthreads();
     for (int d = tid; d < D; d += blockDim.x) {
         int d0, d1; float l1;
@@ -229,7 +229,7 @@ upsample_softargmin_kernel(const float* __restrict__ cost, float* __restrict__ d
         s_l1[d] = (d1 == d0) ? 0.f : l1;                     // clamped top: both taps are the same plane
         atomicAdd(&s_cnt[d0], 1);
     }
-    const int x0 = blockIdx.x * blockDim.x;
+    const int x0 = blockIdx.x * (2 * blockDim.x);            // a thread owns pixels x0+tid and x0+128+tid (shares the d tables)
     const int y = blockIdx.y, b = blockIdx.z;
     int h0, h1, wb, wb1; float lh1, lwb;
     src_index(y, sh, Hl, align_corners, h0, h1, lh1);
@@ -237,47 +237,62 @@ upsample_softargmin_kernel(const float* __restrict__ cost, float* __restrict__ d
     const float lh0 = 1.f - lh1;
     const float* base = cost + (size_t)b * Dl * Hl * Wl;
     const size_t pl = (size_t)Hl * Wl;
-    for (int idx = tid; idx < Dl * rw; idx += blockDim.x) {
-        const int dl = idx / rw, j = idx - dl * rw;
+    for (int j = lane; j < rw; j += 32) {
         const int wl = min(wb + j, Wl - 1);
-        const float* p = base + (size_t)dl * pl + wl;
-        s_row[idx] = lh0 * __ldg(p + (size_t)h0 * Wl) + lh1 * __ldg(p + (size_t)h1 * Wl);
+        const float* p0 = base + (size_t)h0 * Wl + wl;
+        const float* p1 = base + (size_t)h1 * Wl + wl;
+        for (int dl = wrp; dl < Dl; dl += 16) {              // 4 warps x 4 planes per trip: 8 loads in flight
+            float a[4], c[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int dd = min(dl + 4 * u, Dl - 1);
+                a[u] = __ldg(p0 + (size_t)dd * pl); c[u] = __ldg(p1 + (size_t)dd * pl);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (dl + 4 * u < Dl) s_row[(dl + 4 * u) * rw + j] = lh0 * a[u] + lh1 * c[u];
+        }
+        if (wrp == 0) s_row[Dl * rw + j] = 0.f;
     }
     __syncthreads();
-    const int x = x0 + tid;
-    if (x >= W) return;
-    int w0, w1; float lw1;
-    src_index(x, sw, Wl, align_corners, w0, w1, lw1);
-    const float lw0 = 1.f - lw1;
-    const int j0 = w0 - wb, j1 = w1 - wb;
-    float c[MAXDL + 1];
-    float m = -INFINITY;
-#pragma unroll
-    for (int dl = 0; dl < MAXDL; ++dl) {
-        if (dl < Dl) {
-            c[dl] = lw0 * s_row[dl * rw + j0] + lw1 * s_row[dl * rw + j1];
-            m = fmaxf(m, c[dl]);
-        } else c[dl] = 0.f;
+    const int xa = x0 + tid, xb = min(xa + (int)blockDim.x, W - 1);      // xb clamped: computed, stored only if in range
+    if (xa >= W) return;
+    int w0, w1; float lwa1, lwb1;
+    src_index(xa, sw, Wl, align_corners, w0, w1, lwa1);
+    const float* ra0 = s_row + (w0 - wb); const float* ra1 = s_row + (w1 - wb);
+    src_index(xb, sw, Wl, align_corners, w0, w1, lwb1);
+    const float* rb0 = s_row + (w0 - wb); const float* rb1 = s_row + (w1 - wb);
+    const float lwa0 = 1.f - lwa1, lwb0 = 1.f - lwb1;
+    float ma = -INFINITY, mb = -INFINITY;
+    for (int dl = 0; dl < Dl; ++dl) {
+        ma = fmaxf(ma, lwa0 * ra0[dl * rw] + lwa1 * ra1[dl * rw]);
+        mb = fmaxf(mb, lwb0 * rb0[dl * rw] + lwb1 * rb1[dl * rw]);
     }
-    c[MAXDL] = 0.f;
     constexpr float LOG2E = 1.4426950408889634f;
-    const float ml = m * LOG2E;
-#pragma unroll
-    for (int dl = 0; dl <= MAXDL; ++dl) c[dl] = fmaf(c[dl], LOG2E, -ml);
-    float s = 0.f, t = 0.f, fd = 0.f;
+    const float mla = ma * LOG2E, mlb = mb * LOG2E;
+    float sa = 0.f, ta = 0.f, sb = 0.f, tb = 0.f, fd = 0.f;
+    float a0 = fmaf(lwa0 * ra0[0] + lwa1 * ra1[0], LOG2E, -mla);
+    float b0 = fmaf(lwb0 * rb0[0] + lwb1 * rb1[0], LOG2E, -mlb);
     int d = 0;
-#pragma unroll
-    for (int dl = 0; dl < MAXDL; ++dl) {
-        if (dl < Dl) {
-            const float a0 = c[dl], da = c[dl + 1] - a0;
-            const int n = s_cnt[dl];
-            for (int k = 0; k < n; ++k, ++d) {
-                const float e = ex2_approx(fmaf(s_l1[d], da, a0));
-                s += e; t = fmaf(fd, e, t); fd += 1.f;
-            }
+    for (int dl = 0; dl < Dl; ++dl) {
+        const int o = (dl + 1) * rw;                           // row Dl is zero and so is its weight (clamped top)
+        const float a1 = fmaf(lwa0 * ra0[o] + lwa1 * ra1[o], LOG2E, -mla);
+        const float b1 = fmaf(lwb0 * rb0[o] + lwb1 * rb1[o], LOG2E, -mlb);
+        const float da = a1 - a0, db = b1 - b0;
+        const int n = s_cnt[dl];
+        for (int k = 0; k < n; ++k, ++d) {
+            const float l = s_l1[d];
+            const float ea = ex2_approx(fmaf(l, da, a0));
+            const float eb = ex2_approx(fmaf(l, db, b0));
+            sa += ea; ta = fmaf(fd, ea, ta);
+            sb += eb; tb = fmaf(fd, eb, tb);
+            fd += 1.f;
         }
+        a0 = a1; b0 = b1;
     }
-    disp[((size_t)b * H + y) * W + x] = t / s;
+    float* o = disp + ((size_t)b * H + y) * W;
+    o[xa] = ta / sa;
+    if (xa + (int)blockDim.x < W) o[xa + blockDim.x] = tb / sb;
 }
 
 }  // namespace
@@ -334,16 +349,11 @@ extern "C" int dsm_upsample_softargmin_fwd(const float* cost_lr, float* disp, in
         return (float)in / (float)out;
     };
     const float sw = scale(Wl, W);
-    const int rw = (int)(sw * 127.f) + 3;                    // low-res columns one 128-pixel CTA can touch
-    const int maxdl = Dl <= 16 ? 16 : (Dl <= 48 ? 48 : 96);
-    const size_t smem = (size_t)D * sizeof(float) + (size_t)maxdl * sizeof(int) + (size_t)Dl * rw * sizeof(float);
+    const int rw = (int)(sw * 255.f) + 3;                    // low-res columns one 256-pixel CTA can touch
+    const size_t smem = (size_t)D * sizeof(float) + (size_t)Dl * sizeof(int) + (size_t)(Dl + 1) * rw * sizeof(float);
     if (smem > 48 * 1024) return DSM_EUNSUPPORTED;
-    const dim3 grid(dsm_ceil_div(W, 128), H, B);
-    cudaStream_t st = (cudaStream_t)stream;
-#define DSM_UPS(MAXDL) upsample_softargmin_kernel<MAXDL><<<grid, 128, smem, st>>>( \
-        cost_lr, disp, Dl, Hl, Wl, D, H, W, scale(Dl, D), scale(Hl, H), sw, align_corners, rw)
-    if (Dl <= 16) DSM_UPS(16); else if (Dl <= 48) DSM_UPS(48); else if (Dl <= 96) DSM_UPS(96);
-    else return DSM_EUNSUPPORTED;
-#undef DSM_UPS
+    const dim3 grid(dsm_ceil_div(W, 256), H, B);
+    upsample_softargmin_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(
+        cost_lr, disp, Dl, Hl, Wl, D, H, W, scale(Dl, D), scale(Hl, H), sw, align_corners, rw);
     return dsm_launch_status();
 }
