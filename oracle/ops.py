@@ -654,3 +654,68 @@ def gcnet_hotpath_train(params: Dict[str, torch.Tensor], fL: torch.Tensor, fR: t
     x20 = g("l20", g("l19", cost)); x36 = g("l36", x35, 2, True, x20)
     x37 = F.conv_transpose3d(rnd(x36), rnd(params["l37.weight"]), params["l37.bias"], stride=2, padding=1, output_padding=1)
     return softargmin(x37.squeeze(1), -1.0).unsqueeze(1)
+
+
+# ------------------------------------------------------------------------------------------
+# DispNetC (BASELINE config 1): the caller of op 1, restated functionally for model-level parity
+# ------------------------------------------------------------------------------------------
+
+_DISPNETC_ENC = [("conv1", 3, 64, 7, 2), ("conv2", 64, 128, 5, 2), ("redir", 128, 64, 1, 1), ("conv3a", 105, 256, 5, 2),
+                 ("conv3b", 256, 256, 3, 1), ("conv4a", 256, 512, 3, 2), ("conv4b", 512, 512, 3, 1), ("conv5a", 512, 512, 3, 2),
+                 ("conv5b", 512, 512, 3, 1), ("conv6a", 512, 1024, 3, 2), ("conv6b", 1024, 1024, 3, 1)]
+_DISPNETC_DEC = [(5, 1024, 512, 1025), (4, 512, 256, 769), (3, 256, 128, 385), (2, 128, 64, 193), (1, 64, 32, 97)]
+
+
+def dispnetc_random_params(seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Synthetic DispNetC parameters under the reference's names, init law of net_init (util_conv.py:32-53) with the
+    pr* weights scaled by 0.1 (dispnetcorr.py:63-64); numpy RNG so that every host builds the same tensors."""
+    rs = np.random.RandomState(seed)
+    p: Dict[str, torch.Tensor] = {}
+
+    def conv(name, cin, cout, k, transposed=False, gain=1.0):
+        shape = (cin, cout, k, k) if transposed else (cout, cin, k, k)
+        std = math.sqrt(2.0 / (k * k * cout)) * gain
+        p[name + ".weight"] = torch.from_numpy(rs.standard_normal(size=shape).astype(np.float32) * np.float32(std))
+        p[name + ".bias"] = torch.from_numpy(rs.standard_normal(size=(cout,)).astype(np.float32) * np.float32(0.01))
+
+    for name, cin, cout, k, s in _DISPNETC_ENC:
+        conv(name + ".0", cin, cout, k)
+    conv("pr6", 1024, 1, 3, gain=0.1)
+    for lvl, cin, cout, icin in _DISPNETC_DEC:
+        conv("deconv%d.0" % lvl, cin, cout, 4, transposed=True)
+        conv("iconv%d.0" % lvl, icin, cout, 3)
+        conv("pr%d" % lvl, cout, 1, 3, gain=0.1)
+    return p
+
+
+def dispnetc_forward(p: Dict[str, torch.Tensor], imL: torch.Tensor, imR: torch.Tensor, mode: str = "train",
+                     maxdisparity: int = 192, align_corners: bool = True):
+    """dispnetcorr.forward (models/dispnetcorr.py:66-134): returns the 7-level pyramid [pr0 .. pr6]."""
+    strides = {n: s for n, _, _, _, s in _DISPNETC_ENC}
+    ks = {n: k for n, _, _, k, _ in _DISPNETC_ENC}
+
+    def cr(name, x):
+        return F.relu(F.conv2d(x, p[name + ".0.weight"], p[name + ".0.bias"], stride=strides[name], padding=(ks[name] - 1) // 2))
+
+    def up(x):
+        return F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=align_corners)
+
+    def cat(*ts):
+        h = min(t.shape[2] for t in ts); w = min(t.shape[3] for t in ts)
+        return torch.cat([t[:, :, :h, :w] for t in ts], dim=1)
+
+    c1L, c1R = cr("conv1", imL), cr("conv1", imR)
+    c2L, c2R = cr("conv2", c1L), cr("conv2", c1R)
+    x = torch.cat([corr1d(c2L, c2R, 41, 1, 1), cr("redir", c2L)], dim=1)
+    skips = {1: c1L, 2: c2L}
+    for lvl in (3, 4, 5, 6):
+        x = cr("conv%db" % lvl, cr("conv%da" % lvl, x)); skips[lvl] = x
+    out = [F.conv2d(x, p["pr6.weight"], p["pr6.bias"], padding=1)]
+    for lvl, _, _, _ in _DISPNETC_DEC:
+        d = F.relu(F.conv_transpose2d(x, p["deconv%d.0.weight" % lvl], p["deconv%d.0.bias" % lvl], stride=2, padding=1))
+        x = F.relu(F.conv2d(cat(d, up(out[0]), skips[lvl]), p["iconv%d.0.weight" % lvl], p["iconv%d.0.bias" % lvl], padding=1))
+        out.insert(0, F.conv2d(x, p["pr%d.weight" % lvl], p["pr%d.bias" % lvl], padding=1))
+    out.insert(0, up(out[0])[:, :, :imL.shape[-2], :imL.shape[-1]])
+    if mode == "test":
+        out[-1] = out[-1].clamp(1e-6, max(maxdisparity, imL.shape[-1]))
+    return out

@@ -126,6 +126,18 @@ def main():
         gdisp = gnet.layer3d(gvol, "test")                            # [1,1,32,48]
     save("gcnet_hotpath", fL=gfL, fR=gfR, maxdisp=maxdisp, seed=9, params_sha256=params_digest(gparams), disp=gdisp)
 
+    # ---- DispNetC (BASELINE config 1): the reference's dispnetcorr with its Corr1d layer, 7-level pyramid ------
+    dparams = O.dispnetc_random_params(seed=5)
+    dnet = mods["dispnetcorr"].dispnetcorr(192).eval()
+    dmissing = dnet.load_state_dict(dparams, strict=False)
+    assert not dmissing.unexpected_keys and not dmissing.missing_keys, dmissing
+    rs = np.random.RandomState(1)
+    dimL = torch.from_numpy(rs.standard_normal((1, 3, 128, 192)).astype(np.float32))
+    dimR = torch.from_numpy(rs.standard_normal((1, 3, 128, 192)).astype(np.float32))
+    with torch.no_grad(), R.pinned_torch():
+        _, douts = dnet(dimL, dimR, "test")
+    save("dispnetc_forward", imL=dimL, imR=dimR, seed=5, **{"out%d" % i: o for i, o in enumerate(douts)})
+
     # single reference layers (GC-Net style: bias + BN + ReLU; stride 2; transposed with BN3d swap)
     uc = mods["util_conv"]
     torch.manual_seed(77)

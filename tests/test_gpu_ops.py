@@ -51,6 +51,26 @@ def test_corr1d_vs_oracle(B, C, H, W, D, s):
     assert rel_err(a.grad, gL) < REL and rel_err(b.grad, gR) < REL
 
 
+def test_dispnetc_model_golden():
+    """BASELINE config 1 at model level: the drop-in dispnetcorr (Corr1d on the sm_100a kernel, stock 2-D convs) vs the
+    pyramid the reference's own dispnetcorr produced on CPU (fixture), same parameters through load_state_dict."""
+    from dsmnet_b200.dispnetcorr import dispnetcorr
+    g = load_golden("dispnetc_forward")
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False; torch.backends.cuda.matmul.allow_tf32 = False     # SURVEY A13: fp32 reference
+    try:
+        m = dispnetcorr(192)
+        missing = m.load_state_dict(O.dispnetc_random_params(seed=g["seed"]), strict=True)
+        m = m.cuda().eval()
+        with torch.no_grad():
+            scales, outs = m(dev(g["imL"]), dev(g["imR"]), "test")
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    assert scales == list(range(7)) and len(outs) == 7
+    for i, o in enumerate(outs):
+        assert o.shape == g["out%d" % i].shape and rel_err(o, g["out%d" % i]) < 1e-3
+
+
 def test_corr1d_linearity_full_size():
     """size-independent property at the BASELINE size: corr(a*fL, fR) = a*corr(fL, fR); corr(fL, fR1+fR2) additive."""
     from dsmnet_b200.corr1d import corr1d

@@ -76,6 +76,14 @@ def test_psmnet_hotpath():
         assert (mine - ref).abs().mean() < 1e-4
 
 
+def test_dispnetc_forward():
+    """BASELINE config 1: the reference's DispNetC (with its Corr1d layer) vs the oracle restatement, all 7 levels"""
+    g = load_golden("dispnetc_forward")
+    outs = O.dispnetc_forward(O.dispnetc_random_params(seed=g["seed"]), g["imL"], g["imR"], "test")
+    for i, o in enumerate(outs):
+        assert o.shape == g["out%d" % i].shape and rel_err(o, g["out%d" % i]) < 1e-5
+
+
 def test_gcnet_hotpath():
     """the reference's feature3d (19-layer 3-D enc-dec + soft-argmin of -cost) vs the oracle restatement"""
     g = load_golden("gcnet_hotpath")
