@@ -35,7 +35,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "stereo pairs/sec at 384x1248 (PSMNet D=192) hot path: cost volume + stacked-hourglass 3-D convs + soft-argmin"
 H_IMG, W_IMG, MAXDISP, C_FEAT = 384, 1248, 192, 32
-SAMPLE_ROWS = 96          # CPU sample: the top 96 image rows (1/4 of the pair)
+SAMPLE_ROWS = 384         # CPU sample: one whole pair (all 384 image rows; ~3-4 s per pass on 16 host cores)
 
 
 def measured_peaks():
@@ -47,32 +47,61 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every ~2 ms (a timed region of a few
+    tens of milliseconds still yields a median), nvidia-smi every 100 ms as the fallback."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    # NVML clocks-event-reason bits (nvml.h)
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.samples, self.stop_flag, self.active = index, [], False, False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].strip().isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
     def run(self):
         while not self.stop_flag:
+            if self.nvml is not None:
+                try:
+                    mhz = self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM)
+                    try:
+                        mask = self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                    except Exception:
+                        mask = self.nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                    if self.active:
+                        self.samples.append((mhz, self.max_mhz, mask))
+                except Exception:
+                    pass
+                time.sleep(0.002)
+                continue
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                if out and self.active:
+                    f = [x.strip() for x in out.split(",")]
+                    mask = sum(bit for name, bit in self.BITS.items()
+                               if f[2 + ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"].index(name)].lower().startswith("active"))
+                    self.samples.append((int(f[0]), int(f[1]), mask))
             except Exception:
                 pass
             time.sleep(0.1)
 
     def summary(self):
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        sm = sorted(s[0] for s in self.samples)
+        mx = [s[1] for s in self.samples]
+        reasons = sorted({n for s in self.samples for n, bit in self.BITS.items() if s[2] & bit})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+                "reasons": reasons, "samples": len(self.samples), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def synthetic_hotpath(device):
@@ -125,7 +154,7 @@ def run_reference(args, rank):
     frac = SAMPLE_ROWS / H_IMG
     ms = 1e3 * sum(times) / len(times)
     value = frac / (ms / 1e3)
-    sample = "hot path on the top %d of %d image rows of one pair (1/%d of the work) per step, fp32, torch CPU ops" % (SAMPLE_ROWS, H_IMG, int(1 / frac))
+    sample = "one full %dx%d pair per step through the oracle port of the hot path, fp32, torch CPU ops, %d threads" % (H_IMG, W_IMG, nthreads)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
@@ -198,32 +227,67 @@ def run_native(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank); sampler.start()
     barrier()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    sampler.active = True
     e0.record()
     for _ in range(args.steps):
         run()
     e1.record()
     barrier()
+    sampler.active = False
     t_ms = e0.elapsed_time(e1)
 
-    # ---- end to end through the public API with host buffers -------------------------------------
-    def e2e_step():
-        fL.copy_(host_L, non_blocking=True); fR.copy_(host_R, non_blocking=True)
-        preds = static_out if graph is not None else None
-        if graph is not None:
-            graph.replay()
-        else:
-            preds = step()
-        for dst, src in zip(host_out, preds):
-            dst.copy_(src, non_blocking=True)
-        torch.cuda.current_stream().synchronize()        # the caller reads the result
-    for _ in range(2):
-        e2e_step()
+    # ---- end to end through the public API with HOST buffers ---------------------------------------
+    # Every step copies that step's two feature maps from pinned host memory and reads its three disparity maps back
+    # into pinned host memory.  The copies are double-buffered on their own streams so that the H2D of step i+1 and the
+    # D2H of step i-1 overlap the compute of step i (throughput metric; the host waits for the results of step i-1
+    # before it enqueues step i+1, i.e. it does read every result).
+    s_in, s_cmp, s_out = torch.cuda.Stream(device), torch.cuda.Stream(device), torch.cuda.Stream(device)
+    stage_in = [(torch.empty_like(fL), torch.empty_like(fR)) for _ in range(2)]
+    stage_out = [[torch.empty(B, H_IMG, W_IMG, device=device) for _ in range(3)] for _ in range(2)]
+    host_outs = [[torch.empty(B, H_IMG, W_IMG).pin_memory() for _ in range(3)] for _ in range(2)]
+    ev_in = [torch.cuda.Event() for _ in range(2)]; ev_used = [torch.cuda.Event() for _ in range(2)]
+    ev_out = [torch.cuda.Event() for _ in range(2)]; ev_done = [torch.cuda.Event() for _ in range(2)]
+    torch.cuda.synchronize()
+
+    def e2e_enqueue(i):
+        k = i & 1
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(ev_used[k])                       # step i-2 has consumed this staging pair
+            stage_in[k][0].copy_(host_L, non_blocking=True); stage_in[k][1].copy_(host_R, non_blocking=True)
+            ev_in[k].record(s_in)
+        with torch.cuda.stream(s_cmp):
+            s_cmp.wait_event(ev_in[k])
+            fL.copy_(stage_in[k][0], non_blocking=True); fR.copy_(stage_in[k][1], non_blocking=True)
+            ev_used[k].record(s_cmp)
+            if graph is not None:
+                graph.replay(); preds = static_out
+            else:
+                preds = step()
+            s_cmp.wait_event(ev_done[k])                      # step i-2's results have left this staging triple
+            for dst, src in zip(stage_out[k], preds):
+                dst.copy_(src, non_blocking=True)
+            ev_out[k].record(s_cmp)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_out[k])
+            for dst, src in zip(host_outs[k], stage_out[k]):
+                dst.copy_(src, non_blocking=True)
+            ev_done[k].record(s_out)
+
+    def e2e_run(n):
+        for i in range(n):
+            e2e_enqueue(i)
+            if i >= 1:
+                ev_done[(i - 1) & 1].synchronize()            # the caller reads the result of step i-1
+        ev_done[(n - 1) & 1].synchronize()
+
+    e2e_run(4)
     barrier()
+    sampler.active = True
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_run(args.steps)
     barrier()
     t_e2e = time.perf_counter() - t0
+    sampler.active = False
     sampler.stop_flag = True; sampler.join(timeout=2)
 
     if dist is not None:
@@ -246,14 +310,15 @@ def run_native(args, rank, world, local_rank):
     achieved = flops / (ms_k * 1e-3) / 1e12
     roofline = {"bound": "tensor", "kernel": "conv3d_rs_kernel<KC=32,NP=32> (Conv3d 32->32 k3 s1 + BN + ReLU @48x96x312, 7 launches/step)",
                 "achieved": achieved, "peak": tf_burst, "unit": "TFLOP/s", "frac": achieved / tf_burst,
-                "peak_source": which + " bf16 burst (kernel timed alone)", "ms_per_launch": ms_k, "traffic": None}
+                "peak_source": which + " bf16 burst (kernel timed alone)", "ms_per_launch": ms_k,
+                "traffic": 141.0e6, "traffic_source": "dram read+write of this kernel per launch, ncu --set full (profiles/r01c_prof_conv3d_rs_bench_summary.txt); algorithmic 184 MB, part of the output is still in L2 at kernel end"}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        v, dt, nthreads = cpu_sample_pairs_per_s()
+        v, dt, nthreads = cpu_sample_pairs_per_s(reps=3)
         cpu = {"value": v, "unit": "pairs/s", "cores": nthreads, "kind": "port",
-               "sample": "oracle port of the hot path on the top %d of %d image rows of one pair (%.1f s of CPU work, 1 pass), scaled by %d" %
-                         (SAMPLE_ROWS, H_IMG, dt, H_IMG // SAMPLE_ROWS)}
+               "sample": "oracle port (fp32 torch CPU ops) of the whole hot path on one full %dx%d pair, best of 3 passes of %.1f s" %
+                         (H_IMG, W_IMG, dt)}
 
     pairs = B * world * args.steps
     def nbytes(v):
