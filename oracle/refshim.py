@@ -213,3 +213,43 @@ def state_dict_3d(net) -> Dict[str, torch.Tensor]:
     return {k: v.detach().clone() for k, v in net.state_dict().items()
             if k.split(".")[0] in ("dres0", "dres1", "dres2", "dres3", "dres4", "classif1", "classif2", "classif3")
             and not k.endswith("num_batches_tracked")}
+
+
+# ------------------------------------------------------------------------------------------------
+# losses/loss.py (self-supervised training config): Python-2 prints and PyTorch-0.3 idioms are
+# patched textually before exec — nothing else is changed.
+# ------------------------------------------------------------------------------------------------
+
+def load_losses():
+    """The reference's `losses.loss` module (class `losses`), executable under Python 3 / torch 2.x."""
+    import re
+    mods = _load()
+    if "ref_loss" in mods:
+        return mods["ref_loss"]
+    if "matplotlib" not in sys.modules:                       # utils/utils.py imports it at module level
+        mpl = types.ModuleType("matplotlib"); plt = types.ModuleType("matplotlib.pyplot")
+        mpl.pyplot = plt; mpl.use = lambda *a, **k: None
+        sys.modules["matplotlib"] = mpl; sys.modules["matplotlib.pyplot"] = plt
+    import SSIM as ref_ssim                                   # losses/SSIM.py, unmodified (REF/losses is on sys.path)
+    src = open(REF + "/losses/loss.py", encoding="utf-8").read()
+    src = re.sub(r"^(\s*)print [^\n]*$", r"\1pass", src, flags=re.M)                       # 8 Py2 print statements
+    src = src.replace(".data[0]", ".item()")                                                 # 0-dim tensor indexing
+    src = re.sub(r"\(\((.+?)\) \+ mask_ap\)\.detach\(\) > 1", r"((\1) & mask_ap).detach()", src)   # byte '+' used as AND
+    src = src.replace("mask2 = (disp_delt<3) - mask1", "mask2 = (disp_delt<3) & ~mask1")     # byte '-' used as AND-NOT
+    src = src.replace("from utils.utils import imsplot_tensor", "imsplot_tensor = None")
+    m = types.ModuleType("ref_loss")
+    m.__file__ = REF + "/losses/loss.py"
+    exec(compile(src, m.__file__, "exec"), m.__dict__)
+    mods["ref_loss"] = m
+    return m
+
+
+def selfsup_loss(loss_name, scale_disps, dispLs, dispL1s, imL, imR_src, imL1, imR1_src, LeftTop, weight_levels, seed=0):
+    """losses(loss_name)(...) exactly as stereo_selfsupervised.py:88-95 calls it; the global RNG is seeded so that the
+    `delt` draws of the imwrap calls (imwrap.py:70) are reproducible.  Returns the scalar loss tensor."""
+    m = load_losses()
+    L = m.losses(loss_name=loss_name, count_levels=len(weight_levels))
+    L.weight_levels = list(weight_levels)
+    torch.manual_seed(seed)
+    with pinned_torch():
+        return L.lossesfun(imR_src, imL, dispLs, scale_disps, list(LeftTop), imR1_src, imL1, dispL1s, scale_disps, list(LeftTop))

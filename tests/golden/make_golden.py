@@ -138,6 +138,24 @@ def main():
         _, douts = dnet(dimL, dimR, "test")
     save("dispnetc_forward", imL=dimL, imR=dimR, seed=5, **{"out%d" % i: o for i, o in enumerate(douts)})
 
+    # ---- self-supervised pyramid loss (losses/loss.py `depthmono-mask`, 28 imwrap calls) run by the reference itself ----
+    rs = np.random.RandomState(0)
+    sB, sh, sw, ne = 2, 64, 128, 16
+    u = lambda *shape: torch.from_numpy(rs.uniform(0, 1, size=shape).astype(np.float32))
+    sbatch = u(sB, 6, sh + 2 * ne, sw + 2 * ne)
+    sb1 = torch.flip(sbatch, dims=[3])
+    crop = lambda t: t[:, :, ne:-ne, ne:-ne]
+    sdisp = [u(sB, 1, sh >> l, sw >> l) * 6 / (2 ** l) for l in range(7)]
+    sdisp1 = [u(sB, 1, sh >> l, sw >> l) * 6 / (2 ** l) for l in range(7)]
+    wl = [1.0, 0.5, 0.3, 0.2, 0.1, 0.05, 0.01]
+    a = [x.clone().requires_grad_() for x in sdisp]; a1 = [x.clone().requires_grad_() for x in sdisp1]
+    sloss = R.selfsup_loss("depthmono-mask", list(range(7)), a, a1, crop(sbatch[:, :3]), sbatch[:, 3:6], crop(sb1[:, 3:6]), sb1[:, :3],
+                           (ne, ne), wl, seed=3)
+    sloss.backward()
+    save("selfsup_loss", batch=sbatch, nedge=ne, seed=3, weight_levels=np.asarray(wl, dtype=np.float32), loss=sloss.detach(),
+         **{"disp%d" % l: sdisp[l] for l in range(7)}, **{"disp1_%d" % l: sdisp1[l] for l in range(7)},
+         **{"g%d" % l: a[l].grad for l in range(7)}, **{"g1_%d" % l: a1[l].grad for l in range(7)})
+
     # single reference layers (GC-Net style: bias + BN + ReLU; stride 2; transposed with BN3d swap)
     uc = mods["util_conv"]
     torch.manual_seed(77)

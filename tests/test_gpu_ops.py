@@ -71,6 +71,27 @@ def test_dispnetc_model_golden():
         assert o.shape == g["out%d" % i].shape and rel_err(o, g["out%d" % i]) < 1e-3
 
 
+def test_selfsup_pyramid_loss_golden():
+    """the reference's own `depthmono-mask` pyramid loss (fixture: loss value and gradients of all 14 disparity maps) vs
+    dsmnet_b200.selfsup with the 28 warps on the sm_100a imwrap kernels (fwd + bwd)"""
+    import os
+    from conftest import GOLDEN
+    from dsmnet_b200.selfsup import losses_pyramid1
+    z = np.load(os.path.join(GOLDEN, "selfsup_loss.npz"))
+    g = {k: (torch.from_numpy(z[k]) if z[k].ndim else z[k].item()) for k in z.files}
+    ne = g["nedge"]; batch = dev(g["batch"]); b1 = torch.flip(batch, dims=[3])
+    crop = lambda t: t[:, :, ne:-ne, ne:-ne].contiguous()
+    d = [dev(g["disp%d" % l]).requires_grad_() for l in range(7)]
+    d1 = [dev(g["disp1_%d" % l]).requires_grad_() for l in range(7)]
+    torch.manual_seed(g["seed"])                                    # the warps draw delt from the global CPU RNG (imwrap.py:70)
+    loss = losses_pyramid1(batch[:, 3:6].contiguous(), crop(batch[:, :3]), d, list(range(7)), (ne, ne),
+                           b1[:, :3].contiguous(), crop(b1[:, 3:6]), d1, (ne, ne), g["weight_levels"].tolist(), True)
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
+    for l in range(7):
+        assert rel_err(d[l].grad, g["g%d" % l]) < 2e-3 and rel_err(d1[l].grad, g["g1_%d" % l]) < 2e-3
+
+
 def test_corr1d_linearity_full_size():
     """size-independent property at the BASELINE size: corr(a*fL, fR) = a*corr(fL, fR); corr(fL, fR1+fR2) additive."""
     from dsmnet_b200.corr1d import corr1d
