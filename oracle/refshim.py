@@ -74,6 +74,7 @@ def _load() -> Dict[str, types.ModuleType]:
     _loaded["stackhourglass"] = importlib.import_module("stackhourglass")
     _loaded["gcnet"] = importlib.import_module("gcnet")
     _loaded["dispnetcorr"] = importlib.import_module("dispnetcorr")
+    _loaded["iresnet"] = importlib.import_module("iresnet")          # imports `util.imwrap` (sic, iresnet.py:8): aliased above
     return _loaded
 
 

@@ -138,6 +138,22 @@ def main():
         _, douts = dnet(dimL, dimR, "test")
     save("dispnetc_forward", imL=dimL, imR=dimR, seed=5, **{"out%d" % i: o for i, o in enumerate(douts)})
 
+    # ---- iResNet (BASELINE config 4): the reference's iresnet (Corr1d D=81, imwrap feature constancy, Corr1d k3 s2) -------
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import random_state_dict
+    from dsmnet_b200.iresnet import iresnet as _ires_shape          # only to enumerate parameter names/shapes
+    isd = random_state_dict(_ires_shape(192), 11)
+    inet = mods["iresnet"].iresnet(192).eval()
+    imiss = inet.load_state_dict(isd, strict=True)
+    rs = np.random.RandomState(2)
+    iimL = torch.from_numpy(rs.standard_normal((1, 3, 128, 192)).astype(np.float32))
+    iimR = torch.from_numpy(rs.standard_normal((1, 3, 128, 192)).astype(np.float32))
+    with torch.no_grad(), R.pinned_torch():
+        torch.manual_seed(7)                                         # the warp draws delt from the global RNG (imwrap.py:70)
+        iscales, iouts = inet(iimL, iimR, "test")
+    save("iresnet_forward", imL=iimL, imR=iimR, seed=11, rng_seed=7, scales=np.asarray(iscales),
+         **{"out%d" % i: o for i, o in enumerate(iouts)})
+
     # ---- self-supervised pyramid loss (losses/loss.py `depthmono-mask`, 28 imwrap calls) run by the reference itself ----
     rs = np.random.RandomState(0)
     sB, sh, sw, ne = 2, 64, 128, 16

@@ -71,6 +71,28 @@ def test_dispnetc_model_golden():
         assert o.shape == g["out%d" % i].shape and rel_err(o, g["out%d" % i]) < 1e-3
 
 
+def test_iresnet_model_golden():
+    """BASELINE config 4 at model level: the drop-in iresnet (both Corr1d call sites and the imwrap feature warp on the
+    sm_100a kernels, stock 2-D convs) vs the 10 outputs of the reference's own iresnet (CPU fixture)."""
+    from dsmnet_b200.iresnet import iresnet
+    from helpers import random_state_dict
+    g = load_golden("iresnet_forward")
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False; torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        m = iresnet(192)
+        m.load_state_dict(random_state_dict(m, g["seed"]), strict=True)
+        m = m.cuda().eval()
+        with torch.no_grad():
+            torch.manual_seed(g["rng_seed"])
+            scales, outs = m(dev(g["imL"]), dev(g["imR"]), "test")
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    assert scales == [int(x) for x in g["scales"]] and len(outs) == 10
+    for i, o in enumerate(outs):
+        assert o.shape == g["out%d" % i].shape and rel_err(o, g["out%d" % i]) < 2e-3
+
+
 def test_selfsup_pyramid_loss_golden():
     """the reference's own `depthmono-mask` pyramid loss (fixture: loss value and gradients of all 14 disparity maps) vs
     dsmnet_b200.selfsup with the 28 warps on the sm_100a imwrap kernels (fwd + bwd)"""
