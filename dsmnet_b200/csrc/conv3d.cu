@@ -773,7 +773,7 @@ struct DcCfg {
     static constexpr int ACC_COLS = 8 * NP;
     static constexpr int TMEM_COLS = 2 * ACC_COLS;
     static constexpr int SMEM = W_BYTES + STAGES * A_BYTES + 1024 + BAR_BYTES + 2 * NP * 4;
-    static constexpr int THREADS = 320;                          // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+    static constexpr int THREADS = 576;                          // warp 0 TMA, warp 1 MMA, warps 2-17 epilogue
     static_assert(STAGES >= 4, "activation ring too shallow");
     static_assert(((NP * ROWB) % 1024) == 0, "weight blocks must keep the swizzle phase");
 };
@@ -787,7 +787,7 @@ __device__ __forceinline__ bool dc_skip(long long p0, long long P, long long pla
 }
 
 template <int KC, int NP>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(576, 1)
 conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                  const __grid_constant__ DcGeom g, const float* __restrict__ scale, const float* __restrict__ shift,
                  const void* __restrict__ residual, void* __restrict__ y) {
@@ -823,7 +823,7 @@ conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         ptx::prefetch_tensormap(&map_w);
         ptx::prefetch_tensormap(&map_a);
         for (int s = 0; s < C::STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; ++a) { ptx::mbar_init(tfull_bar(a), 1); ptx::mbar_init(tempty_bar(a), 8); }
+        for (int a = 0; a < 2; ++a) { ptx::mbar_init(tfull_bar(a), 1); ptx::mbar_init(tempty_bar(a), 16); }
         ptx::mbar_init(wfull_bar, 1);
         ptx::fence_mbar_init();
     }
@@ -900,9 +900,10 @@ conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
         }
     } else {
-        // ================= epilogue: 8 warps, two per TMEM lane quadrant, 4 classes each =================
+        // ================= epilogue: 16 warps, four per TMEM lane quadrant, 2 classes each =================
+        // (the MMAs of a tile take ~2.3k cycles: the epilogue is the longer leg, so it gets the threads)
         const int q = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int half = (warp - 2) >> 2;                       // 0..3: owns accumulator blocks 2*half, 2*half+1
         const int r = q * 32 + lane;
         constexpr int NV = NP / 8;
         const float4* sc4 = reinterpret_cast<const float4*>(s_scale);
@@ -926,10 +927,10 @@ conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const uint32_t acc_ph = (uint32_t)(tcount >> 1) & 1u;
             ++tcount;
             const uint32_t taddr0 = tmem + ((uint32_t)(q * 32) << 16) + acc * C::ACC_COLS;
-            bool valid[4]; size_t off[4];
+            bool valid[2]; size_t off[2];
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                const int c = kDcPosClass[2 * jj + half];
+            for (int jj = 0; jj < 2; ++jj) {
+                const int c = kDcPosClass[2 * half + jj];
                 const int od = dz + ((c >> 2) & 1), oh = hy + ((c >> 1) & 1), ow = wx + (c & 1);
                 valid[jj] = interior && od < g.Do && oh < g.Ho && ow < g.Wo;
                 off[jj] = g.y_f32 ? (((size_t)ob * g.Do + od) * g.Ho + oh) * g.Wo + ow
@@ -941,29 +942,29 @@ conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
             };
             if (g.y_f32) {
-                float rf[4];
+                float rf[2];
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj)
+                for (int jj = 0; jj < 2; ++jj)
                     rf[jj] = (residual && valid[jj]) ? __ldg(reinterpret_cast<const float*>(residual) + off[jj]) : 0.f;
                 wait_bar(tfull_bar(acc), acc_ph);
                 __syncwarp();
                 ptx::tc_fence_after();
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
+                for (int jj = 0; jj < 2; ++jj) {
                     uint32_t v[16];
-                    ptx::tmem_ld16(taddr0 + (2 * jj + half) * NP, v);
+                    ptx::tmem_ld16(taddr0 + (2 * half + jj) * NP, v);
                     ptx::tc_wait_ld();
                     consume_tmem_load(v[0], scratch_smem);
-                    if (jj == 3) release();
+                    if (jj == 1) release();
                     if (valid[jj]) {
                         reinterpret_cast<float*>(y)[off[jj]] = fuse_act(fmaf(__uint_as_float(v[0]), s_scale[0], s_shift[0]), rf[jj], g.relu);
                     }
                 }
             } else {
                 const __nv_bfloat16* resb = reinterpret_cast<const __nv_bfloat16*>(residual);
-                uint4 rv[4][NV];
+                uint4 rv[2][NV];
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
+                for (int jj = 0; jj < 2; ++jj) {
                     const bool ld = residual && valid[jj];
 #pragma unroll
                     for (int c = 0; c < NV; c += 2) {
@@ -975,12 +976,12 @@ conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 __syncwarp();
                 ptx::tc_fence_after();
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
+                for (int jj = 0; jj < 2; ++jj) {
                     uint32_t v[NP];
-                    if (NP == 32) ptx::tmem_ld32(taddr0 + (2 * jj + half) * NP, v); else ptx::tmem_ld16(taddr0 + (2 * jj + half) * NP, v);
+                    if (NP == 32) ptx::tmem_ld32(taddr0 + (2 * half + jj) * NP, v); else ptx::tmem_ld16(taddr0 + (2 * half + jj) * NP, v);
                     ptx::tc_wait_ld();
                     consume_tmem_load(v[0], scratch_smem);
-                    if (jj == 3) release();
+                    if (jj == 1) release();
                     if (valid[jj]) {
                         uint4* out = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y) + off[jj]);
                         uint4 ovp = make_uint4(0u, 0u, 0u, 0u);
