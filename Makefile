@@ -7,7 +7,7 @@ HDRS      := $(wildcard dsmnet_b200/csrc/*.cuh) include/dsmnet_b200.h
 OBJ       := $(patsubst dsmnet_b200/csrc/%.cu,build/%.o,$(CSRC))
 LIB       := dsmnet_b200/libdsmnet_b200.so
 
-all: $(LIB) tests/cuda/conv3d_selftest tests/cuda/mma_bench
+all: $(LIB) tests/cuda/conv3d_selftest tests/cuda/mma_bench tests/cuda/mnmajor_test
 
 build/%.o: dsmnet_b200/csrc/%.cu $(HDRS)
 	@mkdir -p build
@@ -22,7 +22,10 @@ tests/cuda/conv3d_selftest: tests/cuda/conv3d_selftest.cu $(LIB)
 tests/cuda/mma_bench: tests/cuda/mma_bench.cu dsmnet_b200/csrc/ptx.cuh
 	$(NVCC) $(ARCH) -lineinfo -O2 -std=c++17 -o $@ $<
 
+tests/cuda/mnmajor_test: tests/cuda/mnmajor_test.cu dsmnet_b200/csrc/ptx.cuh dsmnet_b200/csrc/tma_host.cuh
+	$(NVCC) $(ARCH) -lineinfo -O2 -std=c++17 -o $@ $<
+
 clean:
-	rm -rf build $(LIB) tests/cuda/conv3d_selftest tests/cuda/mma_bench
+	rm -rf build $(LIB) tests/cuda/conv3d_selftest tests/cuda/mma_bench tests/cuda/mnmajor_test
 
 .PHONY: all clean

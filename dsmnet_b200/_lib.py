@@ -38,6 +38,13 @@ SIGNATURES = {
     "dsm_conv3d_fwd_ex": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "dsm_conv3d_wgrad_workspace_bytes": [_I, _I],
     "dsm_conv3d_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, c_size_t, _P],
+    "dsm_zero_rim": [_P, _I, _I, _I, _I, _I, _P],
+    "dsm_bn_stats": [_P, _I, _I, _I, _I, _I, _P, _P],
+    "dsm_bn_finalize_fwd": [_P, _P, _P, _P, _I, ctypes.c_longlong, _F, _F, _P, _P, _P, _P, _P, _P, _P],
+    "dsm_bn_act_fwd": [_P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P],
+    "dsm_bn_act_bwd_reduce": [_P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P],
+    "dsm_bn_finalize_bwd": [_P, _P, _P, _P, _I, ctypes.c_longlong, _P, _P, _P, _P],
+    "dsm_bn_act_bwd": [_P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P],
     "dsm_debug_conv_timeouts": [],
     "dsm_pack_ndhwc": [_P, _P, _I, _I, _I, _I, _I, _P],
     "dsm_unpack_ndhwc": [_P, _P, _I, _I, _I, _I, _I, _P],
@@ -46,6 +53,8 @@ SIGNATURES = {
     "dsm_disparity_regression_fwd": [_P, _P, _I, _I, _I, _I, _P],
     "dsm_disparity_regression_bwd": [_P, _P, _I, _I, _I, _I, _P],
     "dsm_upsample_softargmin_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "dsm_upsample_softargmin_fwd_lse": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "dsm_upsample_softargmin_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "dsm_warp_fwd": [_P, _P, _P, _P, _F, _I, _P, _I, _I, _I, _I, _I, _I, _P],
     "dsm_warp_indices": [_P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P],
     "dsm_debug_conv_set_progress": [_P],

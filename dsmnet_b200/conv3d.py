@@ -181,7 +181,7 @@ class Conv3dFunction(torch.autograd.Function):
         cout = weight.shape[1] if transposed else weight.shape[0]
         x = PaddedVolume(xdata, B, cin, D, H, W)
         layer = FusedConv3d(weight, None, None, stride, transposed, 0, xdata.device)
-        y = layer(x, PaddedVolume.empty(B, cout, *odims, xdata.device))
+        y = layer(x, PaddedVolume.empty_zero_rim(B, cout, *odims, xdata.device))
         ctx.save_for_backward(xdata, weight)
         ctx.geom = geom
         return y.data
@@ -197,7 +197,7 @@ class Conv3dFunction(torch.autograd.Function):
         x = PaddedVolume(xdata, B, cin, D, H, W)
         gx = gw = None
         if ctx.needs_input_grad[0]:
-            gx = _dgrad_layer(weight, stride, transposed, dev)(g, PaddedVolume.empty(B, cin, D, H, W, dev)).data
+            gx = _dgrad_layer(weight, stride, transposed, dev)(g, PaddedVolume.empty_zero_rim(B, cin, D, H, W, dev)).data
         if ctx.needs_input_grad[1]:
             if transposed:
                 gw = conv3d_wgrad(x, g, 2, cin, cout)          # anchor = x (coarse), partner = gy

@@ -213,7 +213,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 //     ex2 + two accumulations per plane.  The loops are real loops (compact code: the first, fully
 //     unrolled version of this kernel spent a third of its time on instruction-cache misses).
 __global__ void __launch_bounds__(128)
-upsample_softargmin_kernel(const float* __restrict__ cost, float* __restrict__ disp,
+upsample_softargmin_kernel(const float* __restrict__ cost, float* __restrict__ disp, float* __restrict__ lse2,
                            int Dl, int Hl, int Wl, int D, int H, int W,
                            float sd, float sh, float sw, int align_corners, int rw) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -293,6 +293,118 @@ upsample_softargmin_kernel(const float* __restrict__ cost, float* __restrict__ d
     float* o = disp + ((size_t)b * H + y) * W;
     o[xa] = ta / sa;
     if (xa + (int)blockDim.x < W) o[xa + blockDim.x] = tb / sb;
+    if (lse2) {                                              // log2 of the softmax denominator, for the backward pass
+        float* q = lse2 + ((size_t)b * H + y) * W;
+        q[xa] = mla + log2f(sa);
+        if (xa + (int)blockDim.x < W) q[xa + blockDim.x] = mlb + log2f(sb);
+    }
+}
+
+// Backward of the fused head: gcost_lr += J^T gdisp.  Same CTA shape and shared tables as the forward kernel; the
+// upsampled volume is never materialised.  Per pixel and output plane d:
+//     g_d = gdisp * p_d * (d - disp),  p_d = 2^(c_d*log2e - lse2)          (one ex2 per point)
+// g_d is split onto its two source planes with the D-axis weights while the thread walks the planes, the per-plane
+// totals are split onto the two source columns with shared-memory atomics (s_g[dl][j], the gradient of the blended
+// row), and once per CTA s_g is split onto the two source rows with global atomics.
+__global__ void __launch_bounds__(128)
+upsample_softargmin_bwd_kernel(const float* __restrict__ cost, const float* __restrict__ disp, const float* __restrict__ lse2,
+                               const float* __restrict__ gdisp, float* __restrict__ gcost,
+                               int Dl, int Hl, int Wl, int D, int H, int W,
+                               float sd, float sh, float sw, int align_corners, int rw) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* s_l1 = reinterpret_cast<float*>(smem_raw);        // [D]
+    int* s_cnt = reinterpret_cast<int*>(s_l1 + D);           // [Dl]
+    float* s_row = reinterpret_cast<float*>(s_cnt + Dl);     // [Dl + 1][rw]
+    float* s_g = s_row + (size_t)(Dl + 1) * rw;              // [Dl][rw]
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    for (int i = tid; i < Dl; i += blockDim.x) s_cnt[i] = 0;
+    for (int i = tid; i < Dl * rw; i += blockDim.x) s_g[i] = 0.f;
+    __syncthreads();
+    for (int d = tid; d < D; d += blockDim.x) {
+        int d0, d1; float l1;
+        src_index(d, sd, Dl, align_corners, d0, d1, l1);
+        s_l1[d] = (d1 == d0) ? 0.f : l1;
+        atomicAdd(&s_cnt[d0], 1);
+    }
+    const int x0 = blockIdx.x * (2 * blockDim.x);
+    const int y = blockIdx.y, b = blockIdx.z;
+    int h0, h1, wb, wb1; float lh1, lwb;
+    src_index(y, sh, Hl, align_corners, h0, h1, lh1);
+    src_index(x0, sw, Wl, align_corners, wb, wb1, lwb);
+    const float lh0 = 1.f - lh1;
+    const float* base = cost + (size_t)b * Dl * Hl * Wl;
+    const size_t pl = (size_t)Hl * Wl;
+    for (int j = lane; j < rw; j += 32) {
+        const int wl = min(wb + j, Wl - 1);
+        const float* p0 = base + (size_t)h0 * Wl + wl;
+        const float* p1 = base + (size_t)h1 * Wl + wl;
+        for (int dl = wrp; dl < Dl; dl += 16) {
+            float a[4], c[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int dd = min(dl + 4 * u, Dl - 1);
+                a[u] = __ldg(p0 + (size_t)dd * pl); c[u] = __ldg(p1 + (size_t)dd * pl);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (dl + 4 * u < Dl) s_row[(dl + 4 * u) * rw + j] = lh0 * a[u] + lh1 * c[u];
+        }
+        if (wrp == 0) s_row[Dl * rw + j] = 0.f;
+    }
+    __syncthreads();
+    const int xa = x0 + tid;
+    if (xa < W) {
+        const bool has_b = xa + (int)blockDim.x < W;
+        const int xb = has_b ? xa + (int)blockDim.x : xa;
+        int wa0, wa1, wb0, wb1i; float lwa1, lwb1;
+        src_index(xa, sw, Wl, align_corners, wa0, wa1, lwa1);
+        src_index(xb, sw, Wl, align_corners, wb0, wb1i, lwb1);
+        wa0 -= wb; wa1 -= wb; wb0 -= wb; wb1i -= wb;
+        const float lwa0 = 1.f - lwa1, lwb0 = 1.f - lwb1;
+        const size_t po = ((size_t)b * H + y) * W;
+        constexpr float LOG2E = 1.4426950408889634f;
+        const float la = lse2[po + xa], lb = lse2[po + xb];
+        const float dpa = disp[po + xa], dpb = disp[po + xb];
+        const float ga = gdisp[po + xa], gb = has_b ? gdisp[po + xb] : 0.f;
+        float a0 = fmaf(lwa0 * s_row[wa0] + lwa1 * s_row[wa1], LOG2E, -la);
+        float b0 = fmaf(lwb0 * s_row[wb0] + lwb1 * s_row[wb1i], LOG2E, -lb);
+        float carry_a = 0.f, carry_b = 0.f, fd = 0.f;
+        int d = 0;
+        for (int dl = 0; dl < Dl; ++dl) {
+            const int o = (dl + 1) * rw;
+            const float a1 = fmaf(lwa0 * s_row[o + wa0] + lwa1 * s_row[o + wa1], LOG2E, -la);
+            const float b1 = fmaf(lwb0 * s_row[o + wb0] + lwb1 * s_row[o + wb1i], LOG2E, -lb);
+            const float da = a1 - a0, db = b1 - b0;
+            const int n = s_cnt[dl];
+            float lo_a = carry_a, hi_a = 0.f, lo_b = carry_b, hi_b = 0.f;
+            for (int k = 0; k < n; ++k, ++d) {
+                const float l = s_l1[d];
+                const float va = ex2_approx(fmaf(l, da, a0)) * (fd - dpa);
+                const float vb = ex2_approx(fmaf(l, db, b0)) * (fd - dpb);
+                hi_a = fmaf(l, va, hi_a); lo_a += va;           // lo accumulates the full term, corrected below
+                hi_b = fmaf(l, vb, hi_b); lo_b += vb;
+                fd += 1.f;
+            }
+            lo_a -= hi_a; lo_b -= hi_b;                            // (1-l)*v = v - l*v
+            const float ta = ga * lo_a, tb = gb * lo_b;
+            const int r = dl * rw;
+            atomicAdd(&s_g[r + wa0], lwa0 * ta); atomicAdd(&s_g[r + wa1], lwa1 * ta);
+            atomicAdd(&s_g[r + wb0], lwb0 * tb); atomicAdd(&s_g[r + wb1i], lwb1 * tb);
+            carry_a = hi_a; carry_b = hi_b;
+            a0 = a1; b0 = b1;
+        }
+    }
+    __syncthreads();
+    float* gbase = gcost + (size_t)b * Dl * Hl * Wl;
+    for (int i = tid; i < Dl * rw; i += blockDim.x) {
+        const int dl = i / rw, j = i - dl * rw;
+        if (wb + j >= Wl) continue;
+        const float v = s_g[i];
+        if (v == 0.f) continue;
+        float* q = gbase + (size_t)dl * pl + wb + j;
+        atomicAdd(q + (size_t)h0 * Wl, lh0 * v);
+        atomicAdd(q + (size_t)h1 * Wl, lh1 * v);
+    }
 }
 
 }  // namespace
@@ -339,8 +451,8 @@ extern "C" int dsm_disparity_regression_bwd(const float* gdisp, float* gprob, in
     return dsm_launch_status();
 }
 
-extern "C" int dsm_upsample_softargmin_fwd(const float* cost_lr, float* disp, int B, int Dl, int Hl, int Wl,
-                                           int D, int H, int W, int align_corners, void* stream) {
+static int upsample_softargmin_fwd_impl(const float* cost_lr, float* disp, float* lse2, int B, int Dl, int Hl, int Wl,
+                                        int D, int H, int W, int align_corners, void* stream) {
     if (!cost_lr || !disp || B <= 0 || Dl <= 0 || Hl <= 0 || Wl <= 0 || D <= 0 || H <= 0 || W <= 0) return DSM_EINVAL;
     if (H > 65535 || B > 65535) return DSM_EUNSUPPORTED;
     // ATen: align_corners -> (in-1)/(out-1) (0 when out==1); otherwise in/out; all in fp32
@@ -354,6 +466,40 @@ extern "C" int dsm_upsample_softargmin_fwd(const float* cost_lr, float* disp, in
     if (smem > 48 * 1024) return DSM_EUNSUPPORTED;
     const dim3 grid(dsm_ceil_div(W, 256), H, B);
     upsample_softargmin_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(
-        cost_lr, disp, Dl, Hl, Wl, D, H, W, scale(Dl, D), scale(Hl, H), sw, align_corners, rw);
+        cost_lr, disp, lse2, Dl, Hl, Wl, D, H, W, scale(Dl, D), scale(Hl, H), sw, align_corners, rw);
+    return dsm_launch_status();
+}
+
+extern "C" int dsm_upsample_softargmin_fwd(const float* cost_lr, float* disp, int B, int Dl, int Hl, int Wl,
+                                           int D, int H, int W, int align_corners, void* stream) {
+    return upsample_softargmin_fwd_impl(cost_lr, disp, nullptr, B, Dl, Hl, Wl, D, H, W, align_corners, stream);
+}
+
+extern "C" int dsm_upsample_softargmin_fwd_lse(const float* cost_lr, float* disp, float* lse2, int B, int Dl, int Hl, int Wl,
+                                               int D, int H, int W, int align_corners, void* stream) {
+    if (!lse2) return DSM_EINVAL;
+    return upsample_softargmin_fwd_impl(cost_lr, disp, lse2, B, Dl, Hl, Wl, D, H, W, align_corners, stream);
+}
+
+extern "C" int dsm_upsample_softargmin_bwd(const float* cost_lr, const float* disp, const float* lse2, const float* gdisp,
+                                           float* gcost_lr, int B, int Dl, int Hl, int Wl,
+                                           int D, int H, int W, int align_corners, void* stream) {
+    if (!cost_lr || !disp || !lse2 || !gdisp || !gcost_lr || B <= 0 || Dl <= 0 || Hl <= 0 || Wl <= 0 || D <= 0 || H <= 0 || W <= 0)
+        return DSM_EINVAL;
+    if (H > 65535 || B > 65535) return DSM_EUNSUPPORTED;
+    auto scale = [&](int in, int out) -> float {
+        if (align_corners) return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
+        return (float)in / (float)out;
+    };
+    const float sw = scale(Wl, W);
+    const int rw = (int)(sw * 255.f) + 3;
+    const size_t smem = (size_t)D * sizeof(float) + (size_t)Dl * sizeof(int) + (size_t)(2 * Dl + 1) * rw * sizeof(float);
+    if (smem > 48 * 1024) return DSM_EUNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t ce = cudaMemsetAsync(gcost_lr, 0, sizeof(float) * (size_t)B * Dl * Hl * Wl, st);
+    if (ce != cudaSuccess) return (int)ce;
+    const dim3 grid(dsm_ceil_div(W, 256), H, B);
+    upsample_softargmin_bwd_kernel<<<grid, 128, smem, st>>>(
+        cost_lr, disp, lse2, gdisp, gcost_lr, Dl, Hl, Wl, D, H, W, scale(Dl, D), scale(Hl, H), sw, align_corners, rw);
     return dsm_launch_status();
 }

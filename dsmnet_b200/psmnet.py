@@ -217,11 +217,11 @@ class PSMNetHotPath(nn.Module):
     def forward(self, fL, fR, out_hw):
         c1, c2, c3 = self.aggregate(fL, fR)
         if c1.requires_grad:
-            # differentiable heads (stackhourglass.py:152-166): stock trilinear upsample + the soft-argmin op (fwd+bwd kernels)
-            from .softargmin import softargmin
-            size = [self.maxdisp, out_hw[0], out_hw[1]]
-            return [softargmin(F.interpolate(c.unsqueeze(1), size=size, mode="trilinear", align_corners=self.align_corners).squeeze(1), 1.0)
-                    for c in (c3, c2, c1)]
+            # differentiable heads (stackhourglass.py:152-166): the fused upsample + soft-argmin kernels, forward and
+            # backward, one launch each for the three stacked costs
+            B = c1.shape[0]
+            preds = upsample_softargmin(torch.cat((c3, c2, c1), 0), (self.maxdisp, out_hw[0], out_hw[1]), self.align_corners)
+            return [preds[:B], preds[B:2 * B], preds[2 * B:]]
         B, _, H, W = fL.shape
         ws = self._workspace(B, self.maxdisp // 4, H, W, fL.device)
         size = (self.maxdisp, out_hw[0], out_hw[1])

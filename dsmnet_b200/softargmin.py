@@ -65,11 +65,46 @@ def softargmin(cost, sign=1.0):
     return SoftArgminFunction.apply(cost, sign)
 
 
+class UpsampleSoftargminFunction(torch.autograd.Function):
+    """Differentiable fused head (stackhourglass.py:152-166): trilinear upsample -> softmax over D -> regression,
+    forward and backward without the upsampled [B, D, H, W] volume (dsm_upsample_softargmin_fwd_lse / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, cost_lr, size, align_corners):
+        _lib.require_cuda(cost_lr)
+        cost_lr = cost_lr.contiguous().float()
+        B, Dl, Hl, Wl = cost_lr.shape
+        D, H, W = (int(s) for s in size)
+        disp = torch.empty(B, H, W, device=cost_lr.device, dtype=torch.float32)
+        lse2 = torch.empty(B, H, W, device=cost_lr.device, dtype=torch.float32)
+        _lib.check(_lib.lib().dsm_upsample_softargmin_fwd_lse(cost_lr.data_ptr(), disp.data_ptr(), lse2.data_ptr(), B, Dl, Hl, Wl,
+                                                              D, H, W, 1 if align_corners else 0, _lib.stream_ptr(cost_lr.device)),
+                   "dsm_upsample_softargmin_fwd_lse")
+        ctx.save_for_backward(cost_lr, disp, lse2)
+        ctx.size, ctx.align_corners = (D, H, W), bool(align_corners)
+        return disp
+
+    @staticmethod
+    def backward(ctx, gdisp):
+        cost_lr, disp, lse2 = ctx.saved_tensors
+        B, Dl, Hl, Wl = cost_lr.shape
+        D, H, W = ctx.size
+        gdisp = gdisp.contiguous().float()
+        gcost = torch.empty_like(cost_lr)
+        _lib.check(_lib.lib().dsm_upsample_softargmin_bwd(cost_lr.data_ptr(), disp.data_ptr(), lse2.data_ptr(), gdisp.data_ptr(),
+                                                          gcost.data_ptr(), B, Dl, Hl, Wl, D, H, W, 1 if ctx.align_corners else 0,
+                                                          _lib.stream_ptr(cost_lr.device)), "dsm_upsample_softargmin_bwd")
+        return gcost, None, None
+
+
 def upsample_softargmin(cost_lr, size, align_corners=True, out=None):
-    """cost_lr [B,Dl,Hl,Wl] (or [B,1,Dl,Hl,Wl]) -> disparity [B,H,W] at ``size=(D,H,W)``; no autograd."""
+    """cost_lr [B,Dl,Hl,Wl] (or [B,1,Dl,Hl,Wl]) -> disparity [B,H,W] at ``size=(D,H,W)``.
+    Differentiable (fused backward kernel) when cost_lr requires grad; `out` is honoured on the no-grad route only."""
     _lib.require_cuda(cost_lr)
     if cost_lr.dim() == 5:
         cost_lr = cost_lr.squeeze(1)
+    if torch.is_grad_enabled() and cost_lr.requires_grad:
+        return UpsampleSoftargminFunction.apply(cost_lr, tuple(int(s) for s in size), bool(align_corners))
     cost_lr = cost_lr.contiguous().float()
     B, Dl, Hl, Wl = cost_lr.shape
     D, H, W = (int(s) for s in size)

@@ -1,12 +1,13 @@
 """Training-mode building blocks of the 3-D stacks (PSMNet hourglass, GC-Net enc-dec).
 
-What is custom CUDA here: every convolution, forward and backward (`conv3d.Conv3dFunction`: tcgen05
-forward / dgrad kernels, `dsm_conv3d_wgrad`), the concat volume (`cost_volume`, fwd+bwd) and the
-soft-argmin (`softargmin`, fwd+bwd).  BatchNorm with batch statistics, ReLU, the skip adds and the
-trilinear upsample of the training graph are stock PyTorch ops on views of the padded volumes — the
-reference's are stock modules too (submodule.py:16-19, stackhourglass.py:43-62,152-166).  The
-inference path (`psmnet.PSMNetHotPath.aggregate`) stays fully fused; this path exists so that the
-3-D stack can be trained / fine-tuned without leaving the sm_100a kernels for the convolutions.
+Custom CUDA here: every convolution, forward and backward (`conv3d.Conv3dFunction`: tcgen05 forward /
+dgrad kernels, `dsm_conv3d_wgrad`), BatchNorm3d with batch statistics + ReLU + skip add between them
+(`BnActFunction`: the dsm_bn_* streaming kernels on the padded bf16 volumes, forward and backward), the
+concat volume (`cost_volume`, fwd+bwd) and the soft-argmin heads (`softargmin`, fwd+bwd).  Layers the
+fused BatchNorm does not cover (eval-mode statistics under autograd, a skip tensor that needs cropping,
+no BatchNorm at all) take the stock-PyTorch route in `conv_bn_act`.  The inference path
+(`psmnet.PSMNetHotPath.aggregate`) stays fully fused into the convolution epilogues; this path exists so
+that the 3-D stack can be trained / fine-tuned on the sm_100a kernels.
 """
 from __future__ import annotations
 
@@ -38,6 +39,88 @@ def volume_from_ncdhw(x: torch.Tensor) -> PaddedVolume:
     return from_interior(x.permute(0, 2, 3, 4, 1))
 
 
+class BnActFunction(torch.autograd.Function):
+    """z = act(BatchNorm_batchstats(y) [+ residual]) on padded bf16 volumes (flat storage in, flat storage out).
+
+    forward : dsm_bn_stats -> dsm_bn_finalize_fwd (also the running-statistics update) -> dsm_bn_act_fwd
+    backward: dsm_bn_act_bwd_reduce -> dsm_bn_finalize_bwd -> dsm_bn_act_bwd
+    Saved for backward: y, z (bf16) and 4*C floats.  relu as in `conv_bn_act`."""
+
+    @staticmethod
+    def forward(ctx, ydata, gamma, beta, resdata, geom, relu, eps, momentum, running_mean, running_var, conv_bias):
+        B, C, D, H, W = geom
+        _lib.require_cuda(ydata, gamma, beta, resdata)
+        L, dev = _lib.lib(), ydata.device
+        st = _lib.stream_ptr(dev)
+        ydata = ydata.contiguous()
+        if resdata is not None:
+            resdata = resdata.contiguous()
+        sums = torch.empty(2 * C, device=dev, dtype=torch.float64)
+        stats = torch.empty(4, C, device=dev, dtype=torch.float32)          # scale, shift, mean, rstd
+        g32 = None if gamma is None else gamma.detach().float().contiguous()
+        b32 = None if beta is None else beta.detach().float().contiguous()
+        cb32 = None if conv_bias is None else conv_bias.detach().float().contiguous()
+        count = B * D * H * W
+        _lib.check(L.dsm_bn_stats(ydata.data_ptr(), B, C, D, H, W, sums.data_ptr(), st), "dsm_bn_stats")
+        _lib.check(L.dsm_bn_finalize_fwd(sums.data_ptr(), _lib.ptr(g32), _lib.ptr(b32), _lib.ptr(cb32), C, count,
+                                         float(eps), float(momentum), _lib.ptr(running_mean), _lib.ptr(running_var),
+                                         stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), stats[3].data_ptr(), st),
+                   "dsm_bn_finalize_fwd")
+        z = torch.empty_like(ydata)
+        _lib.check(L.dsm_bn_act_fwd(ydata.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), _lib.ptr(resdata), relu,
+                                    z.data_ptr(), B, C, D, H, W, st), "dsm_bn_act_fwd")
+        ctx.save_for_backward(ydata, z if relu == 1 else None, stats, g32)
+        ctx.geom, ctx.relu, ctx.has_res = geom, relu, resdata is not None
+        ctx.param_dtype = None if gamma is None else gamma.dtype
+        ctx.bias_like = None if conv_bias is None else (conv_bias.shape, conv_bias.dtype)
+        return z
+
+    @staticmethod
+    def backward(ctx, gz):
+        ydata, z, stats, g32 = ctx.saved_tensors
+        B, C, D, H, W = ctx.geom
+        relu = ctx.relu
+        L, dev = _lib.lib(), ydata.device
+        st = _lib.stream_ptr(dev)
+        gz = gz.contiguous()
+        sums = torch.empty(2 * C, device=dev, dtype=torch.float64)
+        out = torch.empty(5, C, device=dev, dtype=torch.float32)            # dgamma, dbeta, a, b, c
+        _lib.check(L.dsm_bn_act_bwd_reduce(gz.data_ptr(), ydata.data_ptr(), _lib.ptr(z), stats[0].data_ptr(), stats[1].data_ptr(),
+                                           relu, sums.data_ptr(), B, C, D, H, W, st), "dsm_bn_act_bwd_reduce")
+        _lib.check(L.dsm_bn_finalize_bwd(sums.data_ptr(), _lib.ptr(g32), stats[2].data_ptr(), stats[3].data_ptr(), C, B * D * H * W,
+                                         out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), st), "dsm_bn_finalize_bwd")
+        dy = torch.empty_like(ydata)
+        # the skip tensor's gradient: the masked gradient when the ReLU sits after the add, gz itself otherwise
+        need_gres = ctx.has_res and ctx.needs_input_grad[3]
+        gres = torch.empty_like(ydata) if (need_gres and relu == 1) else None
+        _lib.check(L.dsm_bn_act_bwd(gz.data_ptr(), ydata.data_ptr(), _lib.ptr(z), stats[0].data_ptr(), stats[1].data_ptr(),
+                                    out[2].data_ptr(), relu, dy.data_ptr(), _lib.ptr(gres), B, C, D, H, W, st), "dsm_bn_act_bwd")
+        if need_gres and relu != 1:
+            gres = gz
+        dgamma = out[0].to(ctx.param_dtype) if (g32 is not None and ctx.needs_input_grad[1]) else None
+        dbeta = out[1].to(ctx.param_dtype) if (ctx.param_dtype is not None and ctx.needs_input_grad[2]) else None
+        # a bias in front of batch-statistics BN has an identically zero gradient (sum of dy over a channel is 0)
+        gbias = torch.zeros(ctx.bias_like[0], device=dev, dtype=ctx.bias_like[1]) if (ctx.bias_like and ctx.needs_input_grad[10]) else None
+        return dy, dgamma, dbeta, gres, None, None, None, None, None, None, gbias
+
+
+def bn_act(y: PaddedVolume, bn: nn.BatchNorm3d, relu: int = 0, residual: Optional[PaddedVolume] = None,
+           conv_bias: Optional[torch.Tensor] = None) -> PaddedVolume:
+    """Training-mode BatchNorm3d (batch statistics, running statistics updated as nn.BatchNorm3d does) + act + skip."""
+    if residual is not None and (residual.B, residual.C, residual.D, residual.H, residual.W) != (y.B, y.C, y.D, y.H, y.W):
+        raise _lib.DsmError("bn_act: the skip tensor must have the geometry of y")
+    momentum = bn.momentum
+    if bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+        if momentum is None:
+            momentum = 1.0 / float(bn.num_batches_tracked)
+    track = bn.track_running_stats
+    z = BnActFunction.apply(y.data, bn.weight, bn.bias, None if residual is None else residual.data,
+                            (y.B, y.C, y.D, y.H, y.W), int(relu), bn.eps, momentum if momentum is not None else 0.1,
+                            bn.running_mean if track else None, bn.running_var if track else None, conv_bias)
+    return PaddedVolume(z, y.B, y.C, y.D, y.H, y.W)
+
+
 def conv_bn_act(x: PaddedVolume, conv: nn.Module, bn: Optional[nn.BatchNorm3d], relu: int = 0,
                 residual: Optional[PaddedVolume] = None) -> PaddedVolume:
     """conv (+bias) -> BatchNorm3d (batch statistics when bn.training) -> [ReLU] -> [+ residual, crop-to-min] -> [ReLU].
@@ -47,6 +130,9 @@ def conv_bn_act(x: PaddedVolume, conv: nn.Module, bn: Optional[nn.BatchNorm3d], 
     nat = conv_out_dims(x.D, x.H, x.W, stride, transposed)
     od = nat if residual is None else (min(nat[0], residual.D), min(nat[1], residual.H), min(nat[2], residual.W))
     y = conv3d_train(x, conv.weight, stride, transposed, od)
+    if (bn is not None and bn.training and y.C in (32, 64, 128)
+            and (residual is None or (residual.D, residual.H, residual.W) == od)):
+        return bn_act(y, bn, relu, residual, conv.bias)
     z = interior(y).float()
     if conv.bias is not None:
         z = z + conv.bias

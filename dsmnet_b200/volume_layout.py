@@ -30,6 +30,13 @@ class PaddedVolume:
         return PaddedVolume(data, B, C, D, H, W)
 
     @staticmethod
+    def empty_zero_rim(B, C, D, H, W, device):
+        """Uninitialised interior, zero rim (dsm_zero_rim): for outputs a convolution kernel fills completely."""
+        v = PaddedVolume.empty(B, C, D, H, W, device, zero_rim=False)
+        _lib.check(_lib.lib().dsm_zero_rim(v.data.data_ptr(), B, C, D, H, W, _lib.stream_ptr(v.data.device)), "dsm_zero_rim")
+        return v
+
+    @staticmethod
     def from_ncdhw(x):
         """NCDHW fp32 (the reference's layout) -> padded NDHWC bf16 (RNE)."""
         _lib.require_cuda(x)

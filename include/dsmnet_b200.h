@@ -113,6 +113,35 @@ int dsm_conv3d_wgrad(const void* anchor, const void* partner, float* dw,
                      int Ca_out, int Cb_out, const float* scale_a, const float* scale_b, int accumulate,
                      void* ws, size_t ws_bytes, void* stream);
 
+/* ---- training-mode BatchNorm3d + ReLU + skip add between the 3-D convolutions -----------------
+ * Replaces nn.BatchNorm3d under model.train() with F.relu and the skip adds around it:
+ * models/psmnet/submodule.py:16-19, models/psmnet/stackhourglass.py:43-62,135-149,
+ * models/util_conv.py:160-178 with models/gcnet.py:65-101.
+ * All volumes are padded NDHWC bf16 [B][D+2][H+2][W+2][C] with a zero rim, C in {32, 64, 128}.
+ * relu: 0 none, 1 after the skip add (mask z > 0), 2 before it (mask y*scale+shift > 0).
+ *   dsm_bn_stats        : sums[0..C) = sum y, sums[C..2C) = sum y*y        (double, zeroed by the call)
+ *   dsm_bn_finalize_fwd : scale = gamma*rstd, shift = beta - mean*scale, mean, rstd (biased variance, eps);
+ *                         running_mean/var (nullable) get torch's momentum update, conv_bias (nullable) is the
+ *                         bias of the convolution in front (it only moves the running mean)
+ *   dsm_bn_act_fwd      : z = act(y*scale + shift [+ residual])
+ *   dsm_bn_act_bwd_reduce: g = gz*mask; sums = (sum g, sum g*y)
+ *   dsm_bn_finalize_bwd : dgamma, dbeta and coef[3][C] (a, b, c) of dy = a*g + b*y + c
+ *   dsm_bn_act_bwd      : dy (zero rim) and, if gres != NULL, gres = g (the gradient of the skip tensor)     */
+/* zero rim of a padded bf16 volume (C % 8 == 0) whose interior a convolution is about to write          */
+int dsm_zero_rim(void* data, int B, int C, int D, int H, int W, void* stream);
+int dsm_bn_stats(const void* y, int B, int C, int D, int H, int W, double* sums, void* stream);
+int dsm_bn_finalize_fwd(const double* sums, const float* gamma, const float* beta, const float* conv_bias,
+                        int C, long long count, float eps, float momentum, float* running_mean, float* running_var,
+                        float* scale, float* shift, float* mean, float* rstd, void* stream);
+int dsm_bn_act_fwd(const void* y, const float* scale, const float* shift, const void* residual, int relu,
+                   void* z, int B, int C, int D, int H, int W, void* stream);
+int dsm_bn_act_bwd_reduce(const void* gz, const void* y, const void* z, const float* scale, const float* shift,
+                          int relu, double* sums, int B, int C, int D, int H, int W, void* stream);
+int dsm_bn_finalize_bwd(const double* sums, const float* gamma, const float* mean, const float* rstd,
+                        int C, long long count, float* dgamma, float* dbeta, float* coef, void* stream);
+int dsm_bn_act_bwd(const void* gz, const void* y, const void* z, const float* scale, const float* shift,
+                   const float* coef, int relu, void* dy, void* gres, int B, int C, int D, int H, int W, void* stream);
+
 /* layout converters at the reference boundary (NCDHW fp32 <-> padded NDHWC bf16)             */
 int dsm_pack_ndhwc(const float* x_ncdhw, void* y_padded_bf16, int B, int C, int D, int H, int W, void* stream);
 int dsm_unpack_ndhwc(const void* x_padded_bf16, float* y_ncdhw, int B, int C, int D, int H, int W, void* stream);
@@ -131,6 +160,14 @@ int dsm_disparity_regression_bwd(const float* gdisp, float* gprob, int B, int D,
  * (D,H,W), softmax over D, regression.  align_corners=1 is the PyTorch<=0.3 behaviour the
  * reference was written for, 0 the modern default.                                           */
 int dsm_upsample_softargmin_fwd(const float* cost_lr, float* disp, int B, int Dl, int Hl, int Wl,
+                                int D, int H, int W, int align_corners, void* stream);
+/* training form: also writes lse2[B][H][W] = log2 of the softmax denominator (max included), which
+ * dsm_upsample_softargmin_bwd needs; the backward accumulates gcost_lr = J^T gdisp (zeroed by the call,
+ * float atomics) without materialising the upsampled volume.                                   */
+int dsm_upsample_softargmin_fwd_lse(const float* cost_lr, float* disp, float* lse2, int B, int Dl, int Hl, int Wl,
+                                    int D, int H, int W, int align_corners, void* stream);
+int dsm_upsample_softargmin_bwd(const float* cost_lr, const float* disp, const float* lse2, const float* gdisp,
+                                float* gcost_lr, int B, int Dl, int Hl, int Wl,
                                 int D, int H, int W, int align_corners, void* stream);
 
 /* ---- op 5: imwrap bilinear warp. Replaces imwrap_BCHW, utils/imwrap.py:59-71 -------------

@@ -212,6 +212,47 @@ def test_upsample_softargmin_vs_oracle(lr, size, ac):
         assert rel_err(out, O.upsample_softargmin(cost, size, ac)) < REL
 
 
+@pytest.mark.parametrize("ac", [True, False])
+@pytest.mark.parametrize("lr,size", [((1, 12, 24, 78), (48, 96, 312)), ((2, 5, 7, 9), (17, 26, 35)), ((2, 6, 9, 70), (24, 36, 280))])
+def test_upsample_softargmin_backward_vs_oracle(lr, size, ac):
+    """fused head backward (dsm_upsample_softargmin_bwd) against autograd through the oracle's
+    F.interpolate(trilinear) -> softmax -> regression (stackhourglass.py:152-166), fp64 on the CPU"""
+    from dsmnet_b200.softargmin import upsample_softargmin
+    torch.manual_seed(11)
+    cost = torch.randn(*lr) * 2
+    g = torch.randn(lr[0], size[1], size[2])
+    c64 = cost.double().requires_grad_(True)
+    ref = O.upsample_softargmin(c64, size, ac)
+    ref.backward(g.double())
+    x = dev(cost).requires_grad_(True)
+    out = upsample_softargmin(x, size, ac)
+    assert out.grad_fn is not None
+    assert rel_err(out, ref.float()) < REL
+    out.backward(dev(g))
+    assert rel_err(x.grad, c64.grad.float()) < REL
+
+
+def test_upsample_softargmin_backward_full_size_properties():
+    """BASELINE size (48x96x312 -> 192x384x1248): the gradient of sum(disp) w.r.t. a constant shift of the cost is 0
+    (softmax invariance), and a directional derivative matches a finite difference of the forward kernel"""
+    from dsmnet_b200.softargmin import upsample_softargmin
+    torch.manual_seed(12)
+    cost = (torch.randn(1, 48, 96, 312) * 2).cuda()
+    x = cost.clone().requires_grad_(True)
+    w = torch.randn(1, 384, 1248, device="cuda")
+    (upsample_softargmin(x, (192, 384, 1248), True) * w).sum().backward()
+    gsum = x.grad.sum().item()
+    assert abs(gsum) < 1e-3 * x.grad.abs().sum().item()
+    v = torch.randn_like(cost)
+    eps = 1e-2
+    with torch.no_grad():
+        fp = (upsample_softargmin(cost + eps * v, (192, 384, 1248), True).double() * w).sum()
+        fm = (upsample_softargmin(cost - eps * v, (192, 384, 1248), True).double() * w).sum()
+    fd = ((fp - fm) / (2 * eps)).item()
+    an = (x.grad.double() * v).sum().item()
+    assert abs(fd - an) < 2e-3 * max(abs(fd), abs(an), 1.0), (fd, an)
+
+
 def test_softargmin_properties_full_size():
     """at the BASELINE head size (192 x 384 x 1248): shift invariance and one-hot limit."""
     from dsmnet_b200.softargmin import softargmin
