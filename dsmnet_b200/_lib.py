@@ -46,6 +46,8 @@ SIGNATURES = {
     "dsm_bn_finalize_bwd": [_P, _P, _P, _P, _I, ctypes.c_longlong, _P, _P, _P, _P],
     "dsm_bn_act_bwd": [_P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P],
     "dsm_debug_conv_timeouts": [],
+    "dsm_debug_wgrad_mode": [_I],
+    "dsm_debug_wgrad_timeouts": [],
     "dsm_pack_ndhwc": [_P, _P, _I, _I, _I, _I, _I, _P],
     "dsm_unpack_ndhwc": [_P, _P, _I, _I, _I, _I, _I, _P],
     "dsm_softargmin_fwd": [_P, _P, _I, _I, _I, _I, _F, _P],

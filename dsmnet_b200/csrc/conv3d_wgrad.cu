@@ -11,17 +11,20 @@
 // Tensors are the padded NDHWC bf16 volumes of the forward path (zero rims: out-of-range partner
 // voxels contribute nothing, exactly like the zero padding / the missing taps of the reference).
 //
-// The reduction dimension (voxels) is the ROW index of both operands, so the MMA operands are the
-// transposes of the stored tiles: this kernel uses the warp-level path (mma.sync m16n8k16 bf16 with
-// ldmatrix.trans, fp32 accumulate in registers).  A tcgen05 version needs voxel-contiguous
-// (transposed) copies of both tensors or MN-major descriptors and is left for the next round; wgrad
-// is 1/3 of a training step's flops and does not exist on the inference path.
+// Two kernels:
+//  * stride 1 (every Conv3d of the stacks except the down-sampling ones): `wgrad_tc_kernel`, tcgen05 with
+//    MN-major operand descriptors — the reduction index (voxels) is the ROW index of the NDHWC tiles, which is
+//    exactly what an MN-major UMMA operand is, so TMA tiles of both tensors feed the MMA untransposed;
+//  * stride 2 / transposed: `conv3d_wgrad_kernel`, the warp-level path (mma.sync m16n8k16 bf16 with
+//    ldmatrix.trans, fp32 accumulate in registers), described next.
 // CTA = 64 anchor voxels of one row; per (kd,kh) one contiguous partner segment of 64*s+2 voxels
 // (the three kw taps are row offsets into it, stride s) is staged with cp.async; a warp owns a set
 // of 16x8 output tiles and keeps the accumulators of ALL its taps in registers across the
 // persistent tile loop; CTA partials go to a workspace and a second kernel reduces them in a fixed
 // order (deterministic, no atomics) and applies the optional per-channel scale (folded BatchNorm).
 #include "common.cuh"
+#include "ptx.cuh"
+#include "tma_host.cuh"
 
 namespace {
 
@@ -174,6 +177,195 @@ conv3d_wgrad_kernel(const __nv_bfloat16* __restrict__ anchor, const __nv_bfloat1
         }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05 weight gradient, stride 1, one 32 x 32 channel block (anchor channels a0.., partner channels b0..).
+//
+// Per padded plane the volume is a flat list of voxels p (row pitch Wq = W+2), and for an interior anchor voxel the
+// partner voxel of tap (kd,kh,kw) is at plane d+kd-1, position p + (kh-1)*Wq + (kw-1): dW is a 1-D correlation of
+// the two flat lists.  One step = 128 consecutive positions of one anchor plane d:
+//     A (M = 128) = gy tile [136 rows][32 ch], MN-major SWIZZLE_64B, read as FOUR OVERLAPPING atoms along M
+//                   (descriptor LBO = 64 B = one voxel row): M-atom j is the tile shifted by j voxels  -> kw = 2 - j
+//     B (N = 96)  = x plane d+kd-1, three TMA copies of [128 rows][32 ch] starting at p0 + (kh-1)*Wq + 1  -> kh
+//     D_kd[(j,co)][(kh,ci)] += A^T B   for kd = 0,1,2  (three accumulators, 288 TMEM columns), K = 128 = 8 MMAs each
+// (verified on the GPU by tests/cuda/mnmajor_test.cu).  M-atom 3 is unused: 25 % of the tensor work buys kw for free.
+// A CTA owns a contiguous range of steps in (chunk, batch, plane) order, so consecutive steps share two of their
+// three x planes (ring of NB plane slots, each loaded once per sweep), accumulates its whole range in TMEM and
+// writes one [27][32][32] partial; wgrad_reduce_kernel sums the partials in a fixed order.
+// Zero rims make every out-of-range product vanish (gy is 0 there); TMA zero-fills out-of-plane rows.
+// Warp 0 = TMA producer, warp 1 = MMA issuer, all four warps drain TMEM at the end.
+// ---------------------------------------------------------------------------------------------
+namespace tc {
+
+constexpr int KB = 128;                         // positions per step
+constexpr int A_ROWS = KB + 8;                  // + the kw shifts, rounded to a swizzle atom
+constexpr int A_SLOT = 9216;                    // A_ROWS * 64 rounded to 1024
+constexpr int B_COPY = KB * 64;                 // 8192
+constexpr int B_SLOT = 3 * B_COPY;
+constexpr int NA = 3, NB = 5;
+constexpr int SMEM = NA * A_SLOT + NB * B_SLOT + 1024;
+constexpr int TMEM_COLS = 512;                  // 3 x 96 used
+
+struct Geom {
+    int D, BD;                                   // interior planes per batch item; B * D
+    int Wq;                                      // padded row pitch (voxels)
+    int nsteps;                                  // nchunks * BD
+    int a0, b0_unused;
+};
+
+__device__ unsigned int g_wgrad_timeouts = 0;
+
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t;
+}
+// bounded wait (a wedged pipeline must not hang the GPU): gives up after limit_ns or as soon as any thread gave up
+__device__ __forceinline__ bool wait_bar(uint32_t bar, uint32_t parity, unsigned long long limit_ns = 200000000ULL) {
+    if (ptx::mbar_try_wait(bar, parity)) return true;
+    unsigned long long t0 = 0;
+    for (uint32_t spins = 1; ; ++spins) {
+        if (ptx::mbar_try_wait(bar, parity)) return true;
+        if ((spins & 4095u) == 0u) {
+            if (t0 == 0) t0 = gtimer();
+            if (gtimer() - t0 > limit_ns || *reinterpret_cast<volatile unsigned int*>(&g_wgrad_timeouts)) {
+                atomicAdd(&g_wgrad_timeouts, 1u);
+                return false;
+            }
+        }
+    }
+}
+__device__ __forceinline__ uint64_t mn_desc_sw64(uint32_t saddr, uint32_t lbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(512u >> 4) << 32) |
+           (1ull << 46) | (4ull << 61);
+}
+
+__global__ void __launch_bounds__(128, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                float* __restrict__ partial, Geom g, int nslice_b) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sA = base, sB = base + NA * A_SLOT;
+    __shared__ __align__(8) uint64_t bars[2 * NA + 2 * NB + 1];
+    __shared__ uint32_t slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    auto full_a = [&](int i) { return ptx::smem_u32(&bars[i]); };
+    auto empty_a = [&](int i) { return ptx::smem_u32(&bars[NA + i]); };
+    auto full_b = [&](int i) { return ptx::smem_u32(&bars[2 * NA + i]); };
+    auto empty_b = [&](int i) { return ptx::smem_u32(&bars[2 * NA + NB + i]); };
+    const uint32_t done_bar = ptx::smem_u32(&bars[2 * NA + 2 * NB]);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2 * NA + 2 * NB + 1; ++i) ptx::mbar_init(ptx::smem_u32(&bars[i]), 1);
+        ptx::fence_mbar_init();
+        ptx::prefetch_tensormap(&map_a); ptx::prefetch_tensormap(&map_b);
+    }
+    if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(&slot), TMEM_COLS);
+    ptx::tc_fence_before(); __syncthreads(); ptx::tc_fence_after();
+    const uint32_t tmem = slot;
+
+    // this CTA's channel block and step range
+    const int z = blockIdx.y;
+    const int ca0 = (z / nslice_b) * 32, cb0 = (z % nslice_b) * 32;
+    const long long t0 = (long long)g.nsteps * blockIdx.x / gridDim.x, t1 = (long long)g.nsteps * (blockIdx.x + 1) / gridDim.x;
+
+    if (warp == 0) {
+        if (ptx::elect_one_sync()) {
+            uint32_t xn = 0, an = 0;
+            bool ok = true;
+            auto load_x = [&](int p0, int plane) {
+                const int s = xn % NB;
+                ok = ok && wait_bar(empty_b(s), ((xn / NB) & 1u) ^ 1u);
+                ptx::mbar_arrive_expect_tx(full_b(s), B_SLOT);
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    ptx::tma_load_3d(sB + s * B_SLOT + c * B_COPY, &map_b, full_b(s), cb0, p0 + (c - 1) * g.Wq + 1, plane);
+                ++xn;
+            };
+            for (long long t = t0; t < t1 && ok;) {
+                const int q = (int)(t / g.BD), r = (int)(t % g.BD);
+                const int b = r / g.D, dl = r % g.D;
+                const int len = (int)min((long long)(g.D - dl), t1 - t);
+                const int p0 = q * KB, pb = b * (g.D + 2);
+                load_x(p0, pb + dl); load_x(p0, pb + dl + 1);
+                for (int i = 0; i < len && ok; ++i) {
+                    load_x(p0, pb + dl + i + 2);
+                    const int s = an % NA;
+                    ok = ok && wait_bar(empty_a(s), ((an / NA) & 1u) ^ 1u);
+                    ptx::mbar_arrive_expect_tx(full_a(s), A_ROWS * 64);
+                    ptx::tma_load_3d(sA + s * A_SLOT, &map_a, full_a(s), ca0, p0, pb + dl + i + 1);
+                    ++an;
+                }
+                t += len;
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (ptx::elect_one_sync()) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(96) | (1u << 15) | (1u << 16);     // both operands MN-major
+            uint32_t xn = 0, an = 0;
+            bool ok = true, first = true;
+            for (long long t = t0; t < t1 && ok;) {
+                const int r = (int)(t % g.BD);
+                const int dl = r % g.D;
+                const int len = (int)min((long long)(g.D - dl), t1 - t);
+                ok = ok && wait_bar(full_b(xn % NB), (xn / NB) & 1u);
+                ok = ok && wait_bar(full_b((xn + 1) % NB), ((xn + 1) / NB) & 1u);
+                for (int i = 0; i < len && ok; ++i) {
+                    const uint32_t xnew = xn + i + 2;
+                    ok = ok && wait_bar(full_b(xnew % NB), (xnew / NB) & 1u);
+                    const int sa = an % NA;
+                    ok = ok && wait_bar(full_a(sa), (an / NA) & 1u);
+                    ptx::tc_fence_after();
+                    const uint64_t ad0 = mn_desc_sw64(sA + sa * A_SLOT, 64u);
+#pragma unroll
+                    for (int kd = 0; kd < 3; ++kd) {
+                        const uint32_t sb = (xn + i + kd) % NB;
+                        const uint64_t bd0 = mn_desc_sw64(sB + sb * B_SLOT, B_COPY);
+#pragma unroll
+                        for (int ks = 0; ks < KB / 16; ++ks)
+                            ptx::umma_bf16(tmem + kd * 96, ptx::desc_advance(ad0, ks * 1024), ptx::desc_advance(bd0, ks * 1024),
+                                           idesc, (first && ks == 0) ? 0u : 1u);
+                    }
+                    first = false;
+                    ptx::umma_commit(empty_a(sa));
+                    ptx::umma_commit(empty_b((xn + i) % NB));
+                    ++an;
+                }
+                ptx::umma_commit(empty_b((xn + len) % NB));
+                ptx::umma_commit(empty_b((xn + len + 1) % NB));
+                xn += len + 2;
+                t += len;
+            }
+            ptx::umma_commit(done_bar);
+        }
+        __syncwarp();
+    }
+    // epilogue: lane quarter w <-> M-atom j = w <-> kw = 2 - w (quarter 3 carries nothing)
+    const bool fin = wait_bar(done_bar, 0, 4000000000ULL);     // the whole sweep: seconds, not the 0.2 s of a pipeline stage
+    __syncwarp();
+    ptx::tc_fence_after();
+    if (fin && warp < 3 && t1 > t0) {
+        const int kw = 2 - warp;
+        float* out = partial + ((size_t)z * gridDim.x + blockIdx.x) * (27 * 32 * 32);
+#pragma unroll 1
+        for (int kd = 0; kd < 3; ++kd)
+#pragma unroll 1
+            for (int kh = 0; kh < 3; ++kh) {
+                uint32_t v[32];
+                ptx::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + kd * 96 + kh * 32, v);
+                ptx::tc_wait_ld();
+                float4* o = reinterpret_cast<float4*>(out + ((size_t)((kd * 3 + kh) * 3 + kw) * 32 + lane) * 32);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    o[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                       __uint_as_float(v[4 * i + 3]));
+            }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem, TMEM_COLS);
+}
+
+}  // namespace tc
+
 // dW[a][b][tap] = scale_a[a] * scale_b[b] * sum_cta partial[slice][kd group][cta][tap][a][b]   (fixed summation order)
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int nkdgroups, int ncta, int Ca, int Cb, int CA, int CB,
@@ -213,6 +405,48 @@ int wgrad_ncta(long long ntiles) {
     return (int)(ntiles < nsm ? ntiles : nsm);
 }
 
+
+int g_wgrad_mode = 0;          // 0 = tcgen05 kernel where it applies, 1 = warp-level kernel everywhere (A/B timing, tests)
+
+// stride-1 path: returns DSM_EUNSUPPORTED (negative) when the shape does not fit the tcgen05 kernel
+int launch_wgrad_tc(const void* anchor, const void* partner, float* partial, int B, int Ca, int Cb, int D, int H, int W,
+                    int* ncta_out, cudaStream_t st) {
+    const long long HpWp = (long long)(H + 2) * (W + 2);
+    const long long planes = (long long)B * (D + 2);
+    if (HpWp > 0x7fffffffLL - 4096 || planes > 0x7fffffffLL) return DSM_EUNSUPPORTED;
+    const int nchunks = (int)dsm_ceil_div_ll(HpWp, tc::KB);
+    const long long nsteps = (long long)nchunks * B * D;
+    if (nsteps > 0x7fffffffLL) return DSM_EUNSUPPORTED;
+    const int nslices = (Ca / 32) * (Cb / 32);
+    int nsm = DSM_NUM_SMS_B200, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    if (nsm > DSM_NUM_SMS_B200) nsm = DSM_NUM_SMS_B200;      // the workspace is sized for <= 148 partials per channel block... x2
+    int ncta = nsm / nslices;
+    if (ncta < 1) ncta = 1;
+    if (ncta > nsteps) ncta = (int)nsteps;
+    CUtensorMap ma, mb;
+    cuuint64_t dims_a[3] = {(cuuint64_t)Ca, (cuuint64_t)HpWp, (cuuint64_t)planes};
+    cuuint64_t str_a[2] = {(cuuint64_t)Ca * 2, (cuuint64_t)HpWp * Ca * 2};
+    cuuint32_t box_a[3] = {32, (cuuint32_t)tc::A_ROWS, 1};
+    cuuint64_t dims_b[3] = {(cuuint64_t)Cb, (cuuint64_t)HpWp, (cuuint64_t)planes};
+    cuuint64_t str_b[2] = {(cuuint64_t)Cb * 2, (cuuint64_t)HpWp * Cb * 2};
+    cuuint32_t box_b[3] = {32, (cuuint32_t)tc::KB, 1};
+    if (!tma_host::encode(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, anchor, 3, dims_a, str_a, box_a, CU_TENSOR_MAP_SWIZZLE_64B) ||
+        !tma_host::encode(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, partner, 3, dims_b, str_b, box_b, CU_TENSOR_MAP_SWIZZLE_64B))
+        return DSM_EDRIVER;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    tc::Geom g;
+    g.D = D; g.BD = B * D; g.Wq = W + 2; g.nsteps = (int)nsteps; g.a0 = 0; g.b0_unused = 0;
+    tc::wgrad_tc_kernel<<<dim3(ncta, nslices), 128, tc::SMEM, st>>>(ma, mb, partial, g, Cb / 32);
+    *ncta_out = ncta;
+    return dsm_launch_status();
+}
+
 }  // namespace
 
 extern "C" size_t dsm_conv3d_wgrad_workspace_bytes(int Ca, int Cb) {
@@ -239,6 +473,17 @@ extern "C" int dsm_conv3d_wgrad(const void* anchor, const void* partner, float* 
     const int ncta = wgrad_ncta(nt);
     cudaStream_t st = (cudaStream_t)stream;
     float* partial = reinterpret_cast<float*>(ws);
+    if (stride == 1 && g_wgrad_mode == 0 && Da == Dp && Ha == Hp && Wa == Wp) {
+        int ncta_tc = 0;
+        const int rc_tc = launch_wgrad_tc(anchor, partner, partial, B, Ca, Cb, Da, Ha, Wa, &ncta_tc, st);
+        if (rc_tc != DSM_EUNSUPPORTED) {
+            if (rc_tc != 0) return rc_tc;
+            const int per_tc = 27 * Ca * Cb;
+            wgrad_reduce_kernel<<<dsm_ceil_div(per_tc, 256), 256, 0, st>>>(partial, dw, 1, ncta_tc, Ca, Cb, 32, 32, Ca_out, Cb_out,
+                                                                          scale_a, scale_b, accumulate);
+            return dsm_launch_status();
+        }
+    }
     const int CA = Ca > 64 ? 64 : Ca, CB = Cb > 64 ? 64 : Cb;      // slice widths; 128-channel tensors run as 2 slices
     int rc, groups;
     if (CA == 32 && CB == 32)      { rc = launch_wgrad<32, 32, 3>(anchor, partner, partial, g, ncta, st); groups = 1; }
@@ -249,4 +494,16 @@ extern "C" int dsm_conv3d_wgrad(const void* anchor, const void* partner, float* 
     const int per = 27 * Ca * Cb;
     wgrad_reduce_kernel<<<dsm_ceil_div(per, 256), 256, 0, st>>>(partial, dw, groups, ncta, Ca, Cb, CA, CB, Ca_out, Cb_out, scale_a, scale_b, accumulate);
     return dsm_launch_status();
+}
+
+// 0 = tcgen05 kernel for stride-1 layers (default), 1 = warp-level kernel everywhere; returns the previous mode
+extern "C" int dsm_debug_wgrad_mode(int mode) {
+    const int prev = g_wgrad_mode;
+    if (mode == 0 || mode == 1) g_wgrad_mode = mode;
+    return prev;
+}
+extern "C" int dsm_debug_wgrad_timeouts(void) {
+    unsigned int v = 0;
+    cudaMemcpyFromSymbol(&v, tc::g_wgrad_timeouts, sizeof(v));
+    return (int)v;
 }

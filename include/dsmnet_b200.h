@@ -142,6 +142,11 @@ int dsm_bn_finalize_bwd(const double* sums, const float* gamma, const float* mea
 int dsm_bn_act_bwd(const void* gz, const void* y, const void* z, const float* scale, const float* shift,
                    const float* coef, int relu, void* dy, void* gres, int B, int C, int D, int H, int W, void* stream);
 
+/* diagnostics: wgrad kernel selection (0 = tcgen05 for stride-1 layers [default], 1 = warp-level everywhere;
+ * returns the previous mode) and the count of bounded pipeline waits that expired (0 in a healthy run)      */
+int dsm_debug_wgrad_mode(int mode);
+int dsm_debug_wgrad_timeouts(void);
+
 /* layout converters at the reference boundary (NCDHW fp32 <-> padded NDHWC bf16)             */
 int dsm_pack_ndhwc(const float* x_ncdhw, void* y_padded_bf16, int B, int C, int D, int H, int W, void* stream);
 int dsm_unpack_ndhwc(const void* x_padded_bf16, float* y_ncdhw, int B, int C, int D, int H, int W, void* stream);

@@ -59,3 +59,47 @@ def test_conv3d_backward_vs_autograd(cin, cout, D, H, W, stride, transposed):
     # rim of the input gradient stays zero (the layout's invariant)
     g6 = xd.grad.view(2, D + 2, H + 2, W + 2, cin)
     assert float(g6[:, 0].abs().max()) == 0.0 and float(g6[:, :, :, 0].abs().max()) == 0.0
+
+
+def _wgrad_both_modes(cin, cout, B, D, H, W):
+    """dW of a stride-1 conv from the tcgen05 kernel (mode 0) and from the warp-level kernel (mode 1)"""
+    from dsmnet_b200 import _lib
+    from dsmnet_b200.conv3d import conv3d_wgrad
+    from dsmnet_b200.volume_layout import PaddedVolume
+    torch.manual_seed(3)
+    x = PaddedVolume.from_ncdhw(torch.randn(B, cin, D, H, W, device="cuda"))
+    gy = PaddedVolume.from_ncdhw(torch.randn(B, cout, D, H, W, device="cuda"))
+    L = _lib.lib()
+    out = []
+    for mode in (0, 1):
+        prev = L.dsm_debug_wgrad_mode(mode)
+        try:
+            out.append(conv3d_wgrad(gy, x, 1, cout, cin).clone())
+        finally:
+            L.dsm_debug_wgrad_mode(prev)
+    torch.cuda.synchronize()
+    assert L.dsm_debug_wgrad_timeouts() == 0
+    return out, x, gy
+
+
+@pytest.mark.parametrize("cin,cout,B,D,H,W", [
+    (32, 32, 1, 12, 24, 78),       # hourglass quarter resolution
+    (32, 32, 2, 1, 3, 5),          # one plane, one chunk
+    (64, 32, 1, 7, 14, 141),       # partner channel blocks; plane size not a multiple of the 128-position step
+    (64, 64, 3, 5, 9, 33),
+    (32, 128, 1, 4, 6, 50),
+])
+def test_wgrad_tcgen05_matches_warp_level_kernel(cin, cout, B, D, H, W):
+    (tcg, leg), x, gy = _wgrad_both_modes(cin, cout, B, D, H, W)
+    assert l2rel(tcg, leg) < 1e-5                                                 # same bf16 products, fp32 sums in another order
+    # and both against autograd of the fp32 definition on the same bf16 operands
+    xr = x.to_ncdhw().requires_grad_(False)
+    wr = torch.zeros(cout, cin, 3, 3, 3, device="cuda", requires_grad=True)
+    F.conv3d(xr, wr, padding=1).backward(gy.to_ncdhw())
+    assert l2rel(tcg, wr.grad) < 2e-3
+
+
+def test_wgrad_tcgen05_full_size():
+    """BASELINE size (32 -> 32 at 48 x 96 x 312): tcgen05 wgrad against the warp-level kernel"""
+    (tcg, leg), _, _ = _wgrad_both_modes(32, 32, 1, 48, 96, 312)
+    assert l2rel(tcg, leg) < 1e-5
