@@ -74,9 +74,12 @@ class FusedConv3d:
             self.cout, self.cin = weight.shape[0], weight.shape[1]
         device = device if device is not None else weight.device
         self.w = pack_weight(weight, self.transposed).to(device)
-        scale, shift = fold_affine(self.cout, bn, bias)
         self.identity_affine = bn is None and bias is None
-        self.scale, self.shift = scale.to(device), shift.to(device)
+        if self.identity_affine:            # the kernels take NULL for scale/shift: nothing to build or copy
+            self.scale = self.shift = None
+        else:
+            scale, shift = fold_affine(self.cout, bn, bias)
+            self.scale, self.shift = scale.to(device), shift.to(device)
         self.variant = variant
 
     def out_dims(self, x: PaddedVolume):
