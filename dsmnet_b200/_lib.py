@@ -45,6 +45,8 @@ SIGNATURES = {
     "dsm_bn_act_bwd_reduce": [_P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P],
     "dsm_bn_finalize_bwd": [_P, _P, _P, _P, _I, ctypes.c_longlong, _P, _P, _P, _P],
     "dsm_bn_act_bwd": [_P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P],
+    "dsm_conv3d_c1_bwd_workspace_bytes": [],
+    "dsm_conv3d_c1_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, c_size_t, _P],
     "dsm_debug_conv_timeouts": [],
     "dsm_debug_wgrad_mode": [_I],
     "dsm_debug_wgrad_timeouts": [],

@@ -82,6 +82,14 @@ class FusedConv3d:
             self.scale, self.shift = scale.to(device), shift.to(device)
         self.variant = variant
 
+    def set_affine(self, scale: torch.Tensor, shift: torch.Tensor):
+        """Replace the folded per-channel affine (fp32 [Cout] each; padded to CoutP with identity)."""
+        dev = self.w.device
+        coutp = max(16, self.cout)
+        sc = torch.ones(coutp, device=dev); sh = torch.zeros(coutp, device=dev)
+        sc[:scale.numel()] = scale.to(dev).float(); sh[:shift.numel()] = shift.to(dev).float()
+        self.scale, self.shift, self.identity_affine = sc.contiguous(), sh.contiguous(), False
+
     def out_dims(self, x: PaddedVolume):
         return conv_out_dims(x.D, x.H, x.W, self.stride, self.transposed)
 

@@ -148,10 +148,13 @@ def conv_bn_act(x: PaddedVolume, conv: nn.Module, bn: Optional[nn.BatchNorm3d], 
     return from_interior(z)
 
 
+_c1_ws = {}
+
+
 class _ConvC1Function(torch.autograd.Function):
     """Single-output-channel layers (PSMNet classif*.2: Conv3d 32->1, GC-Net l37: ConvTranspose3d 32->1):
-    fp32 output [B, Do, Ho, Wo].  Backward pads the one gradient channel to 32 so that the same dgrad /
-    wgrad kernels apply (31 zero channels: 32x redundant MACs on a layer that is 0.3 % of the flops)."""
+    fp32 output [B, Do, Ho, Wo].  Forward on the tcgen05 kernels; backward is dsm_conv3d_c1_bwd, one CUDA-core pass
+    that produces the input gradient and the weight gradient from the 27 gathered gy values of each voxel."""
 
     @staticmethod
     def forward(ctx, xdata, weight, bias, geom):
@@ -170,23 +173,22 @@ class _ConvC1Function(torch.autograd.Function):
         dev = xdata.device
         gy = gy.contiguous().float()
         Do, Ho, Wo = gy.shape[-3:]
-        g5 = torch.zeros(B, Do + 2, Ho + 2, Wo + 2, 32, device=dev, dtype=torch.bfloat16)
-        g5[:, 1:-1, 1:-1, 1:-1, 0] = gy.to(torch.bfloat16)
-        g = PaddedVolume(g5.reshape(-1), B, 32, Do, Ho, Wo)
-        x = PaddedVolume(xdata, B, C, D, H, W)
-        w = weight.detach()
-        if transposed:                              # weight [C][1] -> [C][32]
-            w32 = torch.zeros(C, 32, 3, 3, 3, device=dev, dtype=w.dtype); w32[:, :1] = w
-        else:                                       # weight [1][C] -> [32][C]
-            w32 = torch.zeros(32, C, 3, 3, 3, device=dev, dtype=w.dtype); w32[:1] = w
-        gx = gw = gb = None
-        if ctx.needs_input_grad[0]:
-            gx = _dgrad_layer(w32, 2 if transposed else 1, transposed, dev)(g, PaddedVolume.empty(B, C, D, H, W, dev)).data
+        w = weight.detach().float()
+        w27 = (w[:, 0] if transposed else w[0]).reshape(C, 27).contiguous()
+        gxv = PaddedVolume.empty_zero_rim(B, C, D, H, W, dev)
+        dw = torch.empty(C, 27, device=dev, dtype=torch.float32)
+        L = _lib.lib()
+        ws = _c1_ws.get(str(dev))
+        if ws is None:
+            ws = _c1_ws[str(dev)] = torch.empty(L.dsm_conv3d_c1_bwd_workspace_bytes() // 4, device=dev, dtype=torch.float32)
+        _lib.check(L.dsm_conv3d_c1_bwd(xdata.data_ptr(), gy.data_ptr(), w27.data_ptr(), gxv.data.data_ptr(), dw.data_ptr(),
+                                       B, D, H, W, Do, Ho, Wo, int(transposed), ws.data_ptr(), ws.numel() * 4,
+                                       _lib.stream_ptr(dev)), "dsm_conv3d_c1_bwd")
+        gx = gxv.data if ctx.needs_input_grad[0] else None
+        gw = None
         if ctx.needs_input_grad[1]:
-            gw = conv3d_wgrad(x, g, 2, C, 1) if transposed else conv3d_wgrad(g, x, 1, 1, C)
-            gw = gw.to(weight.dtype)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = gy.sum().reshape(1)
+            gw = (dw.view(C, 1, 3, 3, 3) if transposed else dw.view(1, C, 3, 3, 3)).to(weight.dtype)
+        gb = gy.sum().reshape(1) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         return gx, gw, gb, None
 
 

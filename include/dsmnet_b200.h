@@ -142,6 +142,17 @@ int dsm_bn_finalize_bwd(const double* sums, const float* gamma, const float* mea
 int dsm_bn_act_bwd(const void* gz, const void* y, const void* z, const float* scale, const float* shift,
                    const float* coef, int relu, void* dy, void* gres, int B, int C, int D, int H, int W, void* stream);
 
+/* backward of the single-output-channel layers (PSMNet classif*.2: Conv3d 32->1, stackhourglass.py:99-109;
+ * GC-Net l37: ConvTranspose3d 32->1 stride 2, gcnet.py:60-62): input gradient and weight gradient in one pass.
+ *   x, gx : padded NDHWC bf16 [B][D+2][H+2][W+2][32] (gx: interior written, rim untouched)
+ *   gy    : fp32 [B][Do][Ho][Wo] (= [D][H][W] for the convolution, up to [2D][2H][2W] for the transposed one)
+ *   w, dw : fp32 [32][27] (the weight with its single output channel squeezed)
+ *   ws    : dsm_conv3d_c1_bwd_workspace_bytes() bytes of scratch                                        */
+size_t dsm_conv3d_c1_bwd_workspace_bytes(void);
+int dsm_conv3d_c1_bwd(const void* x, const float* gy, const float* w, void* gx, float* dw,
+                      int B, int D, int H, int W, int Do, int Ho, int Wo, int transposed,
+                      void* ws, size_t ws_bytes, void* stream);
+
 /* diagnostics: wgrad kernel selection (0 = tcgen05 for stride-1 layers [default], 1 = warp-level everywhere;
  * returns the previous mode) and the count of bounded pipeline waits that expired (0 in a healthy run)      */
 int dsm_debug_wgrad_mode(int mode);

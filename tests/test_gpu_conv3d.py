@@ -38,9 +38,7 @@ def run_layer(x, weight, scale, shift, stride, transposed, residual, relu, varia
         pass
     layer = FusedConv3d(weight.cuda(), None, None, stride, transposed, relu, variant=variant)
     if scale is not None:
-        cp = layer.scale.numel()
-        layer.scale[:scale.numel()] = scale.cuda(); layer.shift[:shift.numel()] = shift.cuda()
-        layer.identity_affine = False
+        layer.set_affine(scale, shift)
     xv = PaddedVolume.from_ncdhw(x.cuda())
     rv = None
     if residual is not None:

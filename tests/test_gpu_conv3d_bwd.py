@@ -103,3 +103,41 @@ def test_wgrad_tcgen05_full_size():
     """BASELINE size (32 -> 32 at 48 x 96 x 312): tcgen05 wgrad against the warp-level kernel"""
     (tcg, leg), _, _ = _wgrad_both_modes(32, 32, 1, 48, 96, 312)
     assert l2rel(tcg, leg) < 1e-5
+
+
+@pytest.mark.parametrize("transposed,B,D,H,W", [
+    (False, 1, 4, 6, 20), (False, 2, 3, 5, 70), (False, 1, 2, 3, 129),
+    (True, 1, 3, 4, 9), (True, 2, 2, 5, 66), (True, 1, 5, 3, 64),
+])
+def test_conv_c1_backward_vs_autograd(transposed, B, D, H, W):
+    """32 -> 1 layers (PSMNet classif*.2, GC-Net l37): dsm_conv3d_c1_bwd against autograd of the fp32 definition"""
+    import torch.nn as nn
+    from dsmnet_b200 import train3d as T
+    from dsmnet_b200.volume_layout import PaddedVolume
+    torch.manual_seed(4)
+    conv = (nn.ConvTranspose3d(32, 1, 3, stride=2, padding=1, output_padding=1) if transposed
+            else nn.Conv3d(32, 1, 3, padding=1)).cuda()
+    with torch.no_grad():
+        conv.weight.copy_(conv.weight.to(torch.bfloat16).float())
+    x = torch.randn(B, 32, D, H, W, device="cuda").to(torch.bfloat16).float()
+    # reference in fp64 (cuDNN's fp32 convolutions may run in TF32)
+    xr = x.double().requires_grad_()
+    conv.double()
+    yr = conv(xr)
+    gy = torch.randn_like(yr).float().double()
+    yr.backward(gy)
+    ref_gw, ref_gb = conv.weight.grad.float().clone(), conv.bias.grad.float().clone()
+    conv.zero_grad(); conv.float()
+    yr, gy = yr.float(), gy.float()
+    xv = PaddedVolume.from_ncdhw(x)
+    xd = xv.data.clone().requires_grad_()
+    y = T.conv_c1(PaddedVolume(xd, B, 32, D, H, W), conv)
+    assert tuple(y.shape) == (B,) + tuple(yr.shape[2:])
+    assert l2rel(y, yr.detach().squeeze(1)) < 1e-2
+    y.backward(gy.squeeze(1))
+    gx = PaddedVolume(xd.grad, B, 32, D, H, W).to_ncdhw()
+    assert l2rel(gx, xr.grad.float()) < 5e-3                  # bf16 output rounding
+    assert l2rel(conv.weight.grad, ref_gw) < 1e-4             # fp32 throughout
+    assert l2rel(conv.bias.grad, ref_gb) < 1e-5
+    g6 = xd.grad.view(B, D + 2, H + 2, W + 2, 32)
+    assert float(g6[:, 0].abs().max()) == 0.0 and float(g6[:, :, :, -1].abs().max()) == 0.0
