@@ -198,8 +198,10 @@ conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
     ptx::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
+    ptx::griddep_launch_dependents();
     if (warp == 0) {
         // ================= TMA producer (whole warp walks the loop, one elected lane issues) =================
+        ptx::griddep_wait();                           // the activations are the previous kernel's output
         int it = 0;                                    // ring position, runs on across tiles
         for (int t = blockIdx.x; t < g.ntiles; t += gridDim.x) {
             const TileInfo ti = decode_tile<MODE>(g, t, plane, vol, Dp);
@@ -272,6 +274,7 @@ conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
         }
     } else {
         // ================= epilogue warps (one TMEM lane = one voxel per thread) =================
+        ptx::griddep_wait();                               // residual reads / output writes must follow the previous kernel
         const int q = warp & 3;                            // TMEM lane quadrant this warp may read
         const int r = q * 32 + lane;                       // row of the tile
         int tcount = 0;
@@ -488,6 +491,7 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     ptx::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
+    ptx::griddep_launch_dependents();
     if (warp == 0) {
         // ================= TMA producer =================
         if (ptx::elect_one_sync()) {                            // all 27 weight tiles, once
@@ -499,6 +503,7 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                          g.w_row[(kd * 3 + kh) * 3 + kw] + ch0);
         }
         __syncwarp();
+        ptx::griddep_wait();                                    // weights are parameters; the activations are the previous kernel's output
         int s = 0; uint32_t ph = 0;                              // ring slot and its phase
         for (int t = item0; t < g.nitems; t += item_step) {
             const RsItem item = rs_decode(g, t, C::R);
@@ -586,6 +591,7 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // warp w reads lanes 32*(w%4)..+31 (hardware rule); the two warps of a quadrant take the even / odd
         // output planes of the band.  Residual rows are fetched BEFORE waiting for the accumulator so
         // that their DRAM latency hides behind the MMAs of this item.
+        ptx::griddep_wait();
         const int q = warp & 3;
         const int half = (warp - 4) >> 2;
         const int r = q * 32 + lane;
@@ -833,6 +839,7 @@ conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     ptx::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
+    ptx::griddep_launch_dependents();
     if (warp == 0) {
         // ================= TMA producer =================
         if (ptx::elect_one_sync()) {
@@ -841,6 +848,7 @@ conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 ptx::tma_load_2d(wsm + g.w_dst[i] * C::ROWB, &map_w, wfull_bar, 0, g.w_src[i]);
         }
         __syncwarp();
+        ptx::griddep_wait();
         int s = 0; uint32_t ph = 0;
         for (int t = blockIdx.x; t < g.ntiles; t += gridDim.x) {
             const long long p0 = (long long)t * 128;
@@ -902,6 +910,7 @@ conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     } else {
         // ================= epilogue: 16 warps, four per TMEM lane quadrant, 2 classes each =================
         // (the MMAs of a tile take ~2.3k cycles: the epilogue is the longer leg, so it gets the threads)
+        ptx::griddep_wait();
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;                       // 0..3: owns accumulator blocks 2*half, 2*half+1
         const int r = q * 32 + lane;
@@ -1023,6 +1032,22 @@ bool encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* di
                             (row_bytes == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
+// Kernel launch with the programmatic-stream-serialization attribute when `pdl` is set: the kernel's prologue
+// (barrier init, TMEM allocation, resident weights) then overlaps the tail of the previous kernel in the stream;
+// the kernels order their dependent accesses with griddepcontrol.wait.
+thread_local bool g_launch_pdl = false;        // set per call from `variant` bit 7 (host side, per calling thread)
+
+template <typename... KArgs, typename... Args>
+void launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = g_launch_pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 template <int KC, int NP, int MODE>
 int launch_cfg(const ConvMaps& maps, const ConvGeom& g, dim3 grid, const float* scale, const float* shift,
                const void* residual, void* y, cudaStream_t st) {
@@ -1034,7 +1059,7 @@ int launch_cfg(const ConvMaps& maps, const ConvGeom& g, dim3 grid, const float* 
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     int nblocks = nsm * C::CTAS_PER_SM;
     if (nblocks > (int)grid.x) nblocks = (int)grid.x;
-    kern<<<nblocks, C::THREADS, C::SMEM, st>>>(maps, g, scale, shift, residual, y);
+    launch_kernel(kern, dim3(nblocks), dim3(C::THREADS), C::SMEM, st, maps, g, scale, shift, residual, y);
     return dsm_launch_status();
 }
 
@@ -1060,7 +1085,7 @@ int launch_rs(const CUtensorMap& map_a, const CUtensorMap& map_w, const RsGeom& 
     int per_group = nsm / g.ngroups;                            // persistent: one CTA per SM, split evenly over the channel groups
     if (per_group > g.nitems) per_group = g.nitems;
     const int nblocks = per_group * g.ngroups;
-    kern<<<nblocks, C::THREADS, C::SMEM, st>>>(map_a, map_w, g, scale, shift, residual, y);
+    launch_kernel(kern, dim3(nblocks), dim3(C::THREADS), C::SMEM, st, map_a, map_w, g, scale, shift, residual, y);
     return dsm_launch_status();
 }
 
@@ -1074,7 +1099,7 @@ int launch_dc(const CUtensorMap& map_a, const CUtensorMap& map_w, const DcGeom& 
     int nsm = DSM_NUM_SMS_B200, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     const int nblocks = g.ntiles < nsm ? g.ntiles : nsm;
-    kern<<<nblocks, C::THREADS, C::SMEM, st>>>(map_a, map_w, g, scale, shift, residual, y);
+    launch_kernel(kern, dim3(nblocks), dim3(C::THREADS), C::SMEM, st, map_a, map_w, g, scale, shift, residual, y);
     return dsm_launch_status();
 }
 
@@ -1121,6 +1146,7 @@ int conv3d_dispatch(const void* x, const void* w, const float* scale, const floa
     if (!x || !w || !y || B <= 0 || Cin <= 0 || Cout <= 0 || D <= 0 || H <= 0 || W <= 0) return DSM_EINVAL;
     if (stride != 1 && stride != 2) return DSM_EINVAL;
     if (relu < 0 || relu > 2) return DSM_EINVAL;
+    g_launch_pdl = (variant & 128) != 0;
     if (transposed && stride != 2) return DSM_EUNSUPPORTED;
     if (y_dtype != DSM_BF16 && y_dtype != DSM_F32) return DSM_EINVAL;
     if (Cin != 32 && Cin != 64 && Cin != 128) return DSM_EUNSUPPORTED;

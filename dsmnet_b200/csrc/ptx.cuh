@@ -22,6 +22,13 @@ __device__ __forceinline__ bool elect_one_sync() {
     return pred != 0;
 }
 
+// ---- programmatic dependent launch ----------------------------------------------------------
+// launch_dependents: the next kernel in the stream (if launched with the programmatic-serialization attribute) may
+// start its CTAs as soon as every CTA of this grid has executed this or exited; wait: blocks until the prerequisite
+// grid has fully completed and its memory is visible.  Both are no-ops for a normally launched kernel.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- mbarrier -------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");

@@ -21,6 +21,7 @@ from .conv3d import FusedConv3d, conv_out_dims
 from .cost_volume import concat_volume
 from .softargmin import softargmin
 from .volume_layout import PaddedVolume
+from .psmnet import PDL_VARIANT
 
 
 def conv3d_bn(in_planes, out_planes, kernel_size=3, stride=1):
@@ -65,8 +66,8 @@ class feature3d(nn.Module):
                          "l33", "l34", "l35", "l36"):
                 seq = getattr(self, name)
                 tr = isinstance(seq[0], nn.ConvTranspose3d)
-                plan[name] = FusedConv3d(seq[0].weight, seq[1], seq[0].bias, seq[0].stride[0], tr, 2, device)
-            plan["l37"] = FusedConv3d(self.l37.weight, None, self.l37.bias, 2, True, 0, device)
+                plan[name] = FusedConv3d(seq[0].weight, seq[1], seq[0].bias, seq[0].stride[0], tr, 2, device, PDL_VARIANT)
+            plan["l37"] = FusedConv3d(self.l37.weight, None, self.l37.bias, 2, True, 0, device, PDL_VARIANT)
             self._plan, self._plan_key = plan, key
         return self._plan
 

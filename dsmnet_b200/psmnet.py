@@ -17,6 +17,8 @@ Inference: eval-mode BatchNorm folded into the conv epilogue, everything fused. 
 """
 from __future__ import annotations
 
+import os
+
 import math
 from typing import Dict, Optional, Tuple
 
@@ -54,10 +56,15 @@ class hourglass(nn.Module):
                                    nn.BatchNorm3d(inplanes))
 
 
+# dsm_conv3d_fwd_ex variant bit 7: programmatic dependent launch (DSM_NO_PDL=1 in the environment turns it off)
+PDL_VARIANT = 0 if os.environ.get("DSM_NO_PDL") == "1" else 128
+
+
 class _Plan:
     """Packed weights + folded BatchNorm of every 3-D layer, built once per parameter version."""
 
     def __init__(self, m: "PSMNetHotPath", device, variant=0):
+        variant |= PDL_VARIANT        # consecutive layers: prologue of layer i+1 overlaps the tail of layer i
         def cb(seq, stride=1, transposed=False, relu=False):
             return FusedConv3d(seq[0].weight, seq[1], None, stride, transposed, relu, device, variant)
 

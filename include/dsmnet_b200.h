@@ -209,7 +209,10 @@ int dsm_warp_indices(const float* disp, const float* row, const float* col, int 
  * that is a crop of the natural output size (the reference's crop-to-min add, myadd_3d /
  * myAdd3d, stackhourglass.py:10-20, util_fun.py:41-51; pass 0,0,0 for the natural size) and
  * `variant` (bit0: descriptor base-offset experiment, bit1: force the per-tap kernel instead of the
- * default row-shifted-descriptor kernel for stride-1 convolutions, bits 8-10: bring-up level; 0 = default).                                  */
+ * default row-shifted-descriptor kernel for stride-1 convolutions, bit7: launch with programmatic stream
+ * serialization - the kernel's prologue overlaps the previous kernel's tail, its dependent accesses wait on
+ * griddepcontrol.wait; only for parameters (weights, scale, shift) that were written before the previous kernel
+ * started; 0 = default).                                  */
 int dsm_conv3d_fwd_ex(const void* x, const void* w_packed, const float* scale, const float* shift,
                       const void* residual, void* y,
                       int B, int Cin, int Cout, int D, int H, int W,
