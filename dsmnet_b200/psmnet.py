@@ -58,6 +58,8 @@ class hourglass(nn.Module):
 
 # dsm_conv3d_fwd_ex variant bit 7: programmatic dependent launch (DSM_NO_PDL=1 in the environment turns it off)
 PDL_VARIANT = 0 if os.environ.get("DSM_NO_PDL") == "1" else 128
+# classifier branches on a second stream next to the following hourglass (DSM_CLS_STREAM=0 turns it off)
+CLS_SIDE_STREAM = os.environ.get("DSM_CLS_STREAM", "1") != "0"
 
 
 class _Plan:
@@ -93,6 +95,7 @@ class PSMNetHotPath(nn.Module):
         self.maxdisp = maxdisp
         self.align_corners = align_corners        # PyTorch<=0.3 F.upsample semantics
         self.variant = variant
+        self._side = {}
         self.dres0 = nn.Sequential(convbn_3d(64, 32, 3, 1, 1), nn.ReLU(inplace=True),
                                    convbn_3d(32, 32, 3, 1, 1), nn.ReLU(inplace=True))
         self.dres1 = nn.Sequential(convbn_3d(32, 32, 3, 1, 1), nn.ReLU(inplace=True),
@@ -201,6 +204,15 @@ class PSMNetHotPath(nn.Module):
         x = cost0
         pre_prev = post_prev = None
         pre1 = None
+        costs, prev = [], None
+        side = main = None
+        if CLS_SIDE_STREAM:
+            main = torch.cuda.current_stream(fL.device)
+            side = self._side.get(str(fL.device))
+            if side is None:
+                side = self._side[str(fL.device)] = torch.cuda.Stream(fL.device)
+            if "tc" not in ws:
+                ws["tc"] = [PaddedVolume.empty(B, 32, D, H, W, fL.device) for _ in range(3)]
         for i, hg in enumerate(plan.hg):
             presqu = None if i == 0 else pre1                                   # :141,144 (pre1 both times)
             postsqu = post_prev
@@ -213,8 +225,19 @@ class PSMNetHotPath(nn.Module):
             if i == 0:
                 pre1 = pre
             post_prev = post
-        costs = []
-        prev = None
+            if side is not None:
+                # classif{i+1} needs only out{i+1}: it runs on a second stream next to the following hourglass, whose
+                # half / quarter resolution layers leave SMs idle (partial waves, pipeline fill and drain)
+                ev = torch.cuda.Event(); ev.record(main)
+                side.wait_event(ev)
+                with torch.cuda.stream(side):
+                    c0, c2 = plan.cls[i]
+                    c0(ws["out"][i], ws["tc"][i])
+                    prev = c2(ws["tc"][i], ws["cost"][i], residual=prev)       # :147-149 cumulative adds
+                    costs.append(prev)
+        if side is not None:
+            main.wait_stream(side)
+            return costs
         for i, (c0, c2) in enumerate(plan.cls):
             c0(ws["out"][i], ws["t"])
             prev = c2(ws["t"], ws["cost"][i], residual=prev)                    # :147-149 cumulative adds
