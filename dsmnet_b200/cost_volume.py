@@ -39,6 +39,45 @@ class ConcatVolumeFunction(torch.autograd.Function):
         return gL, gR, None, None
 
 
+class ConcatVolumePaddedFunction(torch.autograd.Function):
+    """The volume in the 3-D stack's layout (flat storage of a PaddedVolume, bf16, zero rim), differentiable:
+    backward sums the padded bf16 gradient over d straight into the two NCHW fp32 feature gradients."""
+
+    @staticmethod
+    def forward(ctx, fL, fR, D, mode):
+        _lib.require_cuda(fL, fR)
+        fL = fL.contiguous().float(); fR = fR.contiguous().float()
+        B, C, H, W = fL.shape
+        vol = PaddedVolume.empty(B, 2 * C, D, H, W, fL.device, zero_rim=False)
+        _lib.check(_lib.lib().dsm_concat_volume_fwd(fL.data_ptr(), fR.data_ptr(), vol.data.data_ptr(), B, C, D, H, W, mode,
+                                                    _lib.DSM_BF16, _lib.DSM_NDHWC_PADDED, _lib.stream_ptr(fL.device)),
+                   "dsm_concat_volume_fwd")
+        ctx.shape, ctx.D, ctx.mode = (B, C, H, W), D, mode
+        return vol.data
+
+    @staticmethod
+    def backward(ctx, g):
+        B, C, H, W = ctx.shape
+        g = g.contiguous()
+        if g.dtype != torch.bfloat16:
+            g = g.to(torch.bfloat16)
+        gL = torch.empty(B, C, H, W, device=g.device, dtype=torch.float32)
+        gR = torch.empty_like(gL)
+        _lib.check(_lib.lib().dsm_concat_volume_bwd(g.data_ptr(), gL.data_ptr(), gR.data_ptr(), B, C, ctx.D, H, W, ctx.mode,
+                                                    _lib.DSM_BF16, _lib.DSM_NDHWC_PADDED, _lib.stream_ptr(g.device)),
+                   "dsm_concat_volume_bwd")
+        return gL, gR, None, None
+
+
+def concat_volume_padded(fL, fR, D, mode="psm") -> PaddedVolume:
+    """Differentiable padded-bf16 volume (training path of the 3-D stacks)."""
+    if fL.shape != fR.shape or fL.dim() != 4:
+        raise _lib.DsmError("concat_volume expects two NCHW tensors of equal shape")
+    B, C, H, W = fL.shape
+    data = ConcatVolumePaddedFunction.apply(fL, fR, int(D), _lib.VOLUME_MODES[mode])
+    return PaddedVolume(data, B, 2 * C, int(D), H, W)
+
+
 def concat_volume(fL, fR, D, mode="psm", padded_bf16=False, out=None):
     if fL.shape != fR.shape or fL.dim() != 4:
         raise _lib.DsmError("concat_volume expects two NCHW tensors of equal shape")

@@ -174,6 +174,77 @@ concat_bwd_ncdhw_kernel(const float* __restrict__ g, float* __restrict__ gL, flo
 }
 
 // ---------------------------------------------------------------------------------------
+// Backward from the 3-D stack's own layout: g is padded NDHWC bf16 [B][D+2][H+2][W+2][2C].
+// CTA = one image row (b, y).  A thread owns output chunks (x, j): 8 channels of one pixel, j < C/8 from the
+// first half of the voxel, j >= C/8 from the second; for every d it reads the 16-byte chunk of the voxel that
+// pixel was copied to — (d, y, x) for the first half, (d, y, x +- d) for the second — so a warp's loads are
+// contiguous runs of the row and nothing needs an atomic.  The fp32 sums are transposed through shared
+// memory into the NCHW gradients of the two feature maps.
+// ---------------------------------------------------------------------------------------
+constexpr int CB_THREADS = 512;
+constexpr int CB_MAXK = 8;                               // chunks per thread: W * 2C/8 <= 4096
+
+__global__ void __launch_bounds__(CB_THREADS)
+concat_bwd_ndhwc_kernel(const uint4* __restrict__ g, float* __restrict__ gL, float* __restrict__ gR,
+                        int C, int D, int H, int W, int mode) {
+    extern __shared__ __align__(16) float s_out[];        // [2C][W + 1]
+    const int y = blockIdx.x, b = blockIdx.y;
+    const int cpv = (2 * C) / 8, half = cpv / 2;
+    const int nchunks = W * cpv;
+    const int Wp = W + 2, Hp = H + 2;
+    const size_t plane = (size_t)Hp * Wp * cpv;            // 16-byte chunks per padded plane
+    const uint4* row = g + (((size_t)b * (D + 2) + 1) * Hp + (y + 1)) * Wp * cpv + cpv;   // voxel (d=0, y, x=0)
+    float acc[CB_MAXK][8];
+    int xk[CB_MAXK], offk[CB_MAXK];                        // pixel and chunk offset of each owned output chunk; xk < 0: none
+#pragma unroll
+    for (int k = 0; k < CB_MAXK; ++k) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
+        const int idx = threadIdx.x + k * CB_THREADS;
+        xk[k] = idx < nchunks ? idx / cpv : -1;
+        offk[k] = idx;                                     // = x * cpv + j
+    }
+    const bool second = (threadIdx.x % cpv) >= half;       // CB_THREADS % cpv == 0: the same half for every k
+    const int step = second ? ((mode == DSM_VOL_GC_RIGHT) ? -cpv : cpv) : 0;      // chunk offset per unit of d
+    for (int d = 0; d < D; ++d) {
+        const uint4* rd = row + (size_t)d * plane;
+#pragma unroll
+        for (int k = 0; k < CB_MAXK; ++k) {
+            const int x = xk[k];
+            if (x < 0) continue;
+            bool ok;
+            if (!second) ok = (mode != DSM_VOL_PSM) || x >= d;
+            else if (mode == DSM_VOL_GC_RIGHT) ok = x - d >= 0;
+            else ok = x + d < W;
+            if (ok) {
+                const uint4 v = __ldg(rd + offk[k] + d * step);
+                const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { acc[k][2 * i] += bf16_lo(w4[i]); acc[k][2 * i + 1] += bf16_hi(w4[i]); }
+            }
+        }
+    }
+    const int pitch = W + 1;
+#pragma unroll
+    for (int k = 0; k < CB_MAXK; ++k) {
+        const int idx = threadIdx.x + k * CB_THREADS;
+        if (idx >= nchunks) break;
+        const int x = idx / cpv, j = idx - x * cpv;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_out[(j * 8 + i) * pitch + x] = acc[k][i];
+    }
+    __syncthreads();
+    // channel ch < C is the first half: fL (fR for GC_RIGHT); ch >= C the other map
+    for (int i = threadIdx.x; i < 2 * C * W; i += CB_THREADS) {
+        const int ch = i / W, x = i - ch * W;
+        const bool first = ch < C;
+        const int c = first ? ch : ch - C;
+        float* dst = (first != (mode == DSM_VOL_GC_RIGHT)) ? gL : gR;
+        dst[(((size_t)b * C + c) * H + y) * W + x] = s_out[ch * pitch + x];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // NCDHW fp32 <-> padded NDHWC bf16.  CTA = (y', d', b); transposes a [C][W] slab through smem.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -263,6 +334,17 @@ extern "C" int dsm_concat_volume_bwd(const void* gout, float* gL, float* gR,
                                      int mode, int dtype, int layout, void* stream) {
     if (!gout || !gL || !gR || B <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0) return DSM_EINVAL;
     if (mode < DSM_VOL_PSM || mode > DSM_VOL_GC_RIGHT) return DSM_EINVAL;
+    if (dtype == DSM_BF16 && layout == DSM_NDHWC_PADDED) {
+        if (C % 8 != 0 || CB_THREADS % (2 * C / 8) != 0 || (long long)W * (2 * C / 8) > CB_THREADS * CB_MAXK || H > 65535 || B > 65535)
+            return DSM_EUNSUPPORTED;
+        if (!dsm_aligned16(gout)) return DSM_EALIGN;
+        const size_t smem = (size_t)2 * C * (W + 1) * sizeof(float);
+        if (smem > 200 * 1024) return DSM_EUNSUPPORTED;
+        cudaError_t e = cudaFuncSetAttribute(concat_bwd_ndhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        concat_bwd_ndhwc_kernel<<<dim3(H, B), CB_THREADS, smem, (cudaStream_t)stream>>>((const uint4*)gout, gL, gR, C, D, H, W, mode);
+        return dsm_launch_status();
+    }
     if (dtype != DSM_F32 || layout != DSM_NCDHW) return DSM_EUNSUPPORTED;
     const long long n = (long long)B * C * H * W;
     const long long blocks = dsm_ceil_div_ll(n, 256);

@@ -18,10 +18,10 @@ import torch.nn as nn
 
 from . import _lib
 from .conv3d import FusedConv3d, conv_out_dims
-from .cost_volume import concat_volume
+from .cost_volume import concat_volume, concat_volume_padded
 from .softargmin import softargmin
 from .volume_layout import PaddedVolume
-from .psmnet import PDL_VARIANT
+from .psmnet import PDL_VARIANT, CLS_SIDE_STREAM
 
 
 def conv3d_bn(in_planes, out_planes, kernel_size=3, stride=1):
@@ -54,6 +54,7 @@ class feature3d(nn.Module):
         self.l35 = deconv3d_bn(F_ * 2, F_ * 2); self.l36 = deconv3d_bn(F_ * 2, F_)
         self.l37 = deconv3d_bn(F_, 1, bn=False)
         self._plan = None
+        self._side = {}
         self._plan_key = None
         self._ws: Dict[Tuple, dict] = {}
 
@@ -130,6 +131,17 @@ class feature3d(nn.Module):
                 return skip
             return PaddedVolume.from_ncdhw(skip.to_ncdhw()[:, :, :like.D, :like.H, :like.W])
 
+        # the full-resolution skip branch l19 -> l20 (59 % of the flops) is needed only by l36: it runs on a second
+        # stream beside the encoder-decoder chain, whose 1/8 .. 1/32 resolution layers cannot fill the machine
+        side = None
+        if CLS_SIDE_STREAM:
+            main = torch.cuda.current_stream(dev)
+            side = self._side.get(str(dev))
+            if side is None:
+                side = self._side[str(dev)] = torch.cuda.Stream(dev)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                x20 = p["l20"](p["l19"](vol, ws["x19"]), ws["x20"])
         x21 = p["l21"](vol, ws["x21"]); x24 = p["l24"](x21, ws["x24"]); x27 = p["l27"](x24, ws["x27"]); x30 = p["l30"](x27, ws["x30"])
         x32 = p["l32"](p["l31"](x30, ws["x31"]), ws["x32"])
         x29 = p["l29"](p["l28"](x27, ws["x28"]), ws["x29"])
@@ -138,7 +150,10 @@ class feature3d(nn.Module):
         x34 = p["l34"](x33, ws["x34"], residual=crop(x26, ws["x34"]))
         x23 = p["l23"](p["l22"](x21, ws["x22"]), ws["x23"])
         x35 = p["l35"](x34, ws["x35"], residual=crop(x23, ws["x35"]))
-        x20 = p["l20"](p["l19"](vol, ws["x19"]), ws["x20"])
+        if side is None:
+            x20 = p["l20"](p["l19"](vol, ws["x19"]), ws["x20"])
+        else:
+            main.wait_stream(side)
         x36 = p["l36"](x35, ws["x36"], residual=crop(x20, ws["x36"]))
         return p["l37"](x36, ws["x37"])
 
@@ -159,8 +174,7 @@ class GCNetHotPath(nn.Module):
     def forward(self, fL, fR):
         if self.training or torch.is_grad_enabled() and (fL.requires_grad or fR.requires_grad or
                                                          any(p.requires_grad for p in self.parameters())):
-            from .train3d import volume_from_ncdhw
-            vol = volume_from_ncdhw(concat_volume(fL, fR, self.D, "gc"))     # differentiable NCDHW volume -> padded bf16
+            vol = concat_volume_padded(fL, fR, self.D, "gc")                 # differentiable, padded bf16 directly
         else:
             vol = concat_volume(fL, fR, self.D, "gc", padded_bf16=True)
         x37 = self.layer3d.aggregate(vol)

@@ -28,7 +28,7 @@ import torch.nn.functional as F
 
 from . import _lib
 from .conv3d import FusedConv3d
-from .cost_volume import concat_volume
+from .cost_volume import concat_volume, concat_volume_padded
 from .softargmin import upsample_softargmin
 from .volume_layout import PaddedVolume
 
@@ -159,7 +159,7 @@ class PSMNetHotPath(nn.Module):
         BatchNorm with batch statistics / ReLU / adds as stock PyTorch ops (dsmnet_b200/train3d.py)."""
         from . import train3d as T
         D = self.maxdisp // 4
-        vol = T.volume_from_ncdhw(concat_volume(fL, fR, D, "psm"))
+        vol = concat_volume_padded(fL, fR, D, "psm")      # padded bf16 directly; backward sums over d into NCHW fp32
 
         def cb(seq, x, relu=0, residual=None):
             return T.conv_bn_act(x, seq[0], seq[1], relu, residual)

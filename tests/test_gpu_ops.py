@@ -161,6 +161,27 @@ def test_volume_vs_oracle(mode, shape):
         assert torch.equal(vol.to_ncdhw().cpu(), ref.to(torch.bfloat16).float())
 
 
+@pytest.mark.parametrize("mode", ["psm", "gc", "gc_right"])
+@pytest.mark.parametrize("shape", [(1, 32, 12, 40, 9), (2, 8, 5, 13, 20), (1, 32, 16, 312, 48), (1, 16, 6, 500, 30)])
+def test_volume_padded_backward_vs_oracle(mode, shape):
+    """differentiable padded-bf16 volume: backward kernel (sum over d of the padded NDHWC bf16 gradient) against the
+    oracle's NCDHW gradient of the same bf16-rounded values"""
+    from dsmnet_b200.cost_volume import concat_volume_padded
+    from dsmnet_b200.volume_layout import PaddedVolume
+    B, C, H, W, D = shape
+    torch.manual_seed(6)
+    fL = torch.randn(B, C, H, W); fR = torch.randn(B, C, H, W)
+    a = dev(fL).requires_grad_(); b = dev(fR).requires_grad_()
+    vol = concat_volume_padded(a, b, D, mode)
+    ref = O.concat_volume(fL, fR, D, mode)
+    assert torch.equal(PaddedVolume(vol.data.detach(), *vol.shape5).to_ncdhw().cpu(), ref.to(torch.bfloat16).float())
+    g = torch.randn_like(ref).to(torch.bfloat16).float()               # bf16-representable gradient, NCDHW
+    gv = PaddedVolume.from_ncdhw(dev(g))
+    vol.data.backward(gv.data)
+    gL, gR = O.concat_volume_grads(g, D, mode)
+    assert rel_err(a.grad, gL) < 1e-5 and rel_err(b.grad, gR) < 1e-5
+
+
 def test_pack_unpack_roundtrip():
     from dsmnet_b200.volume_layout import PaddedVolume
     torch.manual_seed(3)

@@ -47,11 +47,11 @@ def main():
     args = ap.parse_args()
     dev = torch.device("cuda")
     psm = PSMNetHotPath(192).to(dev).train()
-    pl = torch.randn(1, 32, 96, 312, device=dev); pr = torch.randn(1, 32, 96, 312, device=dev)
+    pl = torch.randn(1, 32, 96, 312, device=dev, requires_grad=True); pr = torch.randn(1, 32, 96, 312, device=dev, requires_grad=True)
     gt = torch.rand(1, 384, 1248, device=dev) * 96
 
     def psm_step():
-        psm.zero_grad(set_to_none=True)
+        psm.zero_grad(set_to_none=True); pl.grad = pr.grad = None
         sum((p - gt).abs().mean() for p in psm(pl, pr, (384, 1248))).backward()
 
     if args.host_profile:
@@ -65,11 +65,11 @@ def main():
     del psm
     torch.cuda.empty_cache()
     gc = GCNetHotPath(192).to(dev).train()
-    gl = torch.randn(1, 32, 128, 256, device=dev); gr = torch.randn(1, 32, 128, 256, device=dev)
+    gl = torch.randn(1, 32, 128, 256, device=dev, requires_grad=True); gr = torch.randn(1, 32, 128, 256, device=dev, requires_grad=True)
     gtg = torch.rand(1, 1, 256, 512, device=dev) * 96
 
     def gc_step():
-        gc.zero_grad(set_to_none=True)
+        gc.zero_grad(set_to_none=True); gl.grad = gr.grad = None
         (gc(gl, gr) - gtg).abs().mean().backward()
     measure("GC-Net 256x512 D=192", gc_step)
 
