@@ -53,30 +53,41 @@ bn_reduce_kernel(const uint4* __restrict__ y, const uint4* __restrict__ gz, cons
         for (int i = 0; i < 16; ++i) { sc[i] = scale[grp * 16 + i]; sh[i] = shift[grp * 16 + i]; }
     }
     const long long stride = (long long)gridDim.x * BN_THREADS;
-    for (long long v = (long long)blockIdx.x * BN_THREADS + threadIdx.x; v < nvec; v += stride) {
-        uint4 a, b;
-        float fy[16];
-        ld_nc_v8(y + 2 * v, a, b);
-        unpack16(a, b, fy);
-        if (MODE == 0) {
+    constexpr int U = (MODE == 0) ? 4 : 2;                       // independent 32-byte loads in flight per stream and thread
+    for (long long v0 = (long long)blockIdx.x * BN_THREADS + threadIdx.x; v0 < nvec; v0 += stride * U) {
+        uint4 ya[U], yb[U], ga[U], gb[U], za[U], zb[U];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { s0[i] += fy[i]; s1[i] = fmaf(fy[i], fy[i], s1[i]); }
-        } else {
-            float fg[16];
-            ld_nc_v8(gz + 2 * v, a, b);
-            unpack16(a, b, fg);
-            if (MODE == 2) {
-                float fz[16];
-                ld_nc_v8(z + 2 * v, a, b);
-                unpack16(a, b, fz);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) fg[i] = fz[i] > 0.f ? fg[i] : 0.f;
-            } else if (MODE == 3) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) fg[i] = fmaf(fy[i], sc[i], sh[i]) > 0.f ? fg[i] : 0.f;
+        for (int u = 0; u < U; ++u) {
+            const long long v = v0 + u * stride;
+            if (v < nvec) {
+                ld_nc_v8(y + 2 * v, ya[u], yb[u]);
+                if (MODE != 0) ld_nc_v8(gz + 2 * v, ga[u], gb[u]);
+                if (MODE == 2) ld_nc_v8(z + 2 * v, za[u], zb[u]);
             }
+        }
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { s0[i] += fg[i]; s1[i] = fmaf(fg[i], fy[i], s1[i]); }
+        for (int u = 0; u < U; ++u) {
+            if (v0 + u * stride >= nvec) break;
+            float fy[16];
+            unpack16(ya[u], yb[u], fy);
+            if (MODE == 0) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { s0[i] += fy[i]; s1[i] = fmaf(fy[i], fy[i], s1[i]); }
+            } else {
+                float fg[16];
+                unpack16(ga[u], gb[u], fg);
+                if (MODE == 2) {
+                    float fz[16];
+                    unpack16(za[u], zb[u], fz);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) fg[i] = fz[i] > 0.f ? fg[i] : 0.f;
+                } else if (MODE == 3) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) fg[i] = fmaf(fy[i], sc[i], sh[i]) > 0.f ? fg[i] : 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { s0[i] += fg[i]; s1[i] = fmaf(fg[i], fy[i], s1[i]); }
+            }
         }
     }
     // lanes l and l ^ off share a channel group when off >= groups
@@ -169,35 +180,50 @@ bn_act_fwd_kernel(const uint4* __restrict__ y, const uint4* __restrict__ res, ui
 #pragma unroll
     for (int i = 0; i < 16; ++i) { sc[i] = scale[grp * 16 + i]; sh[i] = shift[grp * 16 + i]; }
     const size_t base = (size_t)blockIdx.y * planevec;
-    for (int v = blockIdx.x * BN_THREADS + threadIdx.x; v < planevec; v += gridDim.x * BN_THREADS) {
-        const int hp = v / rowvec;
-        const int wp = (v - hp * rowvec) / groups;
-        const bool rim = rim_plane || hp == 0 || hp == g.H + 1 || wp == 0 || wp == g.W + 1;
-        uint4 a = make_uint4(0, 0, 0, 0), b = a;
-        if (!rim) {
-            float f[16];
-            ld_nc_v8(y + 2 * (base + v), a, b);
-            unpack16(a, b, f);
+    constexpr int U = 2;                                         // vectors per thread and iteration, loads issued first
+    const int step = gridDim.x * BN_THREADS;
+    for (int v0 = blockIdx.x * BN_THREADS + threadIdx.x; v0 < planevec; v0 += step * U) {
+        uint4 ya[U], yb[U], ra[U], rb[U];
+        bool rim[U];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = fmaf(f[i], sc[i], sh[i]);
-            if (RELU == 2) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+        for (int u = 0; u < U; ++u) {
+            const int v = v0 + u * step;
+            const int hp = v / rowvec;
+            const int wp = (v - hp * rowvec) / groups;
+            rim[u] = rim_plane || hp == 0 || hp >= g.H + 1 || wp == 0 || wp == g.W + 1;
+            if (!rim[u] && v < planevec) {
+                ld_nc_v8(y + 2 * (base + v), ya[u], yb[u]);
+                if (HAS_RES) ld_nc_v8(res + 2 * (base + v), ra[u], rb[u]);
             }
-            if (HAS_RES) {
-                float r[16];
-                ld_nc_v8(res + 2 * (base + v), a, b);
-                unpack16(a, b, r);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) f[i] += r[i];
-            }
-            if (RELU == 1) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
-            }
-            pack16(f, a, b);
         }
-        st_v8(z + 2 * (base + v), a, b);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int v = v0 + u * step;
+            if (v >= planevec) break;
+            uint4 a = make_uint4(0, 0, 0, 0), b = a;
+            if (!rim[u]) {
+                float f[16];
+                unpack16(ya[u], yb[u], f);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f[i] = fmaf(f[i], sc[i], sh[i]);
+                if (RELU == 2) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+                }
+                if (HAS_RES) {
+                    float r[16];
+                    unpack16(ra[u], rb[u], r);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) f[i] += r[i];
+                }
+                if (RELU == 1) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+                }
+                pack16(f, a, b);
+            }
+            st_v8(z + 2 * (base + v), a, b);
+        }
     }
 }
 
@@ -220,34 +246,49 @@ bn_act_bwd_kernel(const uint4* __restrict__ gz, const uint4* __restrict__ y, con
         if (RELU == 2) { sc[i] = scale[grp * 16 + i]; sh[i] = shift[grp * 16 + i]; }
     }
     const size_t base = (size_t)blockIdx.y * planevec;
-    for (int v = blockIdx.x * BN_THREADS + threadIdx.x; v < planevec; v += gridDim.x * BN_THREADS) {
-        const int hp = v / rowvec;
-        const int wp = (v - hp * rowvec) / groups;
-        const bool rim = rim_plane || hp == 0 || hp == g.H + 1 || wp == 0 || wp == g.W + 1;
-        uint4 a = make_uint4(0, 0, 0, 0), b = a, ga = a, gb = a;
-        if (!rim) {
-            float fg[16], fy[16];
-            ld_nc_v8(gz + 2 * (base + v), a, b);
-            unpack16(a, b, fg);
-            ld_nc_v8(y + 2 * (base + v), a, b);
-            unpack16(a, b, fy);
-            if (RELU == 1) {
-                float fz[16];
-                ld_nc_v8(z + 2 * (base + v), a, b);
-                unpack16(a, b, fz);
+    constexpr int U = 2;
+    const int step = gridDim.x * BN_THREADS;
+    for (int v0 = blockIdx.x * BN_THREADS + threadIdx.x; v0 < planevec; v0 += step * U) {
+        uint4 qa[U], qb[U], ya[U], yb[U], za[U], zb[U];
+        bool rim[U];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) fg[i] = fz[i] > 0.f ? fg[i] : 0.f;
-            } else if (RELU == 2) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) fg[i] = fmaf(fy[i], sc[i], sh[i]) > 0.f ? fg[i] : 0.f;
+        for (int u = 0; u < U; ++u) {
+            const int v = v0 + u * step;
+            const int hp = v / rowvec;
+            const int wp = (v - hp * rowvec) / groups;
+            rim[u] = rim_plane || hp == 0 || hp >= g.H + 1 || wp == 0 || wp == g.W + 1;
+            if (!rim[u] && v < planevec) {
+                ld_nc_v8(gz + 2 * (base + v), qa[u], qb[u]);
+                ld_nc_v8(y + 2 * (base + v), ya[u], yb[u]);
+                if (RELU == 1) ld_nc_v8(z + 2 * (base + v), za[u], zb[u]);
             }
-            if (WRITE_GRES) pack16(fg, ga, gb);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) fy[i] = fmaf(ca[i], fg[i], fmaf(cb[i], fy[i], cc[i]));
-            pack16(fy, a, b);
         }
-        st_v8(dy + 2 * (base + v), a, b);
-        if (WRITE_GRES) st_v8(gres + 2 * (base + v), ga, gb);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int v = v0 + u * step;
+            if (v >= planevec) break;
+            uint4 a = make_uint4(0, 0, 0, 0), b = a, ga = a, gb = a;
+            if (!rim[u]) {
+                float fg[16], fy[16];
+                unpack16(qa[u], qb[u], fg);
+                unpack16(ya[u], yb[u], fy);
+                if (RELU == 1) {
+                    float fz[16];
+                    unpack16(za[u], zb[u], fz);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) fg[i] = fz[i] > 0.f ? fg[i] : 0.f;
+                } else if (RELU == 2) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) fg[i] = fmaf(fy[i], sc[i], sh[i]) > 0.f ? fg[i] : 0.f;
+                }
+                if (WRITE_GRES) pack16(fg, ga, gb);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) fy[i] = fmaf(ca[i], fg[i], fmaf(cb[i], fy[i], cc[i]));
+                pack16(fy, a, b);
+            }
+            st_v8(dy + 2 * (base + v), a, b);
+            if (WRITE_GRES) st_v8(gres + 2 * (base + v), ga, gb);
+        }
     }
 }
 

@@ -126,6 +126,15 @@ def main():
         g = torch.randn(B, C, H0, W0, device=dev)
         t2 = timeit(lambda i: torch.autograd.grad(WarpFunction.apply(s2, d2, row, col, 5e-5, False), (s2, d2), g))
         mem("imwrap bwd %s" % tag, 4.0 * B * (4 * C * H0 * W0 + 2 * H0 * W0), max(t2 - t, 1e-9))
+        # the same warp with a spatially smooth disparity field (what a network predicts): neighbouring pixels gather
+        # neighbouring source pixels; the U[0, 0.1 W) field above is per-pixel random, i.e. an incoherent gather
+        yy, xx = torch.meshgrid(torch.linspace(0, 1, H0, device=dev), torch.linspace(0, 1, W0, device=dev), indexing="ij")
+        smooth = ((0.05 + 0.04 * torch.sin(6.0 * xx + 3.0 * yy)) * W0).expand(B, 1, H0, W0).contiguous()
+        t = timeit(lambda i: WarpFunction.apply(src, smooth, row, col, 5e-5, False))
+        mem("imwrap fwd %s, smooth disparity" % tag, 4.0 * B * (2 * C * H0 * W0 + H0 * W0), t)
+        d3 = smooth.clone().requires_grad_()
+        t2 = timeit(lambda i: torch.autograd.grad(WarpFunction.apply(s2, d3, row, col, 5e-5, False), (s2, d3), g))
+        mem("imwrap bwd %s, smooth disparity" % tag, 4.0 * B * (4 * C * H0 * W0 + 2 * H0 * W0), max(t2 - t, 1e-9))
 
     # ---- op 3: the PSMNet 3-D conv layer types (App. C) -------------------------------------------
     def conv_case(name, cin, cout, D, H, W, stride, transposed, res):
