@@ -128,6 +128,30 @@ struct TileInfo {
     bool skip;
 };
 
+// Flat padded position -> (b, d', offset inside the plane).  The single-warp roles (TMA producer, MMA issuer) run
+// this once per tile on their critical path: 64-bit divisions (~120 dependent instructions each) made the bare
+// pipeline of the small-tile kernels cost >2000 cycles per tile, so positions that fit 32 bits use 32-bit divisions.
+struct FlatPos { int b, dp, off; };
+__device__ __forceinline__ FlatPos flat_decode(long long p, long long plane, long long vol) {
+    FlatPos f;
+    if (p < 0x7fffffffLL && vol < 0x7fffffffLL) {
+        const unsigned up = (unsigned)p, uv = (unsigned)vol, upl = (unsigned)plane;
+        const unsigned b = up / uv, rem = up - b * uv, dp = rem / upl;
+        f.b = (int)b; f.dp = (int)dp; f.off = (int)(rem - dp * upl);
+    } else {
+        const long long b = p / vol, rem = p - b * vol, dp = rem / plane;
+        f.b = (int)b; f.dp = (int)dp; f.off = (int)(rem - dp * plane);
+    }
+    return f;
+}
+// a 128-position tile that lies completely inside a rim plane (d' = 0 or D+1) reads only zeros and stores nothing
+__device__ __forceinline__ bool rim_tile(long long p0, long long P, long long plane, long long vol, int Dp) {
+    const FlatPos f = flat_decode(p0, plane, vol);
+    const long long span = (p0 + 127 < P ? 127 : P - 1 - p0);                    // the tail tile is cut at P
+    const bool one_plane = (long long)f.off + span < plane;
+    return one_plane && (f.dp == 0 || f.dp == Dp - 1);
+}
+
 template <int MODE>
 __device__ __forceinline__ TileInfo decode_tile(const ConvGeom& g, int t, long long plane, long long vol, int Dp) {
     TileInfo ti;
@@ -139,11 +163,7 @@ __device__ __forceinline__ TileInfo decode_tile(const ConvGeom& g, int t, long l
     } else {
         ti.cls = t / g.mtiles;
         ti.p0 = (long long)(t - ti.cls * g.mtiles) * 128;
-        // tiles that lie completely inside a rim plane (d' = 0 or D+1) produce nothing
-        const long long pl = min(ti.p0 + 127, g.P - 1);
-        const long long b0 = ti.p0 / vol, b1 = pl / vol;
-        const int dp0 = (int)((ti.p0 - b0 * vol) / plane), dp1 = (int)((pl - b1 * vol) / plane);
-        ti.skip = (b0 == b1 && dp0 == dp1 && (dp0 == 0 || dp0 == Dp - 1));
+        ti.skip = rim_tile(ti.p0, g.P, plane, vol, Dp);
     }
     return ti;
 }
@@ -290,10 +310,9 @@ conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
             } else {
                 const long long p = ti.p0 + r;
                 if (p < g.P) {
-                    const long long b = p / vol, rem = p - b * vol;
-                    const int dp = (int)(rem / plane);
-                    const int rem2 = (int)(rem - (long long)dp * plane);
-                    const int hp = rem2 / Wp, wp = rem2 - hp * Wp;
+                    const FlatPos fp = flat_decode(p, plane, vol);
+                    const int b = fp.b, dp = fp.dp, rem2 = fp.off;
+                    const int hp = (int)((unsigned)rem2 / (unsigned)Wp), wp = rem2 - hp * Wp;
                     if (dp >= 1 && dp <= g.Di && hp >= 1 && hp <= g.Hi && wp >= 1 && wp <= g.Wi) {
                         ob = (int)b;
                         if (g.transposed) {
@@ -761,9 +780,11 @@ struct DcGeom {
     short op_begin[6];       // MMAs of tile a are ops[op_begin[a] .. op_begin[a+1])
     DcOp ops[12];
     short w_dst[27], w_src[27];   // weight block -> first smem row, first packed-weight row
+    int dbg;                 // timing experiments only (variant bits 4..6): 1 = no epilogue global traffic, 2 = no TMA traffic, 4 = no MMAs
 };
 
 __constant__ const int kDcPosClass[8] = {0, 1, 3, 2, 6, 7, 5, 4};   // accumulator block -> parity class (pd<<2|ph<<1|pw)
+__constant__ const int kDcClassPos[8] = {0, 1, 3, 2, 7, 6, 4, 5};   // parity class -> accumulator block
 
 template <int KC, int NP>
 struct DcCfg {
@@ -786,10 +807,7 @@ struct DcCfg {
 
 // tiles that lie completely inside a rim plane (d' = 0 or D+1) read only zeros and store nothing
 __device__ __forceinline__ bool dc_skip(long long p0, long long P, long long plane, long long vol, int Dp) {
-    const long long pl = min(p0 + 127, P - 1);
-    const long long b0 = p0 / vol, b1 = pl / vol;
-    const int dp0 = (int)((p0 - b0 * vol) / plane), dp1 = (int)((pl - b1 * vol) / plane);
-    return b0 == b1 && dp0 == dp1 && (dp0 == 0 || dp0 == Dp - 1);
+    return rim_tile(p0, P, plane, vol, Dp);
 }
 
 template <int KC, int NP>
@@ -829,7 +847,7 @@ conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         ptx::prefetch_tensormap(&map_w);
         ptx::prefetch_tensormap(&map_a);
         for (int s = 0; s < C::STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; ++a) { ptx::mbar_init(tfull_bar(a), 1); ptx::mbar_init(tempty_bar(a), 16); }
+        for (int a = 0; a < 2; ++a) { ptx::mbar_init(tfull_bar(a), 1); ptx::mbar_init(tempty_bar(a), g.y_f32 ? 4 : 16); }
         ptx::mbar_init(wfull_bar, 1);
         ptx::fence_mbar_init();
     }
@@ -857,8 +875,12 @@ conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int a = 0; a < 4; ++a) {                        // (od, oh) = (a>>1, a&1)
                 wait_bar(empty_bar(s), ph ^ 1u);
                 if (ptx::elect_one_sync()) {
-                    ptx::mbar_arrive_expect_tx(full_bar(s), C::TX_BYTES);
-                    ptx::tma_load_2d(ring + s * C::A_BYTES, &map_a, full_bar(s), 0, (int)(p0 + ((a >> 1) * Hp + (a & 1)) * Wp));
+                    if (g.dbg & 2) {
+                        ptx::mbar_arrive(full_bar(s));
+                    } else {
+                        ptx::mbar_arrive_expect_tx(full_bar(s), C::TX_BYTES);
+                        ptx::tma_load_2d(ring + s * C::A_BYTES, &map_a, full_bar(s), 0, (int)(p0 + ((a >> 1) * Hp + (a & 1)) * Wp));
+                    }
                 }
                 __syncwarp();
                 if (++s == C::STAGES) { s = 0; ph ^= 1u; }
@@ -890,7 +912,7 @@ conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 ptx::tc_fence_after();
                 if (ptx::elect_one_sync()) {
                     const uint32_t a_lo0 = ring_lo + (uint32_t)s * (C::A_BYTES >> 4);
-                    for (int op = g.op_begin[a]; op < g.op_begin[a + 1]; ++op) {
+                    for (int op = g.op_begin[a]; op < g.op_begin[a + 1] && !(g.dbg & 4); ++op) {
                         const DcOp o = g.ops[op];
                         const uint32_t a_lo = a_lo0 + (uint32_t)((o.ow * C::ROWB) >> 4);
                         const uint32_t b_lo = w_lo + (uint32_t)((o.brow * C::ROWB) >> 4);
@@ -915,6 +937,63 @@ conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int half = (warp - 2) >> 2;                       // 0..3: owns accumulator blocks 2*half, 2*half+1
         const int r = q * 32 + lane;
         constexpr int NV = NP / 8;
+        if (g.y_f32) {
+            // Single output channel (GC-Net l37), fp32 [B][Do][Ho][Wo]: a tile carries 8 floats per voxel, so the
+            // per-tile coordinate arithmetic is the cost — ONE warp per lane quadrant does it (the other twelve
+            // would only repeat it), reads the 8 class columns and writes the (pw = 0, 1) pairs as 8-byte stores
+            // that are contiguous across the warp.
+            if (half == 0) {
+                int tcount = 0;
+                const bool pair_ok = (g.Wo & 1) == 0;
+                for (int t = blockIdx.x; t < g.ntiles; t += gridDim.x) {
+                    const long long p0 = (long long)t * 128;
+                    if (dc_skip(p0, g.P, plane, vol, Dp)) continue;
+                    const long long p = p0 + r;
+                    bool interior = false;
+                    int ob = 0, dz = 0, hy = 0, wx = 0;
+                    if (p < g.P) {
+                        const FlatPos fp = flat_decode(p, plane, vol);
+                        const int dp = fp.dp, rem2 = fp.off;
+                        ob = fp.b;
+                        const int hp = (int)((unsigned)rem2 / (unsigned)Wp), wp = rem2 - hp * Wp;
+                        interior = dp >= 1 && dp <= g.D && hp >= 1 && hp <= g.H && wp >= 1 && wp <= g.W && !(g.dbg & 1);
+                        dz = 2 * (dp - 1); hy = 2 * (hp - 1); wx = 2 * (wp - 1);
+                    }
+                    const int acc = tcount & 1;
+                    const uint32_t acc_ph = (uint32_t)(tcount >> 1) & 1u;
+                    ++tcount;
+                    const uint32_t taddr0 = tmem + ((uint32_t)(q * 32) << 16) + acc * C::ACC_COLS;
+                    wait_bar(tfull_bar(acc), acc_ph);
+                    __syncwarp();
+                    ptx::tc_fence_after();
+                    uint32_t v[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) v[c] = ptx::tmem_ld1(taddr0 + kDcClassPos[c] * NP);     // v[c] = class c, channel 0
+                    ptx::tc_wait_ld();
+                    consume_tmem_load(v[0], scratch_smem);
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+                    if (!interior) continue;
+                    const float sc0 = s_scale[0], sh0 = s_shift[0];
+                    const float* resf = reinterpret_cast<const float*>(residual);
+                    float* yf = reinterpret_cast<float*>(y);
+#pragma unroll
+                    for (int c2 = 0; c2 < 4; ++c2) {             // (pd, ph) = (c2 >> 1, c2 & 1)
+                        const int od = dz + (c2 >> 1), oh = hy + (c2 & 1);
+                        if (od >= g.Do || oh >= g.Ho || wx >= g.Wo) continue;
+                        const size_t o = (((size_t)ob * g.Do + od) * g.Ho + oh) * g.Wo + wx;
+                        const bool two = wx + 1 < g.Wo;
+                        float r0 = 0.f, r1 = 0.f;
+                        if (resf) { r0 = __ldg(resf + o); if (two) r1 = __ldg(resf + o + 1); }
+                        const float a0 = fuse_act(fmaf(__uint_as_float(v[2 * c2]), sc0, sh0), r0, g.relu);
+                        const float a1 = fuse_act(fmaf(__uint_as_float(v[2 * c2 + 1]), sc0, sh0), r1, g.relu);
+                        if (two && pair_ok) *reinterpret_cast<float2*>(yf + o) = make_float2(a0, a1);
+                        else { yf[o] = a0; if (two) yf[o + 1] = a1; }
+                    }
+                }
+            }
+        } else {
         const float4* sc4 = reinterpret_cast<const float4*>(s_scale);
         const float4* sh4 = reinterpret_cast<const float4*>(s_shift);
         int tcount = 0;
@@ -925,12 +1004,11 @@ conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             bool interior = false;
             int ob = 0, dz = 0, hy = 0, wx = 0;
             if (p < g.P) {
-                const long long b = p / vol, rem = p - b * vol;
-                const int dp = (int)(rem / plane);
-                const int rem2 = (int)(rem - (long long)dp * plane);
-                const int hp = rem2 / Wp, wp = rem2 - hp * Wp;
+                const FlatPos fp = flat_decode(p, plane, vol);
+                const int dp = fp.dp, rem2 = fp.off;
+                const int hp = (int)((unsigned)rem2 / (unsigned)Wp), wp = rem2 - hp * Wp;
                 interior = dp >= 1 && dp <= g.D && hp >= 1 && hp <= g.H && wp >= 1 && wp <= g.W;
-                ob = (int)b; dz = 2 * (dp - 1); hy = 2 * (hp - 1); wx = 2 * (wp - 1);
+                ob = fp.b; dz = 2 * (dp - 1); hy = 2 * (hp - 1); wx = 2 * (wp - 1);
             }
             const int acc = tcount & 1;
             const uint32_t acc_ph = (uint32_t)(tcount >> 1) & 1u;
@@ -941,7 +1019,7 @@ conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int jj = 0; jj < 2; ++jj) {
                 const int c = kDcPosClass[2 * half + jj];
                 const int od = dz + ((c >> 2) & 1), oh = hy + ((c >> 1) & 1), ow = wx + (c & 1);
-                valid[jj] = interior && od < g.Do && oh < g.Ho && ow < g.Wo;
+                valid[jj] = interior && od < g.Do && oh < g.Ho && ow < g.Wo && !(g.dbg & 1);
                 off[jj] = g.y_f32 ? (((size_t)ob * g.Do + od) * g.Ho + oh) * g.Wo + ow
                                   : ((((size_t)ob * (g.Do + 2) + od + 1) * (g.Ho + 2) + oh + 1) * (g.Wo + 2) + ow + 1) * (size_t)g.Cout;
             }
@@ -950,26 +1028,7 @@ conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
             };
-            if (g.y_f32) {
-                float rf[2];
-#pragma unroll
-                for (int jj = 0; jj < 2; ++jj)
-                    rf[jj] = (residual && valid[jj]) ? __ldg(reinterpret_cast<const float*>(residual) + off[jj]) : 0.f;
-                wait_bar(tfull_bar(acc), acc_ph);
-                __syncwarp();
-                ptx::tc_fence_after();
-#pragma unroll
-                for (int jj = 0; jj < 2; ++jj) {
-                    uint32_t v[16];
-                    ptx::tmem_ld16(taddr0 + (2 * half + jj) * NP, v);
-                    ptx::tc_wait_ld();
-                    consume_tmem_load(v[0], scratch_smem);
-                    if (jj == 1) release();
-                    if (valid[jj]) {
-                        reinterpret_cast<float*>(y)[off[jj]] = fuse_act(fmaf(__uint_as_float(v[0]), s_scale[0], s_shift[0]), rf[jj], g.relu);
-                    }
-                }
-            } else {
+            {
                 const __nv_bfloat16* resb = reinterpret_cast<const __nv_bfloat16*>(residual);
                 uint4 rv[2][NV];
 #pragma unroll
@@ -1016,6 +1075,7 @@ conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 }
             }
         }
+        }   // bf16 output
     }
 
     ptx::tc_fence_before();
@@ -1197,6 +1257,7 @@ int conv3d_dispatch(const void* x, const void* w, const float* scale, const floa
         dg.B = B; dg.D = D; dg.H = H; dg.W = W; dg.Do = Do; dg.Ho = Ho; dg.Wo = Wo;
         dg.Cout = Cout; dg.relu = relu; dg.y_f32 = (y_dtype == DSM_F32);
         dg.P = P; dg.ntiles = (int)dsm_ceil_div_ll(P, 128);
+        dg.dbg = (variant >> 4) & 7;
         build_dc_schedule(dg, NP);
         cudaStream_t st = (cudaStream_t)stream;
         if (KC == 32 && NP == 16) return launch_dc<32, 16>(map_a, maps.w, dg, scale, shift, residual, y, st);

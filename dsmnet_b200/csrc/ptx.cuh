@@ -139,6 +139,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
         : "r"(taddr));
 }
 
+// one column: thread i of the warp gets lane (32*(warp%4)+i)
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+    uint32_t v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr));
+    return v;
+}
+
 // zero 32 lanes x 32 consecutive columns (the accumulator block this warp just drained)
 __device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
     const uint32_t z = 0u;

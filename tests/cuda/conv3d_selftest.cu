@@ -282,6 +282,15 @@ int main(int argc, char** argv) {
         Case c2 = {1, 32, 32, 48, 96, 312, 1, 0, 1, 1, 1, 0, 32, "32->32 dbg32 (no TMA)"};
         run_case(c2, true, 10);
     }
+    if (!strcmp(what, "dbgdc")) {
+        // timing experiments on the class-sharing transposed-conv kernel (results are garbage for v != 0)
+        for (int v : {0, 16, 32, 64, 48, 80, 96, 112}) {
+            Case c = {1, 64, 32, 24, 48, 156, 2, 1, 0, 1, 1, 0, v, "conv6 deconv 64->32 dbg"};
+            run_case(c, true, 10);
+            Case c2 = {1, 32, 1, 96, 128, 256, 2, 1, 0, 0, 0, 1, v, "l37 deconv 32->1 dbg"};
+            run_case(c2, true, 5);
+        }
+    }
     if (!strcmp(what, "dbg")) {
         // timing experiments on the plane-sharing kernel (results are garbage): which part of the pipeline bounds it?
         for (int v : {0, 16, 32, 64, 48, 80, 96, 112}) {
