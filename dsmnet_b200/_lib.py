@@ -50,6 +50,7 @@ SIGNATURES = {
     "dsm_debug_conv_timeouts": [],
     "dsm_debug_wgrad_mode": [_I],
     "dsm_debug_wgrad_timeouts": [],
+    "dsm_pack_weight": [_P, _P, _I, _I, _I, _P],
     "dsm_pack_ndhwc": [_P, _P, _I, _I, _I, _I, _I, _P],
     "dsm_unpack_ndhwc": [_P, _P, _I, _I, _I, _I, _I, _P],
     "dsm_softargmin_fwd": [_P, _P, _I, _I, _I, _I, _F, _P],

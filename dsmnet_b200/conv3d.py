@@ -34,6 +34,21 @@ def pack_weight(weight: torch.Tensor, transposed: bool) -> torch.Tensor:
     return w.to(torch.bfloat16).contiguous()
 
 
+def pack_weight_device(weight: torch.Tensor, mode: int) -> torch.Tensor:
+    """One-launch repack of a CUDA fp32 weight (dsm_pack_weight): mode 0 Conv3d [Cout,Cin,3,3,3], 1 ConvTranspose3d
+    [Cin,Cout,3,3,3], 2 the stride-1 dgrad filter of a Conv3d weight [Cout,Cin,...] -> a conv with Cin outputs."""
+    w = weight.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    if mode == 0:
+        cout, cin = w.shape[0], w.shape[1]
+    else:
+        cout, cin = w.shape[1], w.shape[0]
+    out = torch.empty(27, max(16, cout), cin, device=w.device, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().dsm_pack_weight(w.data_ptr(), out.data_ptr(), cout, cin, mode, _lib.stream_ptr(w.device)), "dsm_pack_weight")
+    return out
+
+
 def fold_affine(cout: int, bn=None, bias: Optional[torch.Tensor] = None, eps: float = BN_EPS):
     """Eval-mode BatchNorm3d (+ conv bias) -> per-channel (scale, shift), fp32, padded to CoutP.
     scale = gamma/sqrt(var+eps); shift = beta - mean*scale + bias*scale."""
@@ -64,16 +79,24 @@ def conv_out_dims(D, H, W, stride, transposed):
 class FusedConv3d:
     """One fused layer with device-resident packed weights."""
 
-    def __init__(self, weight, bn=None, bias=None, stride=1, transposed=False, relu=False, device=None, variant=0):
+    def __init__(self, weight, bn=None, bias=None, stride=1, transposed=False, relu=False, device=None, variant=0, dgrad_flip=False):
         # relu: False/0 none, True/1 after the residual add (PSMNet), 2 before it (GC-Net skip adds)
+        # dgrad_flip: `weight` is a Conv3d weight [Cout,Cin,...] and this layer is its stride-1 input-gradient
+        # convolution (Cout inputs -> Cin outputs, flipped taps)
         self.transposed, self.stride, self.relu = bool(transposed), int(stride), int(relu)
-        if self.transposed:
+        if self.transposed or dgrad_flip:
             self.cin, self.cout = weight.shape[0], weight.shape[1]
-            self.stride = 2
+            if self.transposed:
+                self.stride = 2
         else:
             self.cout, self.cin = weight.shape[0], weight.shape[1]
         device = device if device is not None else weight.device
-        self.w = pack_weight(weight, self.transposed).to(device)
+        if weight.is_cuda and torch.device(device) == weight.device:
+            self.w = pack_weight_device(weight, 2 if dgrad_flip else (1 if self.transposed else 0))
+        elif dgrad_flip:
+            self.w = pack_weight(weight.detach().flip(2, 3, 4).transpose(0, 1).contiguous(), False).to(device)
+        else:
+            self.w = pack_weight(weight, self.transposed).to(device)
         self.identity_affine = bn is None and bias is None
         if self.identity_affine:            # the kernels take NULL for scale/shift: nothing to build or copy
             self.scale = self.shift = None
@@ -151,7 +174,7 @@ def _dgrad_layer(weight: torch.Tensor, stride: int, transposed: bool, device) ->
     if transposed:                    # y = conv_transpose(x, w[Cin][Cout]): gx = conv3d(gy, w, stride 2), w read as [out=Cin][in=Cout]
         return FusedConv3d(w, None, None, 2, False, 0, device)
     if stride == 1:                   # gx = conv3d(gy, w'), w'[ci][co][k] = w[co][ci][2-k]
-        return FusedConv3d(w.flip(2, 3, 4).transpose(0, 1).contiguous(), None, None, 1, False, 0, device)
+        return FusedConv3d(w, None, None, 1, False, 0, device, dgrad_flip=True)
     # stride 2: gx = conv_transpose3d(gy, w) cropped to x's extent; w[Cout][Cin] is a ConvTranspose weight with in=Cout
     return FusedConv3d(w, None, None, 2, True, 0, device)
 

@@ -353,6 +353,35 @@ extern "C" int dsm_concat_volume_bwd(const void* gout, float* gL, float* gR,
     return dsm_launch_status();
 }
 
+// Filter repacking: PyTorch fp32 weights -> the kernels' bf16 [27][CoutP][Cin] (tap-major, K-major rows), one launch.
+//   mode 0: w is [Cout][Cin][27]  (nn.Conv3d)                      out[t][co][ci] = w[co][ci][t]
+//   mode 1: w is [Cin][Cout][27]  (nn.ConvTranspose3d)             out[t][co][ci] = w[ci][co][t]
+//   mode 2: w is [Cin][Cout][27] read as the stride-1 dgrad filter out[t][co][ci] = w[ci][co][26-t]   (flipped taps)
+// Rows co >= Cout (CoutP = max(16, Cout)) are zero.
+__global__ void __launch_bounds__(256)
+pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int CoutP, int Cin, int mode) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = 27 * CoutP * Cin;
+    if (i >= n) return;
+    const int ci = i % Cin; int r = i / Cin;
+    const int co = r % CoutP; const int t = r / CoutP;
+    float v = 0.f;
+    if (co < Cout) {
+        if (mode == 0) v = w[((size_t)co * Cin + ci) * 27 + t];
+        else v = w[((size_t)ci * Cout + co) * 27 + (mode == 2 ? 26 - t : t)];
+    }
+    out[i] = __float2bfloat16_rn(v);
+}
+
+extern "C" int dsm_pack_weight(const float* w, void* out, int Cout, int Cin, int mode, void* stream) {
+    if (!w || !out || Cout < 1 || Cin < 1 || mode < 0 || mode > 2) return DSM_EINVAL;
+    const int CoutP = Cout < 16 ? 16 : Cout;
+    const long long n = 27LL * CoutP * Cin;
+    if (n > 0x7fffffffLL) return DSM_EUNSUPPORTED;
+    pack_weight_kernel<<<(unsigned)dsm_ceil_div_ll(n, 256), 256, 0, (cudaStream_t)stream>>>(w, static_cast<__nv_bfloat16*>(out), Cout, CoutP, Cin, mode);
+    return dsm_launch_status();
+}
+
 extern "C" int dsm_pack_ndhwc(const float* x, void* y, int B, int C, int D, int H, int W, void* stream) {
     if (!x || !y || B <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0) return DSM_EINVAL;
     if (C % 8 != 0 || D + 2 > 65535 || B > 65535) return DSM_EUNSUPPORTED;

@@ -159,6 +159,10 @@ int dsm_debug_wgrad_mode(int mode);
 int dsm_debug_wgrad_timeouts(void);
 
 /* layout converters at the reference boundary (NCDHW fp32 <-> padded NDHWC bf16)             */
+/* filter repacking fp32 -> bf16 [27][CoutP][Cin] (CoutP = max(16, Cout), extra rows zero), w has 27 taps innermost:
+ * mode 0: w[Cout][Cin][27] (nn.Conv3d); mode 1: w[Cin][Cout][27] (nn.ConvTranspose3d);
+ * mode 2: w[Cin][Cout][27] with flipped taps (the stride-1 dgrad filter: pass the Conv3d weight, Cout/Cin exchanged) */
+int dsm_pack_weight(const float* w, void* w_packed_bf16, int Cout, int Cin, int mode, void* stream);
 int dsm_pack_ndhwc(const float* x_ncdhw, void* y_padded_bf16, int B, int C, int D, int H, int W, void* stream);
 int dsm_unpack_ndhwc(const void* x_padded_bf16, float* y_ncdhw, int B, int C, int D, int H, int W, void* stream);
 

@@ -298,6 +298,8 @@ int main(int argc, char** argv) {
             run_case(c, true, 10);
             Case c2 = {1, 64, 32, 48, 96, 312, 1, 0, 1, 0, 1, 0, v, "64->32 dbg"};
             run_case(c2, true, 10);
+            Case c3 = {1, 32, 1, 48, 96, 312, 1, 0, 0, 1, 0, 1, v, "classif 32->1 dbg"};
+            run_case(c3, true, 10);
         }
     }
     printf("SELFTEST %s: %d failing case(s), timeouts=%d\n", what, fails, dsm_debug_conv_timeouts());
