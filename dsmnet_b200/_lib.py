@@ -37,6 +37,7 @@ SIGNATURES = {
     "dsm_conv3d_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, c_size_t, _P],
     "dsm_conv3d_fwd_ex": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "dsm_conv3d_wgrad_workspace_bytes": [_I, _I],
+    "dsm_conv3d_wgrad_workspace_bytes_ex": [_I, _I, _I, _I, _I, _I, _I],
     "dsm_conv3d_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, c_size_t, _P],
     "dsm_zero_rim": [_P, _I, _I, _I, _I, _I, _P],
     "dsm_bn_stats": [_P, _I, _I, _I, _I, _I, _P, _P],
@@ -89,7 +90,7 @@ def lib() -> ctypes.CDLL:
     for name, argtypes in SIGNATURES.items():
         fn = getattr(L, name)          # AttributeError here == ABI mismatch; let it surface
         fn.argtypes = argtypes
-        fn.restype = c_char_p if name == "dsm_strerror" else (c_size_t if name.endswith("_workspace_bytes") else c_int)
+        fn.restype = c_char_p if name == "dsm_strerror" else (c_size_t if (name.endswith("_workspace_bytes") or name.endswith("_workspace_bytes_ex")) else c_int)
     if L.dsm_abi_version() != 1:
         raise DsmError("ABI version mismatch")
     _lib = L

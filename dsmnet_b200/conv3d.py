@@ -180,14 +180,17 @@ def _dgrad_layer(weight: torch.Tensor, stride: int, transposed: bool, device) ->
 
 
 _wgrad_ws = {}
+_wgrad_ws_retired = []
 
 
-def _wgrad_workspace(ca: int, cb: int, device) -> torch.Tensor:
-    key = (ca, cb, str(device))
+def _wgrad_workspace(nbytes: int, device) -> torch.Tensor:
+    """One growing scratch buffer per device (partials; for stride-2 layers also the parity-gathered fine tensor)."""
+    key = str(device)
     ws = _wgrad_ws.get(key)
-    if ws is None:
-        n = _lib.lib().dsm_conv3d_wgrad_workspace_bytes(ca, cb)
-        ws = torch.empty(n // 4, device=device, dtype=torch.float32)
+    if ws is None or ws.numel() * 4 < nbytes:
+        if ws is not None:
+            _wgrad_ws_retired.append(ws)          # a captured CUDA graph may still point into it
+        ws = torch.empty((nbytes + 3) // 4, device=device, dtype=torch.float32)
         _wgrad_ws[key] = ws
     return ws
 
@@ -196,8 +199,9 @@ def conv3d_wgrad(anchor: PaddedVolume, partner: PaddedVolume, stride: int, ca_ou
     """dW[ca_out][cb_out][3][3][3] (fp32) from the padded volumes; see dsm_conv3d_wgrad for anchor/partner."""
     dev = anchor.data.device
     dw = torch.empty(ca_out, cb_out, 3, 3, 3, device=dev, dtype=torch.float32)
-    ws = _wgrad_workspace(anchor.C, partner.C, dev)
-    _lib.check(_lib.lib().dsm_conv3d_wgrad(
+    L = _lib.lib()
+    ws = _wgrad_workspace(L.dsm_conv3d_wgrad_workspace_bytes_ex(anchor.B, anchor.C, partner.C, anchor.D, anchor.H, anchor.W, stride), dev)
+    _lib.check(L.dsm_conv3d_wgrad(
         anchor.data.data_ptr(), partner.data.data_ptr(), dw.data_ptr(), anchor.B, anchor.C, partner.C,
         anchor.D, anchor.H, anchor.W, partner.D, partner.H, partner.W, stride, ca_out, cb_out, 0, 0, 0,
         ws.data_ptr(), ws.numel() * 4, _lib.stream_ptr(dev)), "dsm_conv3d_wgrad")

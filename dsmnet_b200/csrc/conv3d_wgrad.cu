@@ -210,7 +210,10 @@ struct Geom {
     int D, BD;                                   // interior planes per batch item; B * D
     int Wq;                                      // padded row pitch (voxels)
     int nsteps;                                  // nchunks * BD
-    int a0, b0_unused;
+    int cls_blocks;                              // 0: plain stride-1 problem.  > 0: the partner is the parity-gathered fine tensor of a
+                                                 // stride-2 layer (8 classes x cls_blocks 32-channel blocks): class bit = 1 on an axis needs
+                                                 // only the centre tap there, bit = 0 the centre and the +1 tap (see s2d_gather_kernel)
+    int pad_;
 };
 
 __device__ unsigned int g_wgrad_timeouts = 0;
@@ -265,6 +268,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int z = blockIdx.y;
     const int ca0 = (z / nslice_b) * 32, cb0 = (z % nslice_b) * 32;
     const long long t0 = (long long)g.nsteps * blockIdx.x / gridDim.x, t1 = (long long)g.nsteps * (blockIdx.x + 1) / gridDim.x;
+    // tap ranges this channel block needs (all 27 for a stride-1 problem)
+    int kd_lo = 0, kd_hi = 2, kh_lo = 0, kh_hi = 2, kw_lo = 0, kw_hi = 2;
+    if (g.cls_blocks > 0) {
+        const int cls = (z % nslice_b) / g.cls_blocks;           // (pd << 2) | (ph << 1) | pw
+        kd_lo = kh_lo = kw_lo = 1;
+        kd_hi = (cls & 4) ? 1 : 2; kh_hi = (cls & 2) ? 1 : 2; kw_hi = (cls & 1) ? 1 : 2;
+    }
 
     if (warp == 0) {
         if (ptx::elect_one_sync()) {
@@ -299,7 +309,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         __syncwarp();
     } else if (warp == 1) {
         if (ptx::elect_one_sync()) {
-            constexpr uint32_t idesc = ptx::make_idesc_bf16(96) | (1u << 15) | (1u << 16);     // both operands MN-major
+            const uint32_t idesc_n = ptx::make_idesc_bf16(32 * (kh_hi - kh_lo + 1)) | (1u << 15) | (1u << 16);     // both operands MN-major
             uint32_t xn = 0, an = 0;
             bool ok = true, first = true;
             for (long long t = t0; t < t1 && ok;) {
@@ -317,12 +327,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     const uint64_t ad0 = mn_desc_sw64(sA + sa * A_SLOT, 64u);
 #pragma unroll
                     for (int kd = 0; kd < 3; ++kd) {
+                        if (kd < kd_lo || kd > kd_hi) continue;
                         const uint32_t sb = (xn + i + kd) % NB;
-                        const uint64_t bd0 = mn_desc_sw64(sB + sb * B_SLOT, B_COPY);
+                        const uint64_t bd0 = mn_desc_sw64(sB + sb * B_SLOT + kh_lo * B_COPY, B_COPY);
 #pragma unroll
                         for (int ks = 0; ks < KB / 16; ++ks)
-                            ptx::umma_bf16(tmem + kd * 96, ptx::desc_advance(ad0, ks * 1024), ptx::desc_advance(bd0, ks * 1024),
-                                           idesc, (first && ks == 0) ? 0u : 1u);
+                            ptx::umma_bf16(tmem + kd * 96 + kh_lo * 32, ptx::desc_advance(ad0, ks * 1024), ptx::desc_advance(bd0, ks * 1024),
+                                           idesc_n, (first && ks == 0) ? 0u : 1u);
                     }
                     first = false;
                     ptx::umma_commit(empty_a(sa));
@@ -352,6 +363,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 uint32_t v[32];
                 ptx::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + kd * 96 + kh * 32, v);
                 ptx::tc_wait_ld();
+                if (kd < kd_lo || kd > kd_hi || kh < kh_lo || kh > kh_hi || kw < kw_lo || kw > kw_hi) {   // tap not computed for this class
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = 0u;
+                }
                 float4* o = reinterpret_cast<float4*>(out + ((size_t)((kd * 3 + kh) * 3 + kw) * 32 + lane) * 32);
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
@@ -365,6 +380,54 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 }
 
 }  // namespace tc
+
+// Parity gather for the stride-2 layers.  With anchor voxel v and tap t the partner voxel is (padded) f = 2v + t per axis:
+// f even -> t = 0 (coarse offset 0) or t = 2 (offset +1), f odd -> t = 1 (offset 0).  Q holds the eight parity classes of the
+// fine tensor as channel blocks of a volume in the ANCHOR's padded geometry,
+//     Q[b][u'][pi*Cb + c] = P[b][2(u'-1) + pi][c]   (per axis; zero where the fine index leaves the padded extent, and at u' = 0),
+// so that class pi is a stride-1 weight-gradient problem against the anchor with coarse offsets {0, +1} — taps k = 1, 2 of the
+// tcgen05 kernel; k = 2 only exists on axes with pi = 0.  One thread per 16-byte chunk of Q.
+__global__ void __launch_bounds__(256)
+s2d_gather_kernel(const uint4* __restrict__ P, uint4* __restrict__ Q, int B, int Cb8, int Da, int Ha, int Wa, int Dp, int Hp, int Wp) {
+    const long long n = (long long)B * (Da + 2) * (Ha + 2) * (Wa + 2) * 8 * Cb8;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = (int)(i % Cb8); long long r = i / Cb8;
+    const int cls = (int)(r % 8); r /= 8;
+    const int uw = (int)(r % (Wa + 2)); r /= (Wa + 2);
+    const int uh = (int)(r % (Ha + 2)); r /= (Ha + 2);
+    const int ud = (int)(r % (Da + 2)); const int b = (int)(r / (Da + 2));
+    const int fd = 2 * (ud - 1) + ((cls >> 2) & 1), fh = 2 * (uh - 1) + ((cls >> 1) & 1), fw = 2 * (uw - 1) + (cls & 1);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (ud >= 1 && uh >= 1 && uw >= 1 && fd <= Dp + 1 && fh <= Hp + 1 && fw <= Wp + 1)
+        v = __ldg(P + ((((size_t)b * (Dp + 2) + fd) * (Hp + 2) + fh) * (Wp + 2) + fw) * Cb8 + c);
+    Q[i] = v;
+}
+
+// Reduction for the gathered form: partial is [a-block][class*nb + b-block][cta][27][32][32] over (kd,kh,kw) in {0,1,2};
+// original tap t per axis <- (class bit, k): t = 0 <- (0, 1), t = 1 <- (1, 1), t = 2 <- (0, 2).
+__global__ void __launch_bounds__(256)
+wgrad_reduce_s2_kernel(const float* __restrict__ partial, float* __restrict__ dw, int ncta, int Ca, int Cb, int CAo, int CBo,
+                       const float* __restrict__ scale_a, const float* __restrict__ scale_b, int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 27 * Ca * Cb) return;
+    const int b = i % Cb; int r = i / Cb;
+    const int a = r % Ca; const int tap = r / Ca;
+    const int td = tap / 9, th = (tap / 3) % 3, tw = tap % 3;
+    const int cls = ((td == 1) << 2) | ((th == 1) << 1) | (tw == 1);
+    const int k = ((td == 2 ? 2 : 1) * 3 + (th == 2 ? 2 : 1)) * 3 + (tw == 2 ? 2 : 1);
+    const int nb = Cb / 32;
+    const int z = (a / 32) * (8 * nb) + cls * nb + (b / 32);
+    const size_t per_cta = (size_t)27 * 32 * 32;
+    const float* p = partial + ((size_t)z * ncta) * per_cta + ((size_t)k * 32 + (a % 32)) * 32 + (b % 32);
+    float sum = 0.f;
+    for (int c = 0; c < ncta; ++c) sum += p[(size_t)c * per_cta];
+    if (a >= CAo || b >= CBo) return;
+    if (scale_a) sum *= scale_a[a];
+    if (scale_b) sum *= scale_b[b];
+    float* o = dw + ((size_t)a * CBo + b) * 27 + tap;
+    *o = accumulate ? *o + sum : sum;
+}
 
 // dW[a][b][tap] = scale_a[a] * scale_b[b] * sum_cta partial[slice][kd group][cta][tap][a][b]   (fixed summation order)
 __global__ void __launch_bounds__(256)
@@ -410,7 +473,7 @@ int g_wgrad_mode = 0;          // 0 = tcgen05 kernel where it applies, 1 = warp-
 
 // stride-1 path: returns DSM_EUNSUPPORTED (negative) when the shape does not fit the tcgen05 kernel
 int launch_wgrad_tc(const void* anchor, const void* partner, float* partial, int B, int Ca, int Cb, int D, int H, int W,
-                    int* ncta_out, cudaStream_t st) {
+                    int* ncta_out, cudaStream_t st, int cls_blocks = 0) {
     const long long HpWp = (long long)(H + 2) * (W + 2);
     const long long planes = (long long)B * (D + 2);
     if (HpWp > 0x7fffffffLL - 4096 || planes > 0x7fffffffLL) return DSM_EUNSUPPORTED;
@@ -441,13 +504,32 @@ int launch_wgrad_tc(const void* anchor, const void* partner, float* partial, int
         attr_set = true;
     }
     tc::Geom g;
-    g.D = D; g.BD = B * D; g.Wq = W + 2; g.nsteps = (int)nsteps; g.a0 = 0; g.b0_unused = 0;
+    g.D = D; g.BD = B * D; g.Wq = W + 2; g.nsteps = (int)nsteps; g.cls_blocks = cls_blocks; g.pad_ = 0;
     tc::wgrad_tc_kernel<<<dim3(ncta, nslices), 128, tc::SMEM, st>>>(ma, mb, partial, g, Cb / 32);
     *ncta_out = ncta;
     return dsm_launch_status();
 }
 
+// bytes of the parity-gathered partner of a stride-2 problem (anchor geometry, 8*Cb channels)
+size_t s2_gather_bytes(int B, int Cb, int Da, int Ha, int Wa) {
+    return (size_t)B * (Da + 2) * (Ha + 2) * (Wa + 2) * 8 * (size_t)Cb * sizeof(__nv_bfloat16);
+}
+size_t s2_partial_bytes(int Ca, int Cb) {
+    return (size_t)DSM_NUM_SMS_B200 * 27 * 32 * 32 * sizeof(float) + (size_t)(Ca / 32) * (Cb / 32) * 8 * 27 * 32 * 32 * sizeof(float);
+}
+
 }  // namespace
+
+// workspace for a given problem: the stride-2 / transposed layers can use the tcgen05 kernel through a parity gather of the
+// fine tensor when the caller provides room for it (otherwise they run on the warp-level kernel)
+extern "C" size_t dsm_conv3d_wgrad_workspace_bytes_ex(int B, int Ca, int Cb, int Da, int Ha, int Wa, int stride) {
+    size_t n = (size_t)DSM_NUM_SMS_B200 * 2 * 27 * (size_t)Ca * Cb * sizeof(float);
+    if (stride == 2 && Ca % 32 == 0 && Cb % 32 == 0) {
+        const size_t m = ((s2_partial_bytes(Ca, Cb) + 1023) / 1024) * 1024 + s2_gather_bytes(B, Cb, Da, Ha, Wa);
+        if (m > n) n = m;
+    }
+    return n;
+}
 
 extern "C" size_t dsm_conv3d_wgrad_workspace_bytes(int Ca, int Cb) {
     return (size_t)DSM_NUM_SMS_B200 * 2 * 27 * (size_t)Ca * Cb * sizeof(float);      // one partial per CTA (<= #SMs), 2x margin
@@ -481,6 +563,26 @@ extern "C" int dsm_conv3d_wgrad(const void* anchor, const void* partner, float* 
             const int per_tc = 27 * Ca * Cb;
             wgrad_reduce_kernel<<<dsm_ceil_div(per_tc, 256), 256, 0, st>>>(partial, dw, 1, ncta_tc, Ca, Cb, 32, 32, Ca_out, Cb_out,
                                                                           scale_a, scale_b, accumulate);
+            return dsm_launch_status();
+        }
+    }
+    if (stride == 2 && g_wgrad_mode == 0 && Ca % 32 == 0 && Cb % 32 == 0 &&
+        ws_bytes >= dsm_conv3d_wgrad_workspace_bytes_ex(B, Ca, Cb, Da, Ha, Wa, 2) &&
+        (long long)B * (Da + 2) * (Ha + 2) * (Wa + 2) * 8 * (Cb / 8) < 0x7fffffffLL * 256LL) {
+        // parity gather of the fine tensor, then the tcgen05 kernel with 8 x (Cb/32) partner blocks and per-class tap masks
+        const size_t poff = ((s2_partial_bytes(Ca, Cb) + 1023) / 1024) * 1024;
+        void* q = static_cast<char*>(ws) + poff;
+        const long long nchunk = (long long)B * (Da + 2) * (Ha + 2) * (Wa + 2) * 8 * (Cb / 8);
+        s2d_gather_kernel<<<(unsigned)dsm_ceil_div_ll(nchunk, 256), 256, 0, st>>>(static_cast<const uint4*>(partner), static_cast<uint4*>(q),
+                                                                                 B, Cb / 8, Da, Ha, Wa, Dp, Hp, Wp);
+        int rc_g = dsm_launch_status();
+        if (rc_g != 0) return rc_g;
+        int ncta_tc = 0;
+        const int rc_tc = launch_wgrad_tc(anchor, q, partial, B, Ca, 8 * Cb, Da, Ha, Wa, &ncta_tc, st, Cb / 32);
+        if (rc_tc != DSM_EUNSUPPORTED) {
+            if (rc_tc != 0) return rc_tc;
+            const int per_tc = 27 * Ca * Cb;
+            wgrad_reduce_s2_kernel<<<dsm_ceil_div(per_tc, 256), 256, 0, st>>>(partial, dw, ncta_tc, Ca, Cb, Ca_out, Cb_out, scale_a, scale_b, accumulate);
             return dsm_launch_status();
         }
     }

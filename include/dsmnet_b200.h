@@ -108,6 +108,9 @@ int dsm_conv3d_fwd(const void* x, const void* w_packed, const float* scale, cons
  *   scale_a / scale_b : optional per-channel factors (the folded BatchNorm scale on the gy side), NULL = 1
  *   accumulate : 0 overwrite dw, 1 add to it;   ws: dsm_conv3d_wgrad_workspace_bytes(Ca, Cb) bytes of scratch  */
 size_t dsm_conv3d_wgrad_workspace_bytes(int Ca, int Cb);
+/* per-problem size: with this much scratch the stride-2 / transposed layers also run on the tcgen05 kernel (through a
+ * parity gather of the finer tensor into the workspace); with only the size above they use the warp-level kernel */
+size_t dsm_conv3d_wgrad_workspace_bytes_ex(int B, int Ca, int Cb, int Da, int Ha, int Wa, int stride);
 int dsm_conv3d_wgrad(const void* anchor, const void* partner, float* dw,
                      int B, int Ca, int Cb, int Da, int Ha, int Wa, int Dp, int Hp, int Wp, int stride,
                      int Ca_out, int Cb_out, const float* scale_a, const float* scale_b, int accumulate,

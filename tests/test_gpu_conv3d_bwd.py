@@ -141,3 +141,31 @@ def test_conv_c1_backward_vs_autograd(transposed, B, D, H, W):
     assert l2rel(conv.bias.grad, ref_gb) < 1e-5
     g6 = xd.grad.view(B, D + 2, H + 2, W + 2, 32)
     assert float(g6[:, 0].abs().max()) == 0.0 and float(g6[:, :, :, -1].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("ca,cb,B,Da,Ha,Wa,Dp,Hp,Wp", [
+    (64, 32, 1, 6, 12, 39, 12, 24, 78),      # conv1-like (32 -> 64, stride 2): anchor = gy (coarse), partner = x (fine)
+    (64, 64, 2, 4, 6, 19, 7, 11, 37),        # odd fine sizes
+    (32, 32, 1, 3, 5, 10, 6, 10, 20),
+    (64, 128, 1, 3, 4, 9, 6, 8, 18),
+    (32, 32, 1, 3, 4, 5, 5, 7, 9),           # transposed layer with a cropped output (partner smaller than 2x)
+])
+def test_wgrad_stride2_tcgen05_matches_warp_level_kernel(ca, cb, B, Da, Ha, Wa, Dp, Hp, Wp):
+    """stride-2 / transposed layers: parity gather + tcgen05 kernel (mode 0) against the warp-level kernel (mode 1)"""
+    from dsmnet_b200 import _lib
+    from dsmnet_b200.conv3d import conv3d_wgrad
+    from dsmnet_b200.volume_layout import PaddedVolume
+    torch.manual_seed(5)
+    anchor = PaddedVolume.from_ncdhw(torch.randn(B, ca, Da, Ha, Wa, device="cuda"))
+    partner = PaddedVolume.from_ncdhw(torch.randn(B, cb, Dp, Hp, Wp, device="cuda"))
+    L = _lib.lib()
+    out = []
+    for mode in (0, 1):
+        prev = L.dsm_debug_wgrad_mode(mode)
+        try:
+            out.append(conv3d_wgrad(anchor, partner, 2, ca, cb).clone())
+        finally:
+            L.dsm_debug_wgrad_mode(prev)
+    torch.cuda.synchronize()
+    assert L.dsm_debug_wgrad_timeouts() == 0
+    assert l2rel(out[0], out[1]) < 1e-5
