@@ -42,32 +42,57 @@ conv3d_c1_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
     for (int t = 0; t < 27; ++t) { wr[t] = w[lane * 27 + t]; acc[t] = 0.f; }
     const int Wq = g.W + 2, Hq = g.H + 2;
 
-    for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
+    // Software pipeline over tiles: the global loads of tile i+1 (its 9 gy rows and its x row segment) are issued into
+    // registers before tile i is computed and land in shared memory after it, so their latency hides behind the FMAs.
+    constexpr int NCOL = S * C1_TW + 2;
+    constexpr int NG = (9 * NCOL + C1_THREADS - 1) / C1_THREADS;      // staged gy elements per thread
+    float pg[NG];
+    uint4 px[2];
+    int pnv = 0; size_t pxrow = 0;
+    auto decode = [&](int tile, int& b, int& d, int& h, int& w0) {
         int r = tile;
         const int tw = r % g.tiles_w; r /= g.tiles_w;
-        const int h = r % g.H; r /= g.H;
-        const int d = r % g.D; const int b = r / g.D;
-        const int w0 = tw * C1_TW;
-        const int nv = min(C1_TW, g.W - w0);
-        // stage: s_g[row][j] = gy[b][S*d + SG*(kd-1)][S*h + SG*(kh-1)][c0 + j],  c0 = S*w0 - 1   (0 outside)
-        const int c0 = S * w0 - 1;
-        constexpr int NCOL = S * C1_TW + 2;
-        for (int i = threadIdx.x; i < 9 * NCOL; i += C1_THREADS) {
+        h = r % g.H; r /= g.H;
+        d = r % g.D; b = r / g.D;
+        w0 = tw * C1_TW;
+    };
+    auto prefetch = [&](int tile) {
+        int b, d, h, w0;
+        decode(tile, b, d, h, w0);
+        pnv = min(C1_TW, g.W - w0);
+        const int c0 = S * w0 - 1;             // s_g[row][j] = gy[b][S*d + SG*(kd-1)][S*h + SG*(kh-1)][c0 + j]   (0 outside)
+#pragma unroll
+        for (int k = 0; k < NG; ++k) {
+            const int i = threadIdx.x + k * C1_THREADS;
             const int row = i / NCOL, j = i - row * NCOL;
             const int kd = row / 3, kh = row - kd * 3;
             const int zd = S * d + SG * (kd - 1), zh = S * h + SG * (kh - 1), zw = c0 + j;
             float v = 0.f;
-            if (zd >= 0 && zd < g.Do && zh >= 0 && zh < g.Ho && zw >= 0 && zw < g.Wo)
+            if (i < 9 * NCOL && zd >= 0 && zd < g.Do && zh >= 0 && zh < g.Ho && zw >= 0 && zw < g.Wo)
                 v = __ldg(gy + (((size_t)b * g.Do + zd) * g.Ho + zh) * g.Wo + zw);
-            s_g[row][j] = v;
+            pg[k] = v;
         }
-        const size_t xrow = ((((size_t)b * (g.D + 2) + d + 1) * Hq + h + 1) * Wq + w0 + 1) * 32;
-        {   // x tile: nv voxels x 64 B, 16-byte vectors (4 per voxel)
-            const uint4* src = reinterpret_cast<const uint4*>(x + xrow);
-            uint4* dst = reinterpret_cast<uint4*>(&s_x[0][0]);
-            for (int i = threadIdx.x; i < nv * 4; i += C1_THREADS) dst[i] = __ldg(src + i);
+        pxrow = ((((size_t)b * (g.D + 2) + d + 1) * Hq + h + 1) * Wq + w0 + 1) * 32;
+        const uint4* src = reinterpret_cast<const uint4*>(x + pxrow);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int i = threadIdx.x + k * C1_THREADS;       // 64 voxels x 4 chunks = 256 chunks of 16 bytes
+            px[k] = (i < pnv * 4) ? __ldg(src + i) : make_uint4(0u, 0u, 0u, 0u);
         }
+    };
+    if ((int)blockIdx.x < g.ntiles) prefetch(blockIdx.x);
+    for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
+        const int nv = pnv;
+        const size_t xrow = pxrow;
+#pragma unroll
+        for (int k = 0; k < NG; ++k) {
+            const int i = threadIdx.x + k * C1_THREADS;
+            if (i < 9 * NCOL) { const int row = i / NCOL; s_g[row][i - row * NCOL] = pg[k]; }
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) reinterpret_cast<uint4*>(&s_x[0][0])[threadIdx.x + k * C1_THREADS] = px[k];
         __syncthreads();
+        if (tile + (int)gridDim.x < g.ntiles) prefetch(tile + gridDim.x);
         // a warp owns voxels [16*warp, 16*warp+16) of the tile, two at a time
 #pragma unroll 1
         for (int p = 0; p < 8; ++p) {
@@ -104,9 +129,8 @@ conv3d_c1_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
             const uint4* src = reinterpret_cast<const uint4*>(&s_o[0][0]);
             for (int i = threadIdx.x; i < nv * 4; i += C1_THREADS) dst[i] = src[i];
         }
-        // s_g / s_x / s_o are rewritten only after the next tile's first __syncthreads... s_g and s_x are written
-        // before it, so separate the tiles explicitly
-        __syncthreads();
+        // the next iteration rewrites s_g / s_x before its barrier and s_o after it: every thread has finished its reads
+        // of s_g / s_x at the barrier above and finishes this copy-out before it arrives at the next one
     }
     // CTA partial of dw: warps are summed in a fixed order
     for (int wi = 0; wi < C1_THREADS / 32; ++wi) {
