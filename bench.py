@@ -308,10 +308,10 @@ def run_native(args, rank, world, local_rank):
     ms_k = time_kernel_alone(lambda: layer(ws["a"], ws["c0"]))
     flops = 2.0 * 27 * 32 * 32 * B * (MAXDISP // 4) * h * w
     achieved = flops / (ms_k * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "conv3d_rs_kernel<KC=32,NP=32> (Conv3d 32->32 k3 s1 + BN + ReLU @48x96x312, 7 launches/step)",
+    roofline = {"bound": "tensor", "kernel": "conv3d_rs_kernel<KC=32,NP=32> (Conv3d 32->32 k3 s1 + BN + ReLU @48x96x312, 6 launches/step)",
                 "achieved": achieved, "peak": tf_burst, "unit": "TFLOP/s", "frac": achieved / tf_burst,
                 "peak_source": which + " bf16 burst (kernel timed alone)", "ms_per_launch": ms_k,
-                "traffic": 146.2e6, "traffic_source": "dram read+write of this kernel per launch, ncu --set full (profiles/r01f_prof_conv3d_rs_bench_summary.txt); algorithmic 184 MB, part of the output is still in L2 at kernel end"}
+                "traffic": 144.7e6, "traffic_source": "dram read+write of this kernel per launch, ncu --set full (profiles/r01h_prof_conv3d_rs_bench_summary.txt); algorithmic 184 MB, part of the output is still in L2 at kernel end"}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

@@ -1,3 +1,5 @@
+"""Per-kernel totals of one bench step from an `ncu --metrics gpu__time_duration.sum --csv` launch list.
+    python tools/launch_summary.py launches.csv"""
 import csv,collections,sys
 rows=list(csv.reader(open(sys.argv[1])))
 hdr=None; seq=[]
@@ -12,9 +14,8 @@ for r in rows:
 # take the last step: find last occurrence of concat kernel
 idx=[i for i,(k,g,v) in enumerate(seq) if 'concat_ndhwc' in k]
 print('launches',len(seq),'concat at',idx[-6:])
-start=idx[-1]
-step=seq[start:]
-# cut at next non-path? print all
+# the last COMPLETE step: from the second-to-last concat launch to the last one (the capture may end mid-step)
+step=seq[idx[-2]:idx[-1]] if len(idx) >= 2 else seq[idx[-1]:]
 agg=collections.OrderedDict(); tot=0
 for k,g,v in step:
     key=k.replace('<unnamed>::','')[:80]+' '+g
