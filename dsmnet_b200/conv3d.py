@@ -120,6 +120,7 @@ class FusedConv3d:
                  residual: Union[PaddedVolume, torch.Tensor, None] = None):
         """``out``: a PaddedVolume (bf16) or, for Cout==1, an fp32 [B,D,H,W] tensor; allocated when None.
         Its extent may be a crop of the natural output size (myadd_3d semantics)."""
+        _lib.require_cuda(x.data, self.w)
         if x.C != self.cin:
             raise _lib.DsmError("FusedConv3d: expected %d input channels, got %d" % (self.cin, x.C))
         nD, nH, nW = self.out_dims(x)

@@ -54,3 +54,45 @@ def test_no_cpu_fallback():
     from dsmnet_b200.corr1d import corr1d
     with pytest.raises(_lib.DsmError):
         corr1d(torch.zeros(1, 4, 4, 8), torch.zeros(1, 4, 4, 8), 3)
+
+
+def test_training_entry_points_validate_arguments():
+    """the training-path entry points reject null pointers / unsupported channel counts before any CUDA call"""
+    L = _lib.lib()
+    assert L.dsm_bn_stats(0, 1, 32, 2, 2, 2, 0, 0) == -1                       # null pointers
+    assert L.dsm_bn_stats(64, 1, 48, 2, 2, 2, 64, 0) == -2                     # C not in {32, 64, 128}
+    assert L.dsm_bn_act_fwd(0, 0, 0, 0, 1, 0, 1, 32, 2, 2, 2, 0) == -1
+    assert L.dsm_bn_act_fwd(64, 64, 64, 0, 3, 64, 1, 32, 2, 2, 2, 0) == -1     # relu mode out of range
+    assert L.dsm_bn_act_bwd_reduce(64, 64, 0, 64, 64, 1, 64, 1, 32, 2, 2, 2, 0) == -1    # relu 1 needs z
+    assert L.dsm_bn_act_bwd(64, 64, 0, 64, 64, 64, 1, 64, 0, 1, 32, 2, 2, 2, 0) == -1
+    assert L.dsm_bn_finalize_fwd(0, 0, 0, 0, 32, 10, 1e-5, 0.1, 0, 0, 0, 0, 0, 0, 0) == -1
+    assert L.dsm_zero_rim(0, 1, 32, 2, 2, 2, 0) == -1
+    assert L.dsm_zero_rim(64, 1, 12, 2, 2, 2, 0) == -1                         # C % 8 != 0
+    assert L.dsm_conv3d_c1_bwd(0, 0, 0, 0, 0, 1, 2, 2, 2, 2, 2, 2, 0, 0, 0, 0) == -1
+    assert L.dsm_upsample_softargmin_bwd(0, 0, 0, 0, 0, 1, 2, 2, 2, 8, 8, 8, 1, 0) == -1
+    assert L.dsm_pack_weight(0, 0, 32, 32, 0, 0) == -1
+    assert L.dsm_pack_weight(64, 64, 32, 32, 3, 0) == -1                       # unknown mode
+    assert L.dsm_conv3d_wgrad(0, 0, 0, 1, 32, 32, 2, 2, 2, 2, 2, 2, 1, 32, 32, 0, 0, 0, 0, 0, 0) == -1
+    # workspace queries are pure arithmetic
+    assert L.dsm_conv3d_wgrad_workspace_bytes(32, 32) > 0
+    assert L.dsm_conv3d_wgrad_workspace_bytes_ex(1, 64, 32, 24, 48, 156, 2) > L.dsm_conv3d_wgrad_workspace_bytes(64, 32)
+    assert L.dsm_conv3d_wgrad_workspace_bytes_ex(1, 32, 32, 48, 96, 312, 1) == L.dsm_conv3d_wgrad_workspace_bytes(32, 32)
+    assert L.dsm_conv3d_c1_bwd_workspace_bytes() > 0
+
+
+def test_training_wrappers_have_no_cpu_fallback():
+    import torch
+    import torch.nn as nn
+    from dsmnet_b200 import train3d as T
+    from dsmnet_b200.cost_volume import concat_volume_padded
+    from dsmnet_b200.softargmin import upsample_softargmin
+    from dsmnet_b200.volume_layout import PaddedVolume
+    y = torch.zeros(1 * 4 * 4 * 4 * 32, dtype=torch.bfloat16)
+    with pytest.raises(_lib.DsmError):
+        T.bn_act(PaddedVolume(y, 1, 32, 2, 2, 2), nn.BatchNorm3d(32).train())
+    with pytest.raises(_lib.DsmError):
+        concat_volume_padded(torch.zeros(1, 8, 4, 8), torch.zeros(1, 8, 4, 8), 3, "psm")
+    with pytest.raises(_lib.DsmError):
+        upsample_softargmin(torch.zeros(1, 2, 3, 4, requires_grad=True), (8, 12, 16), True)
+    with pytest.raises(_lib.DsmError):
+        T.conv_c1(PaddedVolume(y, 1, 32, 2, 2, 2), nn.Conv3d(32, 1, 3, padding=1))
