@@ -195,6 +195,11 @@ __device__ __forceinline__ void src_index(int dst, float scale, int in_size, int
     i1 = min(i0 + 1, in_size - 1);
 }
 
+// 128-bit vector reduction to global memory (sm_90+): four adjacent floats, 16-byte aligned, one L2 operation
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -396,14 +401,40 @@ upsample_softargmin_bwd_kernel(const float* __restrict__ cost, const float* __re
     }
     __syncthreads();
     float* gbase = gcost + (size_t)b * Dl * Hl * Wl;
-    for (int i = tid; i < Dl * rw; i += blockDim.x) {
-        const int dl = i / rw, j = i - dl * rw;
+    // flush: the CTA's window is rw consecutive columns of two low-res rows per plane.  Aligned groups of four columns go
+    // out as ONE 128-bit vector reduction (red.global.add.v4.f32) — the kernel is bound by the number of L2 atomics
+    // (36 M scalar ones for the three heads), not by their bytes; the window's ragged ends stay scalar.
+    const bool vec_ok = ((Wl & 3) == 0) && ((reinterpret_cast<uintptr_t>(gcost) & 15u) == 0);
+    const int lead = vec_ok ? ((4 - (wb & 3)) & 3) : rw;               // scalar columns before the first aligned group
+    const int ngrp = vec_ok ? (rw - lead) / 4 : 0;
+    const int per = lead + ngrp + (rw - lead - 4 * ngrp);              // work items per plane: leading scalars, groups, trailing scalars
+    for (int i = tid; i < Dl * per; i += blockDim.x) {
+        const int dl = i / per, k = i - dl * per;
+        const float* sg = s_g + dl * rw;
+        float* q0 = gbase + (size_t)dl * pl + wb;
+        if (k >= lead && k < lead + ngrp) {
+            const int j = lead + 4 * (k - lead);
+            if (wb + j + 3 < Wl) {
+                const float4 v = make_float4(sg[j], sg[j + 1], sg[j + 2], sg[j + 3]);
+                if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) {
+                    red_add_v4(q0 + (size_t)h0 * Wl + j, lh0 * v.x, lh0 * v.y, lh0 * v.z, lh0 * v.w);
+                    red_add_v4(q0 + (size_t)h1 * Wl + j, lh1 * v.x, lh1 * v.y, lh1 * v.z, lh1 * v.w);
+                }
+                continue;
+            }
+            for (int jj = j; jj < j + 4; ++jj) {                      // the group straddles the right edge of the tensor
+                if (wb + jj >= Wl || sg[jj] == 0.f) continue;
+                atomicAdd(q0 + (size_t)h0 * Wl + jj, lh0 * sg[jj]);
+                atomicAdd(q0 + (size_t)h1 * Wl + jj, lh1 * sg[jj]);
+            }
+            continue;
+        }
+        const int j = (k < lead) ? k : lead + 4 * ngrp + (k - lead - ngrp);
         if (wb + j >= Wl) continue;
-        const float v = s_g[i];
+        const float v = sg[j];
         if (v == 0.f) continue;
-        float* q = gbase + (size_t)dl * pl + wb + j;
-        atomicAdd(q + (size_t)h0 * Wl, lh0 * v);
-        atomicAdd(q + (size_t)h1 * Wl, lh1 * v);
+        atomicAdd(q0 + (size_t)h0 * Wl + j, lh0 * v);
+        atomicAdd(q0 + (size_t)h1 * Wl + j, lh1 * v);
     }
 }
 
