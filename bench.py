@@ -197,7 +197,7 @@ def run_native(args, rank, world, local_rank):
     host_R = torch.randn(B, C_FEAT, h, w, generator=g).pin_memory()
     fL = host_L.to(device); fR = host_R.to(device)
     host_out = [torch.empty(B, H_IMG, W_IMG).pin_memory() for _ in range(3)]
-    launches_per_step = 1 + 28 + 1              # concat volume, 28 conv blocks, one launch for the three heads
+    launches_per_step = 1 + 28 + 3              # concat volume, 28 conv blocks, three head launches (each as soon as its cost exists)
 
     def step():
         with torch.no_grad():

@@ -60,6 +60,8 @@ class hourglass(nn.Module):
 PDL_VARIANT = 0 if os.environ.get("DSM_NO_PDL") == "1" else 128
 # classifier branches on a second stream next to the following hourglass (DSM_CLS_STREAM=0 turns it off)
 CLS_SIDE_STREAM = os.environ.get("DSM_CLS_STREAM", "1") != "0"
+# with the second stream: launch each head as soon as its cost exists (DSM_EARLY_HEADS=0: one stacked launch at the end)
+EARLY_HEADS = os.environ.get("DSM_EARLY_HEADS", "1") != "0"
 
 
 class _Plan:
@@ -187,8 +189,11 @@ class PSMNetHotPath(nn.Module):
             costs.append(prev)
         return costs
 
-    def aggregate(self, fL, fR):
-        """concat volume + dres0..classif3 -> (cost1, cost2, cost3), fp32 [B, D/4, H/4, W/4] each."""
+    def aggregate(self, fL, fR, head=None):
+        """concat volume + dres0..classif3 -> (cost1, cost2, cost3), fp32 [B, D/4, H/4, W/4] each.
+        `head(i, cost)` (inference with the second stream only): called on the classifier stream right after cost{i+1}
+        exists, so that the heads of cost1 / cost2 run beside the later hourglasses instead of after them; returns
+        True if it was used (the caller then skips its own head launch)."""
         if self.training or torch.is_grad_enabled() and (fL.requires_grad or fR.requires_grad or
                                                          any(p.requires_grad for p in self.parameters())):
             return self.aggregate_train(fL, fR)
@@ -235,6 +240,8 @@ class PSMNetHotPath(nn.Module):
                     c0(ws["out"][i], ws["tc"][i])
                     prev = c2(ws["tc"][i], ws["cost"][i], residual=prev)       # :147-149 cumulative adds
                     costs.append(prev)
+                    if head is not None:
+                        head(i, prev)
         if side is not None:
             main.wait_stream(side)
             return costs
@@ -245,6 +252,19 @@ class PSMNetHotPath(nn.Module):
         return costs
 
     def forward(self, fL, fR, out_hw):
+        train = self.training or torch.is_grad_enabled() and (fL.requires_grad or fR.requires_grad or
+                                                              any(p.requires_grad for p in self.parameters()))
+        if CLS_SIDE_STREAM and EARLY_HEADS and not train:
+            # each head is launched on the classifier stream as soon as its cost exists: only the head of cost3 is left
+            # on the critical path (one stacked launch of all three after the last classifier cost ~95 us more)
+            B = fL.shape[0]
+            preds = torch.empty(3, B, out_hw[0], out_hw[1], device=fL.device, dtype=torch.float32)
+            size = (self.maxdisp, out_hw[0], out_hw[1])
+
+            def head(i, cost):
+                upsample_softargmin(cost, size, self.align_corners, out=preds[2 - i])      # preds = (pred3, pred2, pred1)
+            self.aggregate(fL, fR, head)
+            return [preds[0], preds[1], preds[2]]
         c1, c2, c3 = self.aggregate(fL, fR)
         if c1.requires_grad:
             # differentiable heads (stackhourglass.py:152-166): the fused upsample + soft-argmin kernels, forward and
