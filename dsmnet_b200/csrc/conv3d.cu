@@ -499,7 +499,7 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_w);
         ptx::prefetch_tensormap(&map_a);
-        for (int s = 0; s < C::STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), C::KHS); }
+        for (int s = 0; s < C::STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
         for (int a = 0; a < 2; ++a) { ptx::mbar_init(tfull_bar(a), 3); ptx::mbar_init(tempty_bar(a), 8); }
         ptx::mbar_init(wfull_bar, 1);
         ptx::fence_mbar_init();
@@ -559,9 +559,10 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const uint32_t desc_hi = (uint32_t)(dsc >> 32);
         const uint32_t ring_lo = (uint32_t)dsc | (ring >> 4);
         const uint32_t w_lo = ((uint32_t)dsc | (wsm >> 4)) + (uint32_t)((my_kh * 3 * C::W_TILE) >> 4);
-        const uint32_t a_tile = (C::KHS == 3) ? (uint32_t)((my_kh * C::A_BYTES) >> 4) : 0u;
+        const uint32_t a_tile = 0u;
+        const uint32_t w_base = (uint32_t)dsc | (wsm >> 4);
         int s = 0; uint32_t ph = 0;
-        int tcount = 0;
+        int tcount = 0, rot = 0;
         for (int t = item0; t < g.nitems; t += item_step) {
             const RsItem item = rs_decode(g, t, C::R);
             const int acc = tcount & 1;
@@ -580,30 +581,61 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 const uint32_t d_lo = d_tmem + jlo * NP;
                 const uint32_t idesc = idesc0 | ((uint32_t)((jhi - jlo + 1) * NP >> 3) << 17);
                 const uint32_t b_lo0 = w_lo + ((uint32_t)(brow * C::ROWB) >> 4);
-#pragma unroll
-                for (int khs = 0; khs < 3 / C::KHS; ++khs) {
-                    if (C::KHS == 3 || khs == my_kh) {
+                if (C::KHS == 3) {
+                    // one stage = one plane (all three kh tiles): the issuers take the planes in rotation and issue all
+                    // 18 MMAs of theirs, so the per-stage bookkeeping is paid once per 18 MMAs instead of once per 6
+                    if (rot == my_kh) {
                         wait_bar(full_bar(s), ph);
                         ptx::tc_fence_after();
                         if (ptx::elect_one_sync()) {
-                            const uint32_t a_lo0 = ring_lo + (uint32_t)s * (C::STAGE_BYTES >> 4) + a_tile;
                             if (!(g.dbg & 4)) {
 #pragma unroll
-                                for (int kw = 0; kw < 3; ++kw) {
+                                for (int kh = 0; kh < 3; ++kh) {
+                                    const uint32_t a_lo0 = ring_lo + (uint32_t)s * (C::STAGE_BYTES >> 4) + (uint32_t)((kh * C::A_BYTES) >> 4);
+                                    const uint32_t b_kh = w_base + (uint32_t)((kh * 3 * C::W_TILE + brow * C::ROWB) >> 4);
 #pragma unroll
-                                    for (int k = 0; k < KC / 16; ++k)
-                                        ptx::umma_bf16_lohi(d_lo, a_lo0 + ((kw * C::ROWB + k * 32) >> 4),
-                                                            b_lo0 + ((kw * C::W_TILE + k * 32) >> 4), desc_hi, idesc, 1u);
+                                    for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+                                        for (int k = 0; k < KC / 16; ++k)
+                                            ptx::umma_bf16_lohi(d_lo, a_lo0 + ((kw * C::ROWB + k * 32) >> 4),
+                                                                b_kh + ((kw * C::W_TILE + k * 32) >> 4), desc_hi, idesc, 1u);
+                                    }
                                 }
                             }
                             ptx::umma_commit(empty_bar(s));
-                            if (i == last_i) ptx::umma_commit(tfull_bar(acc));
                         }
                         __syncwarp();
                     }
+                    if (++rot == 3) rot = 0;
                     if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+                } else {
+#pragma unroll
+                    for (int khs = 0; khs < 3; ++khs) {
+                        if (khs == my_kh) {
+                            wait_bar(full_bar(s), ph);
+                            ptx::tc_fence_after();
+                            if (ptx::elect_one_sync()) {
+                                const uint32_t a_lo0 = ring_lo + (uint32_t)s * (C::STAGE_BYTES >> 4) + a_tile;
+                                if (!(g.dbg & 4)) {
+#pragma unroll
+                                    for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+                                        for (int k = 0; k < KC / 16; ++k)
+                                            ptx::umma_bf16_lohi(d_lo, a_lo0 + ((kw * C::ROWB + k * 32) >> 4),
+                                                                b_lo0 + ((kw * C::W_TILE + k * 32) >> 4), desc_hi, idesc, 1u);
+                                    }
+                                }
+                                ptx::umma_commit(empty_bar(s));
+                            }
+                            __syncwarp();
+                        }
+                        if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+                    }
                 }
             }
+            // all MMAs this warp issued for the item are in flight: its share of "accumulators complete"
+            if (ptx::elect_one_sync()) ptx::umma_commit(tfull_bar(acc));
+            __syncwarp();
         }
     } else {
         // ================= epilogue: 8 warps, two per TMEM lane quadrant =================
