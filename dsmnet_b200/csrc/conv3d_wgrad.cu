@@ -283,10 +283,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             auto load_x = [&](int p0, int plane) {
                 const int s = xn % NB;
                 ok = ok && wait_bar(empty_b(s), ((xn / NB) & 1u) ^ 1u);
-                ptx::mbar_arrive_expect_tx(full_b(s), B_SLOT);
+                ptx::mbar_arrive_expect_tx(full_b(s), (kh_hi - kh_lo + 1) * B_COPY);     // only the kh copies this class uses
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
-                    ptx::tma_load_3d(sB + s * B_SLOT + c * B_COPY, &map_b, full_b(s), cb0, p0 + (c - 1) * g.Wq + 1, plane);
+                    if (c >= kh_lo && c <= kh_hi)
+                        ptx::tma_load_3d(sB + s * B_SLOT + c * B_COPY, &map_b, full_b(s), cb0, p0 + (c - 1) * g.Wq + 1, plane);
                 ++xn;
             };
             for (long long t = t0; t < t1 && ok;) {
