@@ -146,6 +146,94 @@ void run_rs(const char* what) {
     cudaFree(d);
 }
 
+// ---- cta_group::2 rate probe: a CTA pair issues M=256 (2 x 128) SS MMAs; each SM reads its own 4 KB A slab and HALF of
+// the B tile per instruction, so the shared-memory operand traffic per SM drops from 4 KB + N*32 B to 4 KB + N*16 B.
+// Operand contents are garbage; only the issue/retire rate is measured.  Every wait is bounded.
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <int N, int ROWB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64) rate2_kernel(long long* cycles, int n_iter) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = ptx::smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t slot;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t rank = cluster_rank();
+    if (threadIdx.x == 0) { ptx::mbar_init(ptx::smem_u32(&bar), 1); ptx::fence_mbar_init(); }
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(ptx::smem_u32(&slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    ptx::tc_fence_before(); __syncthreads(); ptx::tc_fence_after();
+    cluster_sync_all();
+    const uint32_t tmem = slot;
+    long long t0 = 0, t1 = 0;
+    if (warp == 0) {
+        // instruction descriptor: as make_idesc_bf16 but M = 256
+        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+        constexpr uint32_t a_bytes = 128 * ROWB, b_bytes = (N / 2) * ROWB;       // per CTA
+        const uint32_t sa = base, sb = base + 2 * a_bytes;
+        uint64_t ad[8], bd[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const uint32_t tile = (u >> 1) & 1, slab = u % (ROWB / 32);
+            ad[u] = ptx::make_kmajor_desc(sa + tile * a_bytes + slab * 32, ROWB, 0u);
+            bd[u] = ptx::make_kmajor_desc(sb + tile * b_bytes + slab * 32, ROWB, 0u);
+        }
+        __syncwarp();
+        t0 = clock64();
+        if (rank == 0 && ptx::elect_one_sync()) {
+            for (int i = 0; i < n_iter; ++i) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t d = tmem + (u & 1) * 256;
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\t"
+                        "setp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                        :: "r"(d), "l"(ad[u]), "l"(bd[u]), "r"(idesc), "r"(1u) : "memory");
+                }
+            }
+            asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                         :: "r"(ptx::smem_u32(&bar)), "h"((uint16_t)3) : "memory");
+        }
+        __syncwarp();
+        long long guard = clock64();
+        while (!ptx::mbar_try_wait(ptx::smem_u32(&bar), 0)) { if (clock64() - guard > 4000000000LL) break; }
+        t1 = clock64();
+        if (threadIdx.x == 0 && rank == 0) cycles[blockIdx.x / 2] = t1 - t0;
+    }
+    ptx::tc_fence_before(); __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u) : "memory");
+}
+
+template <int N, int ROWB>
+void run2(const char* what) {
+    const int n_iter = 512;
+    int nsm = 148; cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
+    const int nblk = (nsm / 2) * 2;
+    const size_t smem = (size_t)2 * (128 * ROWB + (N / 2) * ROWB) + 2048 + 8 * ROWB;
+    auto k = rate2_kernel<N, ROWB>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    long long* d; cudaMalloc(&d, nsm * sizeof(long long)); cudaMemset(d, 0, nsm * sizeof(long long));
+    k<<<nblk, 64, smem>>>(d, n_iter);
+    k<<<nblk, 64, smem>>>(d, n_iter);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long h[1024]; cudaMemcpy(h, d, (nblk / 2) * sizeof(long long), cudaMemcpyDeviceToHost);
+    double mx = 0; for (int i = 0; i < nblk / 2; ++i) mx = h[i] > mx ? h[i] : mx;
+    const double cyc = mx / (n_iter * 8.0);
+    printf("%-6s N=%3d rowB=%3d : %6.1f cyc/op (M=256 per CTA pair) -> %6.0f flop/clk/SM (%s)\n", what, N, ROWB, cyc,
+           2.0 * 256 * N * 16 / cyc / 2.0, cudaGetErrorString(e));
+    cudaFree(d);
+}
+
 template <int N, int ROWB, int MODE, int ASHIFT = 0>
 void run(const char* what) {
     const int n_iter = 512;
@@ -186,6 +274,9 @@ int main(int argc, char** argv) {
         run<256, 128, SS, 100>("SS-dep"); run<32, 64, TS, 100>("TS-dep"); run<96, 64, TS, 100>("TS-dep");
     }
     if (what == 0 || what == 7) { run_rs<1>("RS stream, 1 issuer"); run_rs<3>("RS stream, 3 issuers"); }
+    if (what == 8) {    // cta_group::2 (not part of the default sweep)
+        run2<32, 64>("SS2"); run2<64, 64>("SS2"); run2<96, 64>("SS2"); run2<128, 64>("SS2"); run2<96, 128>("SS2"); run2<256, 128>("SS2");
+    }
     if (what == 0 || what == 4) { run<32, 64, TS_CP>("TS+CP"); run<32, 128, TS_CP>("TS+CP"); run<64, 128, TS_CP>("TS+CP"); }
     return 0;
 }
