@@ -2,7 +2,8 @@
 // (cta_group::1, kind::f16, M=128, K=16, bf16) as a function of N, for
 //   SS : A and B from shared memory (K-major, swizzled rows of 64/128 bytes)
 //   TS : A from tensor memory, B from shared memory
-// and of tcgen05.cp 128x256b (shared -> tensor memory, one 128x16 bf16 A slab).
+// and of tcgen05.cp 128x256b (shared -> tensor memory, one 128x16 bf16 A slab); `mma_bench 8` measures the CTA-pair form
+// (cta_group::2, M = 256 per pair: each SM reads its own A slab and half of B).
 // The issue loop is unrolled x8 with pre-built descriptors so that the single issuing thread is not
 // the limit.  Operand contents are garbage: only rates are measured.
 //   build: make tests/cuda/mma_bench ; run: tests/cuda/mma_bench
