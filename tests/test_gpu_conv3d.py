@@ -306,3 +306,17 @@ def test_psmnet_training_step_gradients():
         # the fp32 gradient of this random, batch-normalised (hence noise-amplifying) network: cos(emu, fp32) ~ 0.97
         assert c_ref > 0.9 and 0.85 < float(mine.norm() / ref.norm()) < 1.15
         assert c_ref > c_fmt - 0.03                                             # no worse than the bf16 format itself
+
+
+@pytest.mark.parametrize("cout,cin", [(32, 64), (1, 32), (64, 32), (128, 64)])
+def test_pack_weight_kernel_matches_host_packing(cout, cin):
+    """dsm_pack_weight (one launch) is bit-identical to the host-side permute/cat/cast packing in all three modes"""
+    from dsmnet_b200.conv3d import pack_weight, pack_weight_device
+    torch.manual_seed(9)
+    w = torch.randn(cout, cin, 3, 3, 3)
+    assert torch.equal(pack_weight_device(w.cuda(), 0).cpu(), pack_weight(w, False))                 # Conv3d
+    wt = torch.randn(cin, cout, 3, 3, 3)
+    assert torch.equal(pack_weight_device(wt.cuda(), 1).cpu(), pack_weight(wt, True))                # ConvTranspose3d
+    if cout >= 16:
+        ref = pack_weight(w.flip(2, 3, 4).transpose(0, 1).contiguous(), False)                        # stride-1 dgrad filter
+        assert torch.equal(pack_weight_device(w.cuda(), 2).cpu(), ref)
