@@ -49,6 +49,9 @@ SIGNATURES = {
     "dsm_conv3d_c1_bwd_workspace_bytes": [],
     "dsm_conv3d_c1_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, c_size_t, _P],
     "dsm_debug_conv_timeouts": [],
+    "dsm_debug_conv_set_trap": [_I],
+    "dsm_crop_add_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "dsm_crop_add_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "dsm_debug_wgrad_mode": [_I],
     "dsm_debug_wgrad_timeouts": [],
     "dsm_pack_weight": [_P, _P, _I, _I, _I, _P],

@@ -164,9 +164,8 @@ def conv_timeouts() -> int:
 #   forward : the same tcgen05 kernels as inference (identity affine, no activation)
 #   dgrad   : those kernels again with transformed weights (see include/dsmnet_b200.h, op 3 training)
 #   wgrad   : dsm_conv3d_wgrad
-# BatchNorm (batch statistics), ReLU and the skip adds of the training graph are stock PyTorch
-# elementwise/reduction ops on views of these volumes (dsmnet_b200/train3d.py) — as in the reference,
-# whose BatchNorm3d/ReLU are stock modules.
+# BatchNorm (batch statistics or frozen), ReLU and the (cropped) skip adds of the training graph are the streaming
+# kernels of csrc/bnact.cu, wrapped in dsmnet_b200/train3d.py.
 # ------------------------------------------------------------------------------------------------
 
 def _dgrad_layer(weight: torch.Tensor, stride: int, transposed: bool, device) -> "FusedConv3d":

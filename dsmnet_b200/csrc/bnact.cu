@@ -316,6 +316,77 @@ zero_rim_kernel(uint4* __restrict__ data, int C8, int D, int H, int W) {
     }
 }
 
+
+// Cropped skip add (the reference's myadd_3d / myAdd3d crop-to-min, stackhourglass.py:10-20, util_fun.py:41-51) for the
+// training path with odd sizes: `full` is the BatchNorm'ed deconv output at its NATURAL extent (Dn,Hn,Wn) — batch
+// statistics are taken over all of it, as the reference does — and the skip tensor / result have the smaller extent
+// (Do,Ho,Wo).  One 16-byte chunk (8 channels) per thread.
+//   fwd: z = act(crop(full) + res)           relu 0 none, 1 after the add
+//   bwd: g = gz * (z > 0 | 1); gres = g (interior; its rim is zeroed by the caller); gfull = g inside the crop, 0 elsewhere
+struct CropGeom { int B, C8, Dn, Hn, Wn, Do, Ho, Wo; };
+
+__device__ __forceinline__ uint4 relu_bf16x8_mask(const uint4& g, const uint4& z) {
+    uint4 r;
+    const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, zw[4] = {z.x, z.y, z.z, z.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t lo = bf16_lo(zw[i]) > 0.f ? (gw[i] & 0xffffu) : 0u;
+        const uint32_t hi = bf16_hi(zw[i]) > 0.f ? (gw[i] & 0xffff0000u) : 0u;
+        o[i] = lo | hi;
+    }
+    r.x = o[0]; r.y = o[1]; r.z = o[2]; r.w = o[3];
+    return r;
+}
+
+template <int RELU>
+__global__ void __launch_bounds__(BN_THREADS)
+crop_add_fwd_kernel(const uint4* __restrict__ full, const uint4* __restrict__ res, uint4* __restrict__ z, CropGeom g) {
+    const long long n = (long long)g.B * (g.Do + 2) * (g.Ho + 2) * (g.Wo + 2) * g.C8;
+    for (long long i = (long long)blockIdx.x * BN_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * BN_THREADS) {
+        const int k = (int)(i % g.C8); long long t = i / g.C8;
+        const int wp = (int)(t % (g.Wo + 2)); t /= (g.Wo + 2);
+        const int hp = (int)(t % (g.Ho + 2)); t /= (g.Ho + 2);
+        const int dp = (int)(t % (g.Do + 2)); const int b = (int)(t / (g.Do + 2));
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (dp >= 1 && dp <= g.Do && hp >= 1 && hp <= g.Ho && wp >= 1 && wp <= g.Wo) {
+            const size_t fi = ((((size_t)b * (g.Dn + 2) + dp) * (g.Hn + 2) + hp) * (g.Wn + 2) + wp) * g.C8 + k;
+            const uint4 a = __ldg(full + fi), r = __ldg(res + i);
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, rw[4] = {r.x, r.y, r.z, r.w};
+            uint32_t ow[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float lo = bf16_lo(aw[j]) + bf16_lo(rw[j]), hi = bf16_hi(aw[j]) + bf16_hi(rw[j]);
+                if (RELU == 1) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+                ow[j] = pack_bf16x2(lo, hi);
+            }
+            o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        }
+        z[i] = o;
+    }
+}
+
+template <int RELU>
+__global__ void __launch_bounds__(BN_THREADS)
+crop_add_bwd_kernel(const uint4* __restrict__ gz, const uint4* __restrict__ z, uint4* __restrict__ gfull,
+                    uint4* __restrict__ gres, CropGeom g) {
+    const long long n = (long long)g.B * (g.Dn + 2) * (g.Hn + 2) * (g.Wn + 2) * g.C8;
+    for (long long i = (long long)blockIdx.x * BN_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * BN_THREADS) {
+        const int k = (int)(i % g.C8); long long t = i / g.C8;
+        const int wp = (int)(t % (g.Wn + 2)); t /= (g.Wn + 2);
+        const int hp = (int)(t % (g.Hn + 2)); t /= (g.Hn + 2);
+        const int dp = (int)(t % (g.Dn + 2)); const int b = (int)(t / (g.Dn + 2));
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (dp >= 1 && dp <= g.Do && hp >= 1 && hp <= g.Ho && wp >= 1 && wp <= g.Wo) {
+            const size_t ci = ((((size_t)b * (g.Do + 2) + dp) * (g.Ho + 2) + hp) * (g.Wo + 2) + wp) * g.C8 + k;
+            o = __ldg(gz + ci);
+            if (RELU == 1) o = relu_bf16x8_mask(o, __ldg(z + ci));
+            if (gres) gres[ci] = o;
+        }
+        gfull[i] = o;
+    }
+}
+
 int check_geom(int B, int C, int D, int H, int W) {
     if (B < 1 || D < 1 || H < 1 || W < 1) return DSM_EINVAL;
     if (C != 32 && C != 64 && C != 128) return DSM_EUNSUPPORTED;
@@ -342,6 +413,7 @@ dim3 apply_grid(int B, int C, int D, int H, int W) {
 }  // namespace
 
 extern "C" int dsm_zero_rim(void* data, int B, int C, int D, int H, int W, void* stream_) {
+    DsmDeviceGuard dsm_guard_(data);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (!data || B < 1 || D < 1 || H < 1 || W < 1 || C < 8 || (C & 7) || C > 1024) return DSM_EINVAL;
     if (!dsm_aligned16(data)) return DSM_EALIGN;
@@ -351,6 +423,7 @@ extern "C" int dsm_zero_rim(void* data, int B, int C, int D, int H, int W, void*
 }
 
 extern "C" int dsm_bn_stats(const void* y, int B, int C, int D, int H, int W, double* sums, void* stream_) {
+    DsmDeviceGuard dsm_guard_(y);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (int e = check_geom(B, C, D, H, W)) return e;
     if (!y || !sums) return DSM_EINVAL;
@@ -367,6 +440,7 @@ extern "C" int dsm_bn_finalize_fwd(const double* sums, const float* gamma, const
                                    int C, long long count, float eps, float momentum,
                                    float* running_mean, float* running_var,
                                    float* scale, float* shift, float* mean, float* rstd, void* stream_) {
+    DsmDeviceGuard dsm_guard_(sums);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (!sums || !scale || !shift || !mean || !rstd || C < 1 || count < 1) return DSM_EINVAL;
     bn_finalize_fwd_kernel<<<dsm_ceil_div(C, 128), 128, 0, stream>>>(sums, gamma, beta, conv_bias, (double)count, eps, momentum,
@@ -376,6 +450,7 @@ extern "C" int dsm_bn_finalize_fwd(const double* sums, const float* gamma, const
 
 extern "C" int dsm_bn_act_fwd(const void* y, const float* scale, const float* shift, const void* residual, int relu,
                               void* z, int B, int C, int D, int H, int W, void* stream_) {
+    DsmDeviceGuard dsm_guard_(y);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (int e = check_geom(B, C, D, H, W)) return e;
     if (!y || !z || !scale || !shift || relu < 0 || relu > 2) return DSM_EINVAL;
@@ -393,6 +468,7 @@ extern "C" int dsm_bn_act_fwd(const void* y, const float* scale, const float* sh
 
 extern "C" int dsm_bn_act_bwd_reduce(const void* gz, const void* y, const void* z, const float* scale, const float* shift,
                                      int relu, double* sums, int B, int C, int D, int H, int W, void* stream_) {
+    DsmDeviceGuard dsm_guard_(gz);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (int e = check_geom(B, C, D, H, W)) return e;
     if (!gz || !y || !sums || relu < 0 || relu > 2) return DSM_EINVAL;
@@ -412,6 +488,7 @@ extern "C" int dsm_bn_act_bwd_reduce(const void* gz, const void* y, const void* 
 
 extern "C" int dsm_bn_finalize_bwd(const double* sums, const float* gamma, const float* mean, const float* rstd,
                                    int C, long long count, float* dgamma, float* dbeta, float* coef, void* stream_) {
+    DsmDeviceGuard dsm_guard_(sums);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (!sums || !mean || !rstd || !dgamma || !dbeta || !coef || C < 1 || count < 1) return DSM_EINVAL;
     bn_finalize_bwd_kernel<<<dsm_ceil_div(C, 128), 128, 0, stream>>>(sums, gamma, mean, rstd, (double)count, dgamma, dbeta, coef, C);
@@ -421,6 +498,7 @@ extern "C" int dsm_bn_finalize_bwd(const double* sums, const float* gamma, const
 extern "C" int dsm_bn_act_bwd(const void* gz, const void* y, const void* z, const float* scale, const float* shift,
                               const float* coef, int relu, void* dy, void* gres,
                               int B, int C, int D, int H, int W, void* stream_) {
+    DsmDeviceGuard dsm_guard_(gz);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (int e = check_geom(B, C, D, H, W)) return e;
     if (!gz || !y || !dy || !coef || relu < 0 || relu > 2) return DSM_EINVAL;
@@ -436,5 +514,39 @@ extern "C" int dsm_bn_act_bwd(const void* gz, const void* y, const void* z, cons
     if (gres) { if (relu == 0) DSM_BN_BWD(0, true); else if (relu == 1) DSM_BN_BWD(1, true); else DSM_BN_BWD(2, true); }
     else      { if (relu == 0) DSM_BN_BWD(0, false); else if (relu == 1) DSM_BN_BWD(1, false); else DSM_BN_BWD(2, false); }
 #undef DSM_BN_BWD
+    return dsm_launch_status();
+}
+
+extern "C" int dsm_crop_add_fwd(const void* full, const void* residual, void* z, int B, int C,
+                                int Dn, int Hn, int Wn, int Do, int Ho, int Wo, int relu, void* stream_) {
+    DsmDeviceGuard dsm_guard_(full);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!full || !residual || !z || B < 1 || C < 8 || (C & 7) || relu < 0 || relu > 1) return DSM_EINVAL;
+    if (Do < 1 || Ho < 1 || Wo < 1 || Do > Dn || Ho > Hn || Wo > Wn) return DSM_EINVAL;
+    if (!dsm_aligned16(full) || !dsm_aligned16(residual) || !dsm_aligned16(z)) return DSM_EALIGN;
+    const CropGeom g{B, C / 8, Dn, Hn, Wn, Do, Ho, Wo};
+    const long long n = (long long)B * (Do + 2) * (Ho + 2) * (Wo + 2) * (C / 8);
+    long long blocks = dsm_ceil_div_ll(n, BN_THREADS);
+    if (blocks > DSM_NUM_SMS_B200 * 16) blocks = DSM_NUM_SMS_B200 * 16;
+    const uint4 *pf = static_cast<const uint4*>(full), *pr = static_cast<const uint4*>(residual);
+    if (relu) crop_add_fwd_kernel<1><<<(unsigned)blocks, BN_THREADS, 0, stream>>>(pf, pr, static_cast<uint4*>(z), g);
+    else      crop_add_fwd_kernel<0><<<(unsigned)blocks, BN_THREADS, 0, stream>>>(pf, pr, static_cast<uint4*>(z), g);
+    return dsm_launch_status();
+}
+
+extern "C" int dsm_crop_add_bwd(const void* gz, const void* z, void* gfull, void* gres, int B, int C,
+                                int Dn, int Hn, int Wn, int Do, int Ho, int Wo, int relu, void* stream_) {
+    DsmDeviceGuard dsm_guard_(gz);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!gz || !gfull || B < 1 || C < 8 || (C & 7) || relu < 0 || relu > 1 || (relu == 1 && !z)) return DSM_EINVAL;
+    if (Do < 1 || Ho < 1 || Wo < 1 || Do > Dn || Ho > Hn || Wo > Wn) return DSM_EINVAL;
+    if (!dsm_aligned16(gz) || !dsm_aligned16(gfull) || (z && !dsm_aligned16(z)) || (gres && !dsm_aligned16(gres))) return DSM_EALIGN;
+    const CropGeom g{B, C / 8, Dn, Hn, Wn, Do, Ho, Wo};
+    const long long n = (long long)B * (Dn + 2) * (Hn + 2) * (Wn + 2) * (C / 8);
+    long long blocks = dsm_ceil_div_ll(n, BN_THREADS);
+    if (blocks > DSM_NUM_SMS_B200 * 16) blocks = DSM_NUM_SMS_B200 * 16;
+    const uint4 *pg = static_cast<const uint4*>(gz), *pz = static_cast<const uint4*>(z);
+    if (relu) crop_add_bwd_kernel<1><<<(unsigned)blocks, BN_THREADS, 0, stream>>>(pg, pz, static_cast<uint4*>(gfull), static_cast<uint4*>(gres), g);
+    else      crop_add_bwd_kernel<0><<<(unsigned)blocks, BN_THREADS, 0, stream>>>(pg, pz, static_cast<uint4*>(gfull), static_cast<uint4*>(gres), g);
     return dsm_launch_status();
 }

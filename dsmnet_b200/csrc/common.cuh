@@ -7,10 +7,31 @@
 
 #define DSM_NUM_SMS_B200 148
 
+// Status of the library's own launch: cudaGetLastError clears a non-sticky error, so a stale error of an earlier,
+// unrelated launch is reported once (to the call that finds it) and not attributed to every later dsm call.
 static inline int dsm_launch_status() {
-    cudaError_t e = cudaPeekAtLastError();
+    cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }
+
+// Every entry point runs on the device that owns its first device pointer: cudaFuncSetAttribute, launches and
+// cudaMemsetAsync act on the CURRENT device, which need not be the tensor's (a model on cuda:1 while cuda:0 is
+// current).  The guard switches to the pointer's device for the duration of the call and restores the caller's.
+struct DsmDeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DsmDeviceGuard(const void* p) {
+        cudaPointerAttributes a;
+        if (p && cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeDevice) {
+            if (cudaGetDevice(&prev) == cudaSuccess && prev != a.device) switched = (cudaSetDevice(a.device) == cudaSuccess);
+        } else {
+            cudaGetLastError();                       // not a device pointer: the entry point's own checks report it
+        }
+    }
+    ~DsmDeviceGuard() { if (switched) cudaSetDevice(prev); }
+    DsmDeviceGuard(const DsmDeviceGuard&) = delete;
+    DsmDeviceGuard& operator=(const DsmDeviceGuard&) = delete;
+};
 
 static inline bool dsm_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

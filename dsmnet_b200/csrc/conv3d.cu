@@ -49,6 +49,7 @@ struct ConvGeom {
 };
 
 __device__ int g_conv_timeouts = 0;
+__device__ int g_conv_trap = 1;              // 1 (default): a timed-out pipeline wait is FATAL (__trap -> sticky CUDA error)
 __device__ int* g_conv_progress = nullptr;   // bring-up only: host-mapped int[4], one slot per warp of CTA 1
 
 // ptxas lowers tcgen05.wait::ld to nothing and relies on the register scoreboard of the first
@@ -79,9 +80,15 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     return t;
 }
 
-// Bounded wait: a broken pipeline must end the kernel (with a counted timeout), never hang the GPU.
-// The fast path is a bare try_wait spin (the instruction itself suspends the warp for a while); the
-// global timeout flag and the wall clock are only consulted every 4096 failed polls.
+// Bounded wait: a broken pipeline must never hang the GPU, and it must never go unnoticed either.  A wait that
+// is not satisfied within 2 s of wall clock (far beyond any legitimate stall: time slicing, a PDL dependent waiting
+// for a long primary kernel) counts a timeout and TRAPS: the kernel dies, the context reports a sticky launch
+// failure at the next CUDA call and no later result can be silently wrong.  Bring-up mode
+// (dsm_debug_conv_set_trap(0)): the wait returns false instead, every further wait in the process gives up at its
+// first check, the kernel runs to its end on garbage and dsm_debug_conv_timeouts() tells — only for
+// debugging a new kernel without losing the context.
+// The fast path is a bare try_wait spin (the instruction itself suspends the warp for a while); the wall clock is
+// only consulted every 4096 failed polls.
 __device__ __forceinline__ bool wait_bar(uint32_t bar, uint32_t parity) {
     if (ptx::mbar_try_wait(bar, parity)) return true;
     unsigned long long t0 = 0;
@@ -89,8 +96,11 @@ __device__ __forceinline__ bool wait_bar(uint32_t bar, uint32_t parity) {
         if (ptx::mbar_try_wait(bar, parity)) return true;
         if ((spins & 4095u) == 0u) {
             if (t0 == 0) t0 = globaltimer_ns();
-            if (globaltimer_ns() - t0 > 200000000ULL /*0.2 s*/ || *reinterpret_cast<volatile int*>(&g_conv_timeouts)) {
+            const bool trap = *reinterpret_cast<volatile int*>(&g_conv_trap) != 0;
+            if (globaltimer_ns() - t0 > 2000000000ULL /*2 s*/ ||
+                (!trap && *reinterpret_cast<volatile int*>(&g_conv_timeouts))) {
                 atomicAdd(&g_conv_timeouts, 1);
+                if (trap) __trap();
                 return false;
             }
         }
@@ -1407,6 +1417,7 @@ extern "C" int dsm_conv3d_fwd(const void* x, const void* w_packed, const float* 
                               int B, int Cin, int Cout, int D, int H, int W,
                               int stride, int transposed, int relu, int y_dtype,
                               void* ws, size_t ws_bytes, void* stream) {
+    DsmDeviceGuard dsm_guard_(x);
     (void)ws; (void)ws_bytes;
     return conv3d_dispatch(x, w_packed, scale, shift, residual, y, B, Cin, Cout, D, H, W, stride, transposed, relu,
                            y_dtype, 0, 0, 0, /*variant=*/0, stream);
@@ -1421,6 +1432,7 @@ extern "C" int dsm_conv3d_fwd_ex(const void* x, const void* w_packed, const floa
                                  int B, int Cin, int Cout, int D, int H, int W,
                                  int stride, int transposed, int relu, int y_dtype,
                                  int Do, int Ho, int Wo, int variant, void* stream) {
+    DsmDeviceGuard dsm_guard_(x);
     return conv3d_dispatch(x, w_packed, scale, shift, residual, y, B, Cin, Cout, D, H, W, stride, transposed, relu,
                            y_dtype, Do, Ho, Wo, variant, stream);
 }
@@ -1428,6 +1440,18 @@ extern "C" int dsm_conv3d_fwd_ex(const void* x, const void* w_packed, const floa
 // bring-up aid: `host_mapped` = device-visible int[4] the kernel writes progress codes into (NULL = off)
 extern "C" int dsm_debug_conv_set_progress(int* host_mapped) {
     return (int)cudaMemcpyToSymbol(g_conv_progress, &host_mapped, sizeof(int*));
+}
+
+// 1 (default): a timed-out pipeline wait traps (fatal, visible); 0: bring-up mode, counted and survivable.  Returns the
+// previous setting.  Applies to the forward/dgrad kernels and to the tcgen05 weight-gradient kernel.
+extern "C" int dsm_debug_wgrad_set_trap(int on);
+extern "C" int dsm_debug_conv_set_trap(int on) {
+    int prev = 1;
+    cudaMemcpyFromSymbol(&prev, g_conv_trap, sizeof(int));
+    on = on ? 1 : 0;
+    cudaMemcpyToSymbol(g_conv_trap, &on, sizeof(int));
+    dsm_debug_wgrad_set_trap(on);
+    return prev;
 }
 
 // number of pipeline waits that timed out since the library was loaded (0 in a healthy run)

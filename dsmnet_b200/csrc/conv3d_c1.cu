@@ -161,6 +161,7 @@ extern "C" size_t dsm_conv3d_c1_bwd_workspace_bytes(void) { return (size_t)C1_MA
 extern "C" int dsm_conv3d_c1_bwd(const void* x, const float* gy, const float* w, void* gx, float* dw,
                                  int B, int D, int H, int W, int Do, int Ho, int Wo, int transposed,
                                  void* ws, size_t ws_bytes, void* stream) {
+    DsmDeviceGuard dsm_guard_(x);
     if (!x || !gy || !w || !gx || !dw || !ws || B < 1 || D < 1 || H < 1 || W < 1 || Do < 1 || Ho < 1 || Wo < 1) return DSM_EINVAL;
     if (ws_bytes < dsm_conv3d_c1_bwd_workspace_bytes()) return DSM_EINVAL;
     if (!dsm_aligned16(x) || !dsm_aligned16(gx)) return DSM_EALIGN;

@@ -217,20 +217,24 @@ struct Geom {
 };
 
 __device__ unsigned int g_wgrad_timeouts = 0;
+__device__ int g_wgrad_trap = 1;                 // see conv3d.cu: a timed-out wait is fatal unless bring-up mode is on
 
 __device__ __forceinline__ unsigned long long gtimer() {
     unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t;
 }
-// bounded wait (a wedged pipeline must not hang the GPU): gives up after limit_ns or as soon as any thread gave up
-__device__ __forceinline__ bool wait_bar(uint32_t bar, uint32_t parity, unsigned long long limit_ns = 200000000ULL) {
+// bounded wait (a wedged pipeline must not hang the GPU): after limit_ns the kernel traps (sticky CUDA error, nothing
+// can be silently wrong); in bring-up mode it gives up instead, and so does every later wait
+__device__ __forceinline__ bool wait_bar(uint32_t bar, uint32_t parity, unsigned long long limit_ns = 2000000000ULL) {
     if (ptx::mbar_try_wait(bar, parity)) return true;
     unsigned long long t0 = 0;
     for (uint32_t spins = 1; ; ++spins) {
         if (ptx::mbar_try_wait(bar, parity)) return true;
         if ((spins & 4095u) == 0u) {
             if (t0 == 0) t0 = gtimer();
-            if (gtimer() - t0 > limit_ns || *reinterpret_cast<volatile unsigned int*>(&g_wgrad_timeouts)) {
+            const bool trap = *reinterpret_cast<volatile int*>(&g_wgrad_trap) != 0;
+            if (gtimer() - t0 > limit_ns || (!trap && *reinterpret_cast<volatile unsigned int*>(&g_wgrad_timeouts))) {
                 atomicAdd(&g_wgrad_timeouts, 1u);
+                if (trap) __trap();
                 return false;
             }
         }
@@ -540,6 +544,7 @@ extern "C" int dsm_conv3d_wgrad(const void* anchor, const void* partner, float* 
                                 int B, int Ca, int Cb, int Da, int Ha, int Wa, int Dp, int Hp, int Wp, int stride,
                                 int Ca_out, int Cb_out, const float* scale_a, const float* scale_b, int accumulate,
                                 void* ws, size_t ws_bytes, void* stream) {
+    DsmDeviceGuard dsm_guard_(anchor);
     if (!anchor || !partner || !dw || !ws || B <= 0 || Da <= 0 || Ha <= 0 || Wa <= 0 || Dp <= 0 || Hp <= 0 || Wp <= 0) return DSM_EINVAL;
     if (stride != 1 && stride != 2) return DSM_EINVAL;
     if (Ca_out <= 0 || Ca_out > Ca || Cb_out <= 0 || Cb_out > Cb) return DSM_EINVAL;
@@ -605,6 +610,11 @@ extern "C" int dsm_debug_wgrad_mode(int mode) {
     if (mode == 0 || mode == 1) g_wgrad_mode = mode;
     return prev;
 }
+extern "C" int dsm_debug_wgrad_set_trap(int on) {
+    on = on ? 1 : 0;
+    return (int)cudaMemcpyToSymbol(tc::g_wgrad_trap, &on, sizeof(int));
+}
+
 extern "C" int dsm_debug_wgrad_timeouts(void) {
     unsigned int v = 0;
     cudaMemcpyFromSymbol(&v, tc::g_wgrad_timeouts, sizeof(v));

@@ -480,6 +480,7 @@ corr1d_bwd_right_kernel(const float* __restrict__ g, const float* __restrict__ f
 
 extern "C" int dsm_corr1d_fwd(const float* fL, const float* fR, float* out,
                               int B, int C, int H, int W, int D, int stride, void* stream) {
+    DsmDeviceGuard dsm_guard_(fL);
     if (!fL || !fR || !out || B <= 0 || C <= 0 || H <= 0 || W <= 0 || D <= 0) return DSM_EINVAL;
     if (stride != 1 && stride != 2) return DSM_EUNSUPPORTED;
     if (H > 65535 || B > 65535) return DSM_EUNSUPPORTED;
@@ -538,6 +539,7 @@ extern "C" int dsm_corr1d_fwd(const float* fL, const float* fR, float* out,
 
 extern "C" int dsm_corr1d_bwd(const float* gout, const float* fL, const float* fR, float* gL, float* gR,
                               int B, int C, int H, int W, int D, int stride, void* stream) {
+    DsmDeviceGuard dsm_guard_(gout);
     if (!gout || !fL || !fR || !gL || !gR || B <= 0 || C <= 0 || H <= 0 || W <= 0 || D <= 0) return DSM_EINVAL;
     if (stride < 1 || stride > 4) return DSM_EUNSUPPORTED;
     if (H > 65535 || B > 65535) return DSM_EUNSUPPORTED;

@@ -441,6 +441,7 @@ upsample_softargmin_bwd_kernel(const float* __restrict__ cost, const float* __re
 }  // namespace
 
 extern "C" int dsm_softargmin_fwd(const float* cost, float* disp, int B, int D, int H, int W, float sign, void* stream) {
+    DsmDeviceGuard dsm_guard_(cost);
     if (!cost || !disp || B <= 0 || D <= 0 || H <= 0 || W <= 0) return DSM_EINVAL;
     if (B > 65535) return DSM_EUNSUPPORTED;
     const long long HW = (long long)H * W;
@@ -459,6 +460,7 @@ extern "C" int dsm_softargmin_fwd(const float* cost, float* disp, int B, int D, 
 
 extern "C" int dsm_softargmin_bwd(const float* cost, const float* disp, const float* gdisp, float* gcost,
                                   int B, int D, int H, int W, float sign, void* stream) {
+    DsmDeviceGuard dsm_guard_(cost);
     if (!cost || !disp || !gdisp || !gcost || B <= 0 || D <= 0 || H <= 0 || W <= 0) return DSM_EINVAL;
     if (B > 65535) return DSM_EUNSUPPORTED;
     const long long HW = (long long)H * W;
@@ -467,6 +469,7 @@ extern "C" int dsm_softargmin_bwd(const float* cost, const float* disp, const fl
 }
 
 extern "C" int dsm_disparity_regression_fwd(const float* prob, float* disp, int B, int D, int H, int W, void* stream) {
+    DsmDeviceGuard dsm_guard_(prob);
     if (!prob || !disp || B <= 0 || D <= 0 || H <= 0 || W <= 0) return DSM_EINVAL;
     if (B > 65535) return DSM_EUNSUPPORTED;
     const long long HW = (long long)H * W;
@@ -475,6 +478,7 @@ extern "C" int dsm_disparity_regression_fwd(const float* prob, float* disp, int 
 }
 
 extern "C" int dsm_disparity_regression_bwd(const float* gdisp, float* gprob, int B, int D, int H, int W, void* stream) {
+    DsmDeviceGuard dsm_guard_(gdisp);
     if (!gdisp || !gprob || B <= 0 || D <= 0 || H <= 0 || W <= 0) return DSM_EINVAL;
     if (B > 65535) return DSM_EUNSUPPORTED;
     const long long HW = (long long)H * W;
@@ -503,11 +507,13 @@ static int upsample_softargmin_fwd_impl(const float* cost_lr, float* disp, float
 
 extern "C" int dsm_upsample_softargmin_fwd(const float* cost_lr, float* disp, int B, int Dl, int Hl, int Wl,
                                            int D, int H, int W, int align_corners, void* stream) {
+    DsmDeviceGuard dsm_guard_(cost_lr);
     return upsample_softargmin_fwd_impl(cost_lr, disp, nullptr, B, Dl, Hl, Wl, D, H, W, align_corners, stream);
 }
 
 extern "C" int dsm_upsample_softargmin_fwd_lse(const float* cost_lr, float* disp, float* lse2, int B, int Dl, int Hl, int Wl,
                                                int D, int H, int W, int align_corners, void* stream) {
+    DsmDeviceGuard dsm_guard_(cost_lr);
     if (!lse2) return DSM_EINVAL;
     return upsample_softargmin_fwd_impl(cost_lr, disp, lse2, B, Dl, Hl, Wl, D, H, W, align_corners, stream);
 }
@@ -515,6 +521,7 @@ extern "C" int dsm_upsample_softargmin_fwd_lse(const float* cost_lr, float* disp
 extern "C" int dsm_upsample_softargmin_bwd(const float* cost_lr, const float* disp, const float* lse2, const float* gdisp,
                                            float* gcost_lr, int B, int Dl, int Hl, int Wl,
                                            int D, int H, int W, int align_corners, void* stream) {
+    DsmDeviceGuard dsm_guard_(cost_lr);
     if (!cost_lr || !disp || !lse2 || !gdisp || !gcost_lr || B <= 0 || Dl <= 0 || Hl <= 0 || Wl <= 0 || D <= 0 || H <= 0 || W <= 0)
         return DSM_EINVAL;
     if (H > 65535 || B > 65535) return DSM_EUNSUPPORTED;

@@ -190,7 +190,11 @@ concat_bwd_ndhwc_kernel(const uint4* __restrict__ g, float* __restrict__ gL, flo
     extern __shared__ __align__(16) float s_out[];        // [2C][W + 1]
     const int y = blockIdx.x, b = blockIdx.y;
     const int cpv = (2 * C) / 8, half = cpv / 2;
-    const int nchunks = W * cpv;
+    // blockIdx.z = x-chunk: a CTA owns at most CB_THREADS*CB_MAXK/cpv pixels of the row, so any width works
+    const int wchunk = (CB_THREADS * CB_MAXK) / cpv;
+    const int x0 = blockIdx.z * wchunk;
+    const int wc = min(wchunk, W - x0);                     // pixels of this CTA
+    const int nchunks = wc * cpv;
     const int Wp = W + 2, Hp = H + 2;
     const size_t plane = (size_t)Hp * Wp * cpv;            // 16-byte chunks per padded plane
     const uint4* row = g + (((size_t)b * (D + 2) + 1) * Hp + (y + 1)) * Wp * cpv + cpv;   // voxel (d=0, y, x=0)
@@ -201,8 +205,8 @@ concat_bwd_ndhwc_kernel(const uint4* __restrict__ g, float* __restrict__ gL, flo
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
         const int idx = threadIdx.x + k * CB_THREADS;
-        xk[k] = idx < nchunks ? idx / cpv : -1;
-        offk[k] = idx;                                     // = x * cpv + j
+        xk[k] = idx < nchunks ? x0 + idx / cpv : -1;
+        offk[k] = x0 * cpv + idx;                          // = x * cpv + j
     }
     const bool second = (threadIdx.x % cpv) >= half;       // CB_THREADS % cpv == 0: the same half for every k
     const int step = second ? ((mode == DSM_VOL_GC_RIGHT) ? -cpv : cpv) : 0;      // chunk offset per unit of d
@@ -224,23 +228,23 @@ concat_bwd_ndhwc_kernel(const uint4* __restrict__ g, float* __restrict__ gL, flo
             }
         }
     }
-    const int pitch = W + 1;
+    const int pitch = wc + 1;
 #pragma unroll
     for (int k = 0; k < CB_MAXK; ++k) {
         const int idx = threadIdx.x + k * CB_THREADS;
         if (idx >= nchunks) break;
-        const int x = idx / cpv, j = idx - x * cpv;
+        const int x = idx / cpv, j = idx - x * cpv;          // x local to the chunk
 #pragma unroll
         for (int i = 0; i < 8; ++i) s_out[(j * 8 + i) * pitch + x] = acc[k][i];
     }
     __syncthreads();
     // channel ch < C is the first half: fL (fR for GC_RIGHT); ch >= C the other map
-    for (int i = threadIdx.x; i < 2 * C * W; i += CB_THREADS) {
-        const int ch = i / W, x = i - ch * W;
+    for (int i = threadIdx.x; i < 2 * C * wc; i += CB_THREADS) {
+        const int ch = i / wc, x = i - ch * wc;
         const bool first = ch < C;
         const int c = first ? ch : ch - C;
         float* dst = (first != (mode == DSM_VOL_GC_RIGHT)) ? gL : gR;
-        dst[(((size_t)b * C + c) * H + y) * W + x] = s_out[ch * pitch + x];
+        dst[(((size_t)b * C + c) * H + y) * W + x0 + x] = s_out[ch * pitch + x];
     }
 }
 
@@ -300,6 +304,7 @@ unpack_ndhwc_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, 
 extern "C" int dsm_concat_volume_fwd(const float* fL, const float* fR, void* out,
                                      int B, int C, int D, int H, int W,
                                      int mode, int out_dtype, int out_layout, void* stream) {
+    DsmDeviceGuard dsm_guard_(fL);
     if (!fL || !fR || !out || B <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0) return DSM_EINVAL;
     if (mode < DSM_VOL_PSM || mode > DSM_VOL_GC_RIGHT) return DSM_EINVAL;
     if (B > 65535 || 2 * C > 65535) return DSM_EUNSUPPORTED;
@@ -332,17 +337,20 @@ extern "C" int dsm_concat_volume_fwd(const float* fL, const float* fR, void* out
 extern "C" int dsm_concat_volume_bwd(const void* gout, float* gL, float* gR,
                                      int B, int C, int D, int H, int W,
                                      int mode, int dtype, int layout, void* stream) {
+    DsmDeviceGuard dsm_guard_(gout);
     if (!gout || !gL || !gR || B <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0) return DSM_EINVAL;
     if (mode < DSM_VOL_PSM || mode > DSM_VOL_GC_RIGHT) return DSM_EINVAL;
     if (dtype == DSM_BF16 && layout == DSM_NDHWC_PADDED) {
-        if (C % 8 != 0 || CB_THREADS % (2 * C / 8) != 0 || (long long)W * (2 * C / 8) > CB_THREADS * CB_MAXK || H > 65535 || B > 65535)
+        if (C % 8 != 0 || CB_THREADS % (2 * C / 8) != 0 || H > 65535 || B > 65535)
             return DSM_EUNSUPPORTED;
         if (!dsm_aligned16(gout)) return DSM_EALIGN;
-        const size_t smem = (size_t)2 * C * (W + 1) * sizeof(float);
+        const int wchunk = (CB_THREADS * CB_MAXK) / (2 * C / 8);       // pixels per CTA; wider rows take several CTAs
+        const int xchunks = dsm_ceil_div(W, wchunk);
+        const size_t smem = (size_t)2 * C * ((W < wchunk ? W : wchunk) + 1) * sizeof(float);
         if (smem > 200 * 1024) return DSM_EUNSUPPORTED;
         cudaError_t e = cudaFuncSetAttribute(concat_bwd_ndhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        concat_bwd_ndhwc_kernel<<<dim3(H, B), CB_THREADS, smem, (cudaStream_t)stream>>>((const uint4*)gout, gL, gR, C, D, H, W, mode);
+        concat_bwd_ndhwc_kernel<<<dim3(H, B, xchunks), CB_THREADS, smem, (cudaStream_t)stream>>>((const uint4*)gout, gL, gR, C, D, H, W, mode);
         return dsm_launch_status();
     }
     if (dtype != DSM_F32 || layout != DSM_NCDHW) return DSM_EUNSUPPORTED;
@@ -374,6 +382,7 @@ pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
 }
 
 extern "C" int dsm_pack_weight(const float* w, void* out, int Cout, int Cin, int mode, void* stream) {
+    DsmDeviceGuard dsm_guard_(w);
     if (!w || !out || Cout < 1 || Cin < 1 || mode < 0 || mode > 2) return DSM_EINVAL;
     const int CoutP = Cout < 16 ? 16 : Cout;
     const long long n = 27LL * CoutP * Cin;
@@ -383,6 +392,7 @@ extern "C" int dsm_pack_weight(const float* w, void* out, int Cout, int Cin, int
 }
 
 extern "C" int dsm_pack_ndhwc(const float* x, void* y, int B, int C, int D, int H, int W, void* stream) {
+    DsmDeviceGuard dsm_guard_(x);
     if (!x || !y || B <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0) return DSM_EINVAL;
     if (C % 8 != 0 || D + 2 > 65535 || B > 65535) return DSM_EUNSUPPORTED;
     if (!dsm_aligned16(y)) return DSM_EALIGN;
@@ -395,6 +405,7 @@ extern "C" int dsm_pack_ndhwc(const float* x, void* y, int B, int C, int D, int 
 }
 
 extern "C" int dsm_unpack_ndhwc(const void* x, float* y, int B, int C, int D, int H, int W, void* stream) {
+    DsmDeviceGuard dsm_guard_(x);
     if (!x || !y || B <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0) return DSM_EINVAL;
     if (D > 65535 || B > 65535) return DSM_EUNSUPPORTED;
     const size_t smem = (size_t)W * (C + 2) * sizeof(__nv_bfloat16);

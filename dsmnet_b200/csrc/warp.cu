@@ -129,6 +129,7 @@ warp_indices_kernel(const float* __restrict__ disp, const float* __restrict__ ro
 // [B][H][W] int32 that dsm_warp_fwd/bwd use for every output pixel (same arithmetic as make_tap).
 extern "C" int dsm_warp_indices(const float* disp, const float* row, const float* col, int fliplr,
                                 int* x0, int* y0, int B, int H0, int W0, int H, int W, void* stream) {
+    DsmDeviceGuard dsm_guard_(disp);
     if (!disp || !row || !col || !x0 || !y0 || B <= 0) return DSM_EINVAL;
     if (H0 < 2 || W0 < 2 || H < 2 || W < 2) return DSM_EINVAL;
     if (H > 65535 || B > 65535) return DSM_EUNSUPPORTED;
@@ -140,6 +141,7 @@ extern "C" int dsm_warp_indices(const float* disp, const float* row, const float
 extern "C" int dsm_warp_fwd(const float* src, const float* disp, const float* row, const float* col,
                             float delt, int fliplr, float* out,
                             int B, int C, int H0, int W0, int H, int W, void* stream) {
+    DsmDeviceGuard dsm_guard_(src);
     if (!src || !disp || !row || !col || !out || B <= 0 || C <= 0) return DSM_EINVAL;
     if (H0 < 2 || W0 < 2 || H < 2 || W < 2) return DSM_EINVAL;            // imwrap.py:48
     if (H > 65535 || B > 65535) return DSM_EUNSUPPORTED;
@@ -151,6 +153,7 @@ extern "C" int dsm_warp_fwd(const float* src, const float* disp, const float* ro
 extern "C" int dsm_warp_bwd(const float* gout, const float* src, const float* disp, const float* row,
                             const float* col, float delt, int fliplr, float* gsrc, float* gdisp,
                             int B, int C, int H0, int W0, int H, int W, void* stream) {
+    DsmDeviceGuard dsm_guard_(gout);
     if (!gout || !src || !disp || !row || !col || !gsrc || !gdisp || B <= 0 || C <= 0) return DSM_EINVAL;
     if (H0 < 2 || W0 < 2 || H < 2 || W < 2) return DSM_EINVAL;
     if (H > 65535 || B > 65535) return DSM_EUNSUPPORTED;

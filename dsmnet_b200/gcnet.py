@@ -6,7 +6,8 @@ soft-argmin of MINUS the cost (:104-111).
 ``l19.1.running_var``, ..., bare ``l37.weight``) so that the ``layer3d.*`` part of a reference
 ``state_dict`` loads unchanged.  Inference: eval-mode BatchNorm folded into the conv epilogue, everything
 fused.  With gradients enabled (train mode) the same graph runs with autograd: convolutions forward /
-backward on the sm_100a kernels, BatchNorm with batch statistics, ReLU and skip adds as stock ops.  The 2-D trunk ``feature2d`` (:14-29) is a caller of the path and stays
+backward on the sm_100a kernels, BatchNorm (batch statistics) + ReLU + skip adds (cropped where sizes are odd) on the
+fused streaming kernels of ``train3d``.  The 2-D trunk ``feature2d`` (:14-29) is a caller of the path and stays
 stock PyTorch in the reference; ``GCNetHotPath`` therefore starts from the two feature maps.
 """
 from __future__ import annotations
@@ -59,8 +60,20 @@ class feature3d(nn.Module):
         self._ws: Dict[Tuple, dict] = {}
 
     # -- packed weights + folded BatchNorm, rebuilt when a parameter changes ------------------------
+    def _wants_autograd(self, *inputs):
+        if self.training:
+            return True
+        if torch.is_grad_enabled() and (any(t.requires_grad for t in inputs) or any(p.requires_grad for p in self.parameters())):
+            if not getattr(self, "_warned_eval_grad", False):
+                import warnings
+                warnings.warn("dsmnet_b200: eval-mode forward with autograd enabled takes the differentiable (unfused) path; "
+                              "wrap inference in torch.no_grad() for the fused kernels", stacklevel=3)
+                self._warned_eval_grad = True
+            return True
+        return False
+
     def _get_plan(self, device):
-        key = (str(device),) + tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+        key = (str(device),) + tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()) if t.dim() > 0)
         if self._plan is None or key != self._plan_key:
             plan = {}
             for name in ("l19", "l20", "l21", "l22", "l23", "l24", "l25", "l26", "l27", "l28", "l29", "l30", "l31", "l32",
@@ -102,7 +115,7 @@ class feature3d(nn.Module):
 
     def aggregate_train(self, vol: PaddedVolume) -> torch.Tensor:
         """The same graph with autograd (gcnet.py:65-101 under model.train()): convolutions fwd/bwd on the sm_100a
-        kernels, BatchNorm with batch statistics / ReLU / skip adds as stock PyTorch ops (dsmnet_b200/train3d.py)."""
+        kernels, BatchNorm with batch statistics + ReLU + (cropped) skip adds on the kernels of dsmnet_b200/train3d.py."""
         from . import train3d as T
 
         def g(name, x, residual=None):
@@ -119,7 +132,7 @@ class feature3d(nn.Module):
 
     def aggregate(self, vol: PaddedVolume) -> torch.Tensor:
         """x37 of gcnet.py:65-101 as fp32 [B, 2D, 2H, 2W]."""
-        if self.training or torch.is_grad_enabled() and (vol.data.requires_grad or any(p.requires_grad for p in self.parameters())):
+        if self._wants_autograd(vol.data):
             return self.aggregate_train(vol)
         dev = vol.data.device
         p = self._get_plan(dev)
@@ -172,8 +185,7 @@ class GCNetHotPath(nn.Module):
         self.layer3d = feature3d(32)
 
     def forward(self, fL, fR):
-        if self.training or torch.is_grad_enabled() and (fL.requires_grad or fR.requires_grad or
-                                                         any(p.requires_grad for p in self.parameters())):
+        if self.training or self.layer3d._wants_autograd(fL, fR):
             vol = concat_volume_padded(fL, fR, self.D, "gc")                 # differentiable, padded bf16 directly
         else:
             vol = concat_volume(fL, fR, self.D, "gc", padded_bf16=True)

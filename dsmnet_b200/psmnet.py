@@ -13,7 +13,8 @@ path from the two feature maps on — concat volume (stackhourglass.py:124-133),
   ->  3 fused upsample+soft-argmin kernels.
 Inference: eval-mode BatchNorm folded into the conv epilogue, everything fused.  With gradients enabled
 (train mode, or eval-mode with parameters/inputs that require grad) the same graph runs through
-``aggregate_train``: convolutions forward/backward on the sm_100a kernels, BatchNorm/ReLU/adds as stock ops.
+``aggregate_train``: convolutions forward/backward on the sm_100a kernels, BatchNorm (batch statistics or frozen) +
+ReLU + skip adds on the fused streaming kernels of ``train3d`` (no stock-PyTorch ops on the volumes).
 """
 from __future__ import annotations
 
@@ -122,8 +123,30 @@ class PSMNetHotPath(nn.Module):
         self._ws: Dict[Tuple, dict] = {}
 
     # -- plan / workspace caches ------------------------------------------------------------
+    _STACK = ("dres0", "dres1", "dres2", "dres3", "dres4", "classif1", "classif2", "classif3")
+
+    def _stack_tensors(self):
+        """Parameters and buffers of the 3-D stack only (a subclass may add a 2-D trunk with its own plan)."""
+        return [t for n in self._STACK for m in (getattr(self, n),) for t in list(m.parameters()) + list(m.buffers())
+                if t.dim() > 0]                                     # num_batches_tracked does not enter the plan
+
+    def _wants_autograd(self, fL, fR):
+        """The autograd graph is needed in train mode, or when gradients are on and something on the path asks for one.
+        model.eval() without torch.no_grad() lands here too (parameters require grad by default): warn once, because that
+        path computes batch-norm-frozen training kernels and saves activations — inference should run under no_grad."""
+        if self.training:
+            return True
+        if torch.is_grad_enabled() and (fL.requires_grad or fR.requires_grad or any(t.requires_grad for t in self._stack_tensors())):
+            if not getattr(self, "_warned_eval_grad", False):
+                import warnings
+                warnings.warn("dsmnet_b200: eval-mode forward with autograd enabled takes the differentiable (unfused) path; "
+                              "wrap inference in torch.no_grad() for the fused kernels", stacklevel=3)
+                self._warned_eval_grad = True
+            return True
+        return False
+
     def _get_plan(self, device):
-        key = (str(device),) + tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+        key = (str(device),) + tuple((t.data_ptr(), t._version) for t in self._stack_tensors())
         if self._plan is None or key != self._plan_key:
             self._plan = _Plan(self, device, self.variant)
             self._plan_key = key
@@ -158,7 +181,7 @@ class PSMNetHotPath(nn.Module):
     # -- the path -----------------------------------------------------------------------------
     def aggregate_train(self, fL, fR):
         """The same graph with autograd (stackhourglass.py:123-149): convolutions fwd/bwd on the sm_100a kernels,
-        BatchNorm with batch statistics / ReLU / adds as stock PyTorch ops (dsmnet_b200/train3d.py)."""
+        BatchNorm (batch statistics in train mode) + ReLU + skip adds on the fused kernels of dsmnet_b200/train3d.py."""
         from . import train3d as T
         D = self.maxdisp // 4
         vol = concat_volume_padded(fL, fR, D, "psm")      # padded bf16 directly; backward sums over d into NCHW fp32
@@ -194,8 +217,7 @@ class PSMNetHotPath(nn.Module):
         `head(i, cost)` (inference with the second stream only): called on the classifier stream right after cost{i+1}
         exists, so that the heads of cost1 / cost2 run beside the later hourglasses instead of after them; returns
         True if it was used (the caller then skips its own head launch)."""
-        if self.training or torch.is_grad_enabled() and (fL.requires_grad or fR.requires_grad or
-                                                         any(p.requires_grad for p in self.parameters())):
+        if self._wants_autograd(fL, fR):
             return self.aggregate_train(fL, fR)
         B, C, H, W = fL.shape
         D = self.maxdisp // 4
@@ -252,8 +274,7 @@ class PSMNetHotPath(nn.Module):
         return costs
 
     def forward(self, fL, fR, out_hw):
-        train = self.training or torch.is_grad_enabled() and (fL.requires_grad or fR.requires_grad or
-                                                              any(p.requires_grad for p in self.parameters()))
+        train = self._wants_autograd(fL, fR)
         if CLS_SIDE_STREAM and EARLY_HEADS and not train:
             # each head is launched on the classifier stream as soon as its cost exists: only the head of cost3 is left
             # on the critical path (one stacked launch of all three after the last classifier cost ~95 us more)

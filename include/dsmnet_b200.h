@@ -156,6 +156,16 @@ int dsm_conv3d_c1_bwd(const void* x, const float* gy, const float* w, void* gx, 
                       int B, int D, int H, int W, int Do, int Ho, int Wo, int transposed,
                       void* ws, size_t ws_bytes, void* stream);
 
+/* cropped skip add of the training path (myadd_3d / myAdd3d crop-to-min, stackhourglass.py:10-20, util_fun.py:41-51):
+ * `full` is a padded bf16 volume of extent (Dn,Hn,Wn) (the BatchNorm'ed deconv output, statistics over all of it as in
+ * the reference), residual / z have the smaller extent (Do,Ho,Wo): z = act(crop(full) + residual), relu 0/1 (after the
+ * add).  Backward: g = gz masked by z > 0 when relu; gfull = g inside the crop and 0 elsewhere (whole padded array
+ * written); gres (optional) = g on the interior voxels (the caller zeroes its rim).                                  */
+int dsm_crop_add_fwd(const void* full, const void* residual, void* z, int B, int C,
+                     int Dn, int Hn, int Wn, int Do, int Ho, int Wo, int relu, void* stream);
+int dsm_crop_add_bwd(const void* gz, const void* z, void* gfull, void* gres, int B, int C,
+                     int Dn, int Hn, int Wn, int Do, int Ho, int Wo, int relu, void* stream);
+
 /* diagnostics: wgrad kernel selection (0 = tcgen05 for stride-1 layers [default], 1 = warp-level everywhere;
  * returns the previous mode) and the count of bounded pipeline waits that expired (0 in a healthy run)      */
 int dsm_debug_wgrad_mode(int mode);
@@ -225,7 +235,11 @@ int dsm_conv3d_fwd_ex(const void* x, const void* w_packed, const float* scale, c
                       int B, int Cin, int Cout, int D, int H, int W,
                       int stride, int transposed, int relu, int y_dtype,
                       int Do, int Ho, int Wo, int variant, void* stream);
-/* number of bounded pipeline waits that expired inside conv kernels since load (0 when healthy) */
+/* A pipeline wait inside a conv / wgrad kernel that is not satisfied within 2 s is FATAL by default: the kernel traps
+ * and the context reports a launch failure (nothing can be silently wrong).  dsm_debug_conv_set_trap(0) selects the
+ * bring-up mode instead (the wait gives up, the kernel finishes on garbage, the counter below tells); returns the
+ * previous setting.  dsm_debug_conv_timeouts: expired waits since load (0 when healthy).                          */
+int dsm_debug_conv_set_trap(int on);
 int dsm_debug_conv_timeouts(void);
 /* bring-up aid (library built with -DDSM_CONV_TRACE): host-mapped int[4] progress slots */
 int dsm_debug_conv_set_progress(int* host_mapped);

@@ -575,15 +575,33 @@ def gcnet_random_params(seed: int = 0, calibrate_on: Optional[torch.Tensor] = No
 # training-mode restatement (BatchNorm with batch statistics), differentiable with torch autograd
 # ------------------------------------------------------------------------------------------
 
-def _convbn_train(params, prefix, x, stride=1, transposed=False, residual=None, relu=0, operand_dtype=None, eps=1e-5):
+class _RoundST(torch.autograd.Function):
+    """Number-format emulation for the training path: forward rounds to `dtype` (straight-through), backward rounds the
+    gradient that flows through this point to `grad_dtype` — the CUDA path stores activations AND activation gradients
+    (conv-output gradients, conv-input gradients, skip gradients) in bf16; weight gradients stay fp32."""
+
+    @staticmethod
+    def forward(ctx, t, dtype, grad_dtype):
+        ctx.grad_dtype = grad_dtype
+        return t if dtype is None else t.to(dtype).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return (g if ctx.grad_dtype is None else g.to(ctx.grad_dtype).float()), None, None
+
+
+def _convbn_train(params, prefix, x, stride=1, transposed=False, residual=None, relu=0, operand_dtype=None, eps=1e-5,
+                  grad_dtype=None):
     """convbn_3d in TRAIN mode (submodule.py:16-19 under model.train()): conv -> batch-stat BatchNorm -> [+res] -> [relu].
     `operand_dtype=torch.bfloat16` rounds conv operands and the stored block output like the kernels do (straight-through
-    for autograd)."""
+    for autograd); `grad_dtype` additionally rounds the activation gradients at the same points."""
     def rnd(t):
-        return t if operand_dtype is None else t + (t.to(operand_dtype).float() - t).detach()
+        return t if operand_dtype is None else _RoundST.apply(t, operand_dtype, grad_dtype)
     w = params[prefix + ".0.weight"]
-    y = F.conv_transpose3d(rnd(x), rnd(w), None, stride=2, padding=1, output_padding=1) if transposed else \
-        F.conv3d(rnd(x), rnd(w), None, stride=stride, padding=1)
+    if operand_dtype is not None:
+        w = _RoundST.apply(w, operand_dtype, None)                # weight gradients are fp32
+    y = F.conv_transpose3d(rnd(x), w, None, stride=2, padding=1, output_padding=1) if transposed else \
+        F.conv3d(rnd(x), w, None, stride=stride, padding=1)
     y = rnd(y)                                            # the conv kernel stores bf16
     y = F.batch_norm(y, None, None, params[prefix + ".1.weight"], params[prefix + ".1.bias"], True, 0.1, eps)
     if residual is not None:
@@ -594,12 +612,12 @@ def _convbn_train(params, prefix, x, stride=1, transposed=False, residual=None, 
 
 
 def psmnet_hotpath_train(params: Dict[str, torch.Tensor], fL: torch.Tensor, fR: torch.Tensor, maxdisp: int,
-                         out_hw: Tuple[int, int], align_corners: bool = True, operand_dtype=None):
+                         out_hw: Tuple[int, int], align_corners: bool = True, operand_dtype=None, grad_dtype=None):
     """PSMNet.forward from the feature maps on in TRAIN mode (stackhourglass.py:123-168 under model.train()):
     the graph of psmnet_hotpath with batch-statistics BatchNorm; every tensor in `params` / fL / fR may require grad."""
     od = operand_dtype
     cost = concat_volume(fL, fR, maxdisp // 4, "psm")
-    cb = lambda p, x, s=1, t=False, r=None, relu=0: _convbn_train(params, p, x, s, t, r, relu, od)
+    cb = lambda p, x, s=1, t=False, r=None, relu=0: _convbn_train(params, p, x, s, t, r, relu, od, grad_dtype=grad_dtype)
     c0 = cb("dres0.0", cost, relu=1); c0 = cb("dres0.2", c0, relu=1)
     t = cb("dres1.0", c0, relu=1); cost0 = cb("dres1.2", t, r=c0)
 
@@ -619,7 +637,7 @@ def psmnet_hotpath_train(params: Dict[str, torch.Tensor], fL: torch.Tensor, fR: 
         t = cb(p + ".0", x, relu=1)
         w = params[p + ".2.weight"]
         if od is not None:
-            w = w + (w.to(od).float() - w).detach()
+            w = _RoundST.apply(w, od, None)
         return F.conv3d(t, w, None, stride=1, padding=1)
     cost1 = classif("classif1", out1); cost2 = classif("classif2", out2) + cost1; cost3 = classif("classif3", out3) + cost2
     size = [maxdisp, out_hw[0], out_hw[1]]
@@ -627,18 +645,18 @@ def psmnet_hotpath_train(params: Dict[str, torch.Tensor], fL: torch.Tensor, fR: 
 
 
 def gcnet_hotpath_train(params: Dict[str, torch.Tensor], fL: torch.Tensor, fR: torch.Tensor, maxdisp: int, operand_dtype=None,
-                        eps: float = 1e-5) -> torch.Tensor:
+                        eps: float = 1e-5, grad_dtype=None) -> torch.Tensor:
     """gcnet.forward from the feature maps on in TRAIN mode (gcnet.py:129-137, feature3d :65-111 under model.train()):
     conv+bias -> batch-stat BatchNorm -> ReLU, skip adds after the activation; differentiable with torch autograd."""
     od = operand_dtype
 
-    def rnd(t):
-        return t if od is None else t + (t.to(od).float() - t).detach()
+    def rnd(t, gd=grad_dtype):
+        return t if od is None else _RoundST.apply(t, od, gd)
 
     def g(name, x, stride=1, transposed=False, residual=None):
         w, b = params[name + ".0.weight"], params[name + ".0.bias"]
-        y = F.conv_transpose3d(rnd(x), rnd(w), None, stride=2, padding=1, output_padding=1) if transposed else \
-            F.conv3d(rnd(x), rnd(w), None, stride=stride, padding=1)
+        y = F.conv_transpose3d(rnd(x), rnd(w, None), None, stride=2, padding=1, output_padding=1) if transposed else \
+            F.conv3d(rnd(x), rnd(w, None), None, stride=stride, padding=1)
         y = rnd(y) + b.view(1, -1, 1, 1, 1)
         y = F.relu(F.batch_norm(y, None, None, params[name + ".1.weight"], params[name + ".1.bias"], True, 0.1, eps))
         if residual is not None:
@@ -652,7 +670,7 @@ def gcnet_hotpath_train(params: Dict[str, torch.Tensor], fL: torch.Tensor, fR: t
     x26 = g("l26", g("l25", x24)); x34 = g("l34", x33, 2, True, x26)
     x23 = g("l23", g("l22", x21)); x35 = g("l35", x34, 2, True, x23)
     x20 = g("l20", g("l19", cost)); x36 = g("l36", x35, 2, True, x20)
-    x37 = F.conv_transpose3d(rnd(x36), rnd(params["l37.weight"]), params["l37.bias"], stride=2, padding=1, output_padding=1)
+    x37 = F.conv_transpose3d(rnd(x36), rnd(params["l37.weight"], None), params["l37.bias"], stride=2, padding=1, output_padding=1)
     return softargmin(x37.squeeze(1), -1.0).unsqueeze(1)
 
 

@@ -254,3 +254,23 @@ def selfsup_loss(loss_name, scale_disps, dispLs, dispL1s, imL, imR_src, imL1, im
     torch.manual_seed(seed)
     with pinned_torch():
         return L.lossesfun(imR_src, imL, dispLs, scale_disps, list(LeftTop), imR1_src, imL1, dispL1s, scale_disps, list(LeftTop))
+
+
+# ------------------------------------------------------------------------------------------------
+# TRAIN-mode runs of the reference's own 3-D stacks (batch-statistics BatchNorm, autograd): what pins
+# oracle.ops.psmnet_hotpath_train / gcnet_hotpath_train (tests/golden/make_golden_train.py, tests/test_oracle_vs_reference.py)
+# ------------------------------------------------------------------------------------------------
+
+def psmnet_train_from_features(net, fL, fR, maxdisp, H, W):
+    """stackhourglass.py:123-168 from the feature maps on with the reference's modules under net.train(); fL / fR and the
+    parameters may require grad (the volume loop of :124-133 is differentiable through its slice assignments)."""
+    net.train()
+    return psmnet_forward_from_features(net, fL, fR, maxdisp, H, W)
+
+
+def gcnet_train_from_features(net, fL, fR):
+    """gcnet.forward (:126-137) from the feature maps on with the reference's layer3d under net.train()."""
+    net.train()
+    vol = gc_volume(fL, fR, int(net.D))
+    with pinned_torch():
+        return net.layer3d(vol, "train")

@@ -144,3 +144,96 @@ def test_north_star_path_full_size_random_weights():
         d_emu = float((mine - e).abs().mean()); d_fmt = float((e - r).abs().mean()); d_ref = float((mine - r).abs().mean())
         print("%s: mean |ours-emu| %.4f, |emu-ref| %.4f, |ours-ref| %.4f px" % (name, d_emu, d_fmt, d_ref))
         assert d_emu < d_fmt and d_ref < 2.0 * d_fmt + 1e-3
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# BASELINE config 3 at its full size: GC-Net 256x512 crop, maxdisp 192 -> volume 64 x 96 x 128 x 256 (half resolution),
+# l36 output 32 x 96 x 128 x 256, l37 output fp32 192 x 256 x 512, encoder chain down to 6 x 8 x 16.
+# ------------------------------------------------------------------------------------------------------------------
+GD, GH, GW = 96, 128, 256
+
+
+@pytest.mark.parametrize("tap", [(1, 1, 1), (0, 0, 0), (2, 2, 2), (0, 2, 1)])
+def test_gc_fullsize_l19_delta_filter_is_a_shift(tap):
+    """64 -> 32 stride-1 plane-sharing kernel over the whole GC-Net volume extent (the 32-bit flat decode, every band/tile edge)"""
+    torch.manual_seed(10)
+    x = torch.randn(1, 64, GD, GH, GW, device="cuda").to(torch.bfloat16).float()
+    y = _run(x, _delta_weight(64, 32, tap, False), 1, False)
+    kd, kh, kw = tap
+    xp = F.pad(x[:, :32], (1, 1, 1, 1, 1, 1))
+    assert torch.equal(y, xp[:, :, kd:kd + GD, kh:kh + GH, kw:kw + GW])
+
+
+@pytest.mark.parametrize("tap", [(1, 1, 1), (0, 0, 0), (2, 2, 2), (1, 0, 2)])
+def test_gc_fullsize_stride2_chain_is_a_subsample(tap):
+    """l21 -> l24 -> l27 -> l30 geometry: four stride-2 convolutions 96x128x256 -> 6x8x16 (64 -> 64 ... -> 128), delta filters"""
+    torch.manual_seed(11)
+    x = torch.randn(1, 64, GD, GH, GW, device="cuda").to(torch.bfloat16).float()
+    kd, kh, kw = tap
+    ref = x
+    cur = x
+    for cout in (64, 64, 64, 128):
+        cin = cur.shape[1]
+        cur = _run(cur, _delta_weight(cin, cout, tap, False), 2, False)
+        d, h, w = ref.shape[2:]
+        rp = F.pad(ref, (1, 1, 1, 1, 1, 1))
+        ref = rp[:, :, kd:kd + d:2, kh:kh + h:2, kw:kw + w:2]
+        assert cur.shape[2:] == ref.shape[2:]
+        assert torch.equal(cur[:, :64], ref[:, :64]) and (cur.shape[1] == 64 or float(cur[:, 64:].abs().max()) == 0.0)
+    assert tuple(cur.shape) == (1, 128, 6, 8, 16)
+
+
+@pytest.mark.parametrize("tap", [(1, 1, 1), (0, 0, 0), (2, 2, 2), (2, 0, 1)])
+def test_gc_fullsize_l36_transposed_delta_filter(tap):
+    """l36: 64 -> 32 transposed (class-sharing kernel), 48x64x128 -> 96x128x256"""
+    torch.manual_seed(12)
+    x = torch.randn(1, 64, GD // 2, GH // 2, GW // 2, device="cuda").to(torch.bfloat16).float()
+    wt = _delta_weight(64, 32, tap, True)
+    y = _run(x, wt, 2, True)
+    ref = F.conv_transpose3d(x[:, :32], wt[:32].cuda(), stride=2, padding=1, output_padding=1)
+    assert y.shape == (1, 32, GD, GH, GW) and torch.equal(y, ref)
+
+
+@pytest.mark.parametrize("tap", [(1, 1, 1), (0, 0, 0), (2, 2, 2), (0, 1, 2)])
+def test_gc_fullsize_l37_fp32_output(tap):
+    """l37: 32 -> 1 transposed with the fp32 [192][256][512] output (one-warp-per-quadrant epilogue, 8-byte pair stores)"""
+    from dsmnet_b200.conv3d import FusedConv3d, conv_timeouts
+    from dsmnet_b200.volume_layout import PaddedVolume
+    torch.manual_seed(13)
+    x = torch.randn(1, 32, GD, GH, GW, device="cuda").to(torch.bfloat16).float()
+    wt = torch.zeros(32, 1, 3, 3, 3)
+    kd, kh, kw = tap
+    wt[5, 0, kd, kh, kw] = 1.0                                 # picks channel 5: exact in bf16 x fp32
+    y = FusedConv3d(wt.cuda(), None, None, 2, True, False)(PaddedVolume.from_ncdhw(x))
+    torch.cuda.synchronize()
+    assert conv_timeouts() == 0
+    ref = F.conv_transpose3d(x[:, 5:6], wt[5:6].cuda(), stride=2, padding=1, output_padding=1)[:, 0]
+    assert y.shape == (1, 2 * GD, 2 * GH, 2 * GW) and y.dtype == torch.float32
+    assert torch.equal(y, ref)
+
+
+def test_gcnet_full_size_vs_oracle():
+    """One 256x512 crop (feature maps 32 x 128 x 256, D = 96) through GCNetHotPath vs the CPU oracle: the gates of the
+    small-size tests (kernel error vs the bf16-emulating oracle, format error vs fp32) at BASELINE config 3's extents;
+    the numbers go to profiles/ through tools/parity_fullsize.py."""
+    from dsmnet_b200.gcnet import GCNetHotPath
+    from dsmnet_b200.conv3d import conv_timeouts
+    maxdisp = 192
+    fL, fR, disp2 = O.synthetic_stereo_features(GH, GW, d_lo=5.0, d_hi=40.0, seed=6)
+    cost = O.concat_volume(fL, fR, maxdisp // 2, "gc")
+    params = O.gcnet_random_params(seed=23, calibrate_on=cost)
+    ref = O.gcnet_hotpath(params, fL, fR, maxdisp)
+    emu = O.gcnet_hotpath(params, fL, fR, maxdisp, operand_dtype=(torch.bfloat16, torch.bfloat16))
+    del cost
+    m = GCNetHotPath(maxdisp)
+    m.load_state_dict({"layer3d." + k: v for k, v in params.items()}, strict=False)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        disp = m(fL.cuda(), fR.cuda()).cpu()
+    torch.cuda.synchronize()
+    assert conv_timeouts() == 0
+    assert disp.shape == ref.shape == (1, 1, 2 * GH, 2 * GW) and bool(torch.isfinite(disp).all())
+    d_emu = float((disp - emu).abs().mean()); d_fmt = float((emu - ref).abs().mean()); d_ref = float((disp - ref).abs().mean())
+    print("gcnet 256x512: mean |ours-emu| %.4f, |emu-ref| %.4f, |ours-ref| %.4f px" % (d_emu, d_fmt, d_ref))
+    assert d_emu < max(0.5 * d_fmt, 0.02)
+    assert d_ref < 2.0 * d_fmt + 0.02

@@ -107,3 +107,49 @@ def test_gc_layers(name, transposed, stride):
     scale, shift = O.fold_bn(cout, bn, g["bias"])
     y = O.conv3d_block(g["x"], g["weight"], scale, shift, stride, transposed, None, True)
     assert y.shape == g["y"].shape and rel_err(y, g["y"]) < 1e-5
+
+
+# ---- TRAIN mode: the oracle's batch-statistics restatements against the reference's own modules under .train() ---------
+# (fixtures: tests/golden/make_golden_train.py).  This is what pins the yardstick of the GPU training-parity tests.
+
+@pytest.mark.parametrize("name", ["psmnet_train", "psmnet_train_odd"])
+def test_psmnet_train_oracle_vs_reference_golden(name):
+    from helpers import PSM_TRAIN_GRADS, golden_grad, cosine, psm_train_loss
+    g = load_golden(name)
+    params = O.psmnet_random_params(seed=g["seed"])
+    req = lambda k, v: v.dim() == 5 or k.endswith(".1.weight") or k.endswith(".1.bias")
+    pr = {k: v.clone().requires_grad_(req(k, v)) for k, v in params.items()}
+    a = g["fL"].clone().requires_grad_(); b = g["fR"].clone().requires_grad_()
+    H, W = g["gt"].shape[-2:]
+    preds = O.psmnet_hotpath_train(pr, a, b, g["maxdisp"], (H, W))
+    loss = psm_train_loss(preds, g["gt"])
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
+    for mine, ref in zip(preds, (g["pred3"], g["pred2"], g["pred1"])):
+        assert mine.shape == ref.shape and (mine - ref).abs().max() < 5e-3
+    for mine, ref in ((a.grad, g["gL"]), (b.grad, g["gR"])):
+        assert cosine(mine, ref) > 0.9999 and rel_err(mine, ref) < 2e-2
+    for k in PSM_TRAIN_GRADS:
+        mine, ref = golden_grad(g, k, pr[k].grad)
+        assert cosine(mine, ref) > 0.9999 and rel_err(mine, ref) < 2e-2, k
+
+
+@pytest.mark.parametrize("name", ["gcnet_train", "gcnet_train_odd"])
+def test_gcnet_train_oracle_vs_reference_golden(name):
+    from helpers import GC_TRAIN_GRADS, golden_grad, cosine
+    g = load_golden(name)
+    params = O.gcnet_random_params(seed=g["seed"])
+    req = lambda k, v: v.dim() == 5 or k.endswith(".bias") or k.endswith(".1.weight")
+    pr = {k: v.clone().requires_grad_(req(k, v)) for k, v in params.items()}
+    a = g["fL"].clone().requires_grad_(); b = g["fR"].clone().requires_grad_()
+    disp = O.gcnet_hotpath_train(pr, a, b, g["maxdisp"])
+    assert disp.shape == g["disp"].shape and (disp - g["disp"]).abs().max() < 5e-3
+    gt = g["gt"][:, :, :disp.shape[2], :disp.shape[3]]
+    loss = (disp - gt).abs().mean()
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
+    for mine, ref in ((a.grad, g["gL"]), (b.grad, g["gR"])):
+        assert cosine(mine, ref) > 0.9999 and rel_err(mine, ref) < 2e-2
+    for k in GC_TRAIN_GRADS:
+        mine, ref = golden_grad(g, k, pr[k].grad)
+        assert cosine(mine, ref) > 0.9999 and rel_err(mine, ref) < 2e-2, k
