@@ -57,6 +57,10 @@ SIGNATURES = {
     "dsm_pack_weight": [_P, _P, _I, _I, _I, _P],
     "dsm_pack_ndhwc": [_P, _P, _I, _I, _I, _I, _I, _P],
     "dsm_unpack_ndhwc": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "dsm_conv2d_fwd": [_P, _P, _P, _P, _P, _P] + [_I] * 16 + [_P],
+    "dsm_conv2d_first_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "dsm_spp_workspace_bytes": [_I, _I, _I],
+    "dsm_spp_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, c_size_t, _P],
     "dsm_softargmin_fwd": [_P, _P, _I, _I, _I, _I, _F, _P],
     "dsm_softargmin_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "dsm_disparity_regression_fwd": [_P, _P, _I, _I, _I, _I, _P],

@@ -46,6 +46,14 @@ struct ConvGeom {
     int cls_begin[9];
     int a_off[27];           // FLAT/SHIFT: row offset of the tap; BOX: map | ow<<4 | oh<<5 | od<<6
     int w_row[27];           // first row of the tap in the packed weights
+    // generalisation to 2-D images (the feature-extraction trunks run on the same kernel): a 3-D volume has
+    // dpad = ri = ro = dil = 1, ldy = ldr = Cout, y_mode = y_f32
+    int dpad;                // rim planes along D: 1 for volumes, 0 for images (Di = Do = 1)
+    int ri, ro;              // rim width along H and W of the input / of the output and residual buffers
+    int dil;                 // dilation (stride-1 kernels): tap offsets and the kw row shift scale with it
+    int ldy, ldr;            // channels per voxel of the y / residual buffers (>= Cout: a channel slice of a wider tensor)
+    int y_mode;              // 0 padded NDHWC bf16; 1 fp32 single channel [B][Do][Ho][Wo]; 2 fp32 NCHW [B][Cout][Ho][Wo] (images)
+    int tx_bytes;            // bytes one pipeline stage receives (A rows * row bytes + the weight tiles)
 };
 
 __device__ int g_conv_timeouts = 0;
@@ -121,7 +129,6 @@ struct Cfg {
     static constexpr int BUDGET = (CTAS_PER_SM == 2 ? 100 : 200) * 1024;
     static constexpr int S_RAW = BUDGET / STAGE;
     static constexpr int STAGES = S_RAW > 8 ? 8 : (S_RAW < 2 ? 2 : S_RAW);
-    static constexpr int TX_BYTES = A_ROWS * ROWB + NB * B_TILE;
     static constexpr int ACC_COLS = NP < 32 ? 32 : NP;        // TMEM columns of one accumulator
     static constexpr int NUM_ACC = 2;                         // double-buffered: MMA of tile i+1 overlaps epilogue of tile i
     static constexpr int TMEM_COLS = NUM_ACC * ACC_COLS;      // 64 / 128 / 256: a power of two
@@ -155,7 +162,8 @@ __device__ __forceinline__ FlatPos flat_decode(long long p, long long plane, lon
     return f;
 }
 // a 128-position tile that lies completely inside a rim plane (d' = 0 or D+1) reads only zeros and stores nothing
-__device__ __forceinline__ bool rim_tile(long long p0, long long P, long long plane, long long vol, int Dp) {
+__device__ __forceinline__ bool rim_tile(long long p0, long long P, long long plane, long long vol, int Dp, int dpad = 1) {
+    if (!dpad) return false;                                                      // an image has no rim planes
     const FlatPos f = flat_decode(p0, plane, vol);
     const long long span = (p0 + 127 < P ? 127 : P - 1 - p0);                    // the tail tile is cut at P
     const bool one_plane = (long long)f.off + span < plane;
@@ -173,7 +181,7 @@ __device__ __forceinline__ TileInfo decode_tile(const ConvGeom& g, int t, long l
     } else {
         ti.cls = t / g.mtiles;
         ti.p0 = (long long)(t - ti.cls * g.mtiles) * 128;
-        ti.skip = rim_tile(ti.p0, g.P, plane, vol, Dp);
+        ti.skip = rim_tile(ti.p0, g.P, plane, vol, Dp, g.dpad);
     }
     return ti;
 }
@@ -192,7 +200,7 @@ conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
                     const void* __restrict__ residual, void* __restrict__ y) {
     using C = Cfg<KC, NP, MODE>;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int Dp = g.Di + 2, Hp = g.Hi + 2, Wp = g.Wi + 2;
+    const int Dp = g.Di + 2 * g.dpad, Hp = g.Hi + 2 * g.ri, Wp = g.Wi + 2 * g.ri;
     const long long plane = (long long)Hp * Wp, vol = plane * Dp;
 
     // ---- shared memory carve-up ---------------------------------------------------------
@@ -247,7 +255,7 @@ conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
                     wait_bar(empty_bar(s), ph ^ 1u);
                     const uint32_t sa = base + s * C::STAGE, sb = sa + C::A_BYTES;
                     if (ptx::elect_one_sync()) {
-                        ptx::mbar_arrive_expect_tx(full_bar(s), C::TX_BYTES);
+                        ptx::mbar_arrive_expect_tx(full_bar(s), (uint32_t)g.tx_bytes);
                         if (MODE == MODE_BOX) {
                             const int code = g.a_off[tp];
                             ptx::tma_load_5d(sa, &maps.a[code & 7], full_bar(s), kc * KC,
@@ -291,7 +299,7 @@ conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
                     for (int j = 0; j < C::NB; ++j) {
 #pragma unroll
                         for (int k = 0; k < KC / 16; ++k) {
-                            ptx::umma_bf16(d_tmem, ptx::desc_advance(ad0, j * C::ROWB + k * 32),
+                            ptx::umma_bf16(d_tmem, ptx::desc_advance(ad0, j * g.dil * C::ROWB + k * 32),
                                            ptx::desc_advance(bd0, j * C::B_TILE + k * 32), idesc, (i | j | k) ? 1u : 0u);
                         }
                     }
@@ -323,11 +331,11 @@ conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
                     const FlatPos fp = flat_decode(p, plane, vol);
                     const int b = fp.b, dp = fp.dp, rem2 = fp.off;
                     const int hp = (int)((unsigned)rem2 / (unsigned)Wp), wp = rem2 - hp * Wp;
-                    if (dp >= 1 && dp <= g.Di && hp >= 1 && hp <= g.Hi && wp >= 1 && wp <= g.Wi) {
+                    if (dp >= g.dpad && dp < g.Di + g.dpad && hp >= g.ri && hp < g.Hi + g.ri && wp >= g.ri && wp < g.Wi + g.ri) {
                         ob = (int)b;
                         if (g.transposed) {
                             od = 2 * (dp - 1) + ((ti.cls >> 2) & 1); oh = 2 * (hp - 1) + ((ti.cls >> 1) & 1); ow = 2 * (wp - 1) + (ti.cls & 1);
-                        } else { od = dp - 1; oh = hp - 1; ow = wp - 1; }
+                        } else { od = dp - g.dpad; oh = hp - g.ri; ow = wp - g.ri; }
                         valid = (od < g.Do) && (oh < g.Ho) && (ow < g.Wo);
                     }
                 }
@@ -355,11 +363,39 @@ conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
                                              residual ? __ldg(reinterpret_cast<const float*>(residual) + o) : 0.f, g.relu);
                     reinterpret_cast<float*>(y)[o] = a;
                 }
+            } else if (g.y_mode == 2) {
+                // images only: fp32 NCHW [B][Cout][Ho][Wo] (the layout the cost-volume / correlation ops take); a warp's 32
+                // consecutive pixels make every per-channel store a 128-byte run
+                constexpr int CH = NP >= 32 ? 32 : 16;
+                const size_t hw = (size_t)g.Ho * g.Wo;
+                float* outp = reinterpret_cast<float*>(y) + (size_t)ob * g.Cout * hw + (size_t)oh * g.Wo + ow;
+#pragma unroll
+                for (int c0 = 0; c0 < NP; c0 += CH) {
+                    uint32_t v[CH];
+                    if (CH == 32) ptx::tmem_ld32(taddr + c0, v); else ptx::tmem_ld16(taddr + c0, v);
+                    ptx::tc_wait_ld();
+                    consume_tmem_load(v[0], scratch_smem);
+                    if (c0 + CH >= NP) {
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+                    }
+                    if (valid) {
+#pragma unroll
+                        for (int i = 0; i < CH; ++i) {
+                            if (c0 + i < g.Cout) {
+                                float a = fmaf(__uint_as_float(v[i]), s_scale[c0 + i], s_shift[c0 + i]);
+                                if (g.relu) a = fmaxf(a, 0.f);
+                                outp[(size_t)(c0 + i) * hw] = a;
+                            }
+                        }
+                    }
+                }
             } else {
                 constexpr int CH = NP >= 32 ? 32 : 16;
-                const size_t o = ((((size_t)ob * (g.Do + 2) + od + 1) * (g.Ho + 2) + oh + 1) * (g.Wo + 2) + ow + 1) * (size_t)g.Cout;
-                const uint4* res = residual ? reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(residual) + o) : nullptr;
-                uint4* out = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y) + o);
+                const size_t ov = (((size_t)ob * (g.Do + 2 * g.dpad) + od + g.dpad) * (g.Ho + 2 * g.ro) + oh + g.ro) * (g.Wo + 2 * g.ro) + ow + g.ro;
+                const uint4* res = residual ? reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(residual) + ov * (size_t)g.ldr) : nullptr;
+                uint4* out = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y) + ov * (size_t)g.ldy);
 #pragma unroll
                 for (int c0 = 0; c0 < NP; c0 += CH) {
                     uint32_t v[CH];
@@ -1276,6 +1312,7 @@ int conv3d_dispatch(const void* x, const void* w, const float* scale, const floa
     g.B = B; g.Di = D; g.Hi = H; g.Wi = W; g.Do = Do; g.Ho = Ho; g.Wo = Wo;
     g.Cout = Cout; g.transposed = transposed; g.relu = relu; g.y_f32 = (y_dtype == DSM_F32);
     g.nchunks = Cin / KC; g.P = P; g.desc_variant = variant & 1;
+    g.dpad = 1; g.ri = 1; g.ro = 1; g.dil = 1; g.ldy = Cout; g.ldr = Cout; g.y_mode = g.y_f32 ? 1 : 0;
     const int row_bytes = KC * 2;
     // bit1 of `variant` SET selects the per-tap kernel (MODE_FLAT); the default for stride-1 convolutions is the
     // row-shifted-descriptor kernel (validated bit-identical on B200), except N=128 whose stage would not fit twice
@@ -1405,9 +1442,109 @@ int conv3d_dispatch(const void* x, const void* w, const float* scale, const floa
         grid = dim3((unsigned)g.ntiles, 1, 1);
     }
     cudaStream_t st = (cudaStream_t)stream;
+    g.tx_bytes = (mode == MODE_SHIFT ? 130 : 128) * row_bytes + (mode == MODE_SHIFT ? 3 : 1) * NP * row_bytes;
     if (mode == MODE_BOX)   return launch_mode<MODE_BOX>(KC, NP, maps, g, grid, scale, shift, residual, y, st);
     if (mode == MODE_SHIFT) return launch_mode<MODE_SHIFT>(KC, NP, maps, g, grid, scale, shift, residual, y, st);
     return launch_mode<MODE_FLAT>(KC, NP, maps, g, grid, scale, shift, residual, y, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2-D convolutions of the feature-extraction trunks (models/psmnet/submodule.py:65-140, models/gcnet.py:14-29,
+// models/util_conv.py:119-132,180-208) on the same implicit-GEMM kernel: an image is a volume without rim planes
+// (dpad = 0, Di = 1).  Activations are padded NHWC bf16 [B][H+2r][W+2r][ld] with a zero rim of r >= dilation pixels;
+// ld >= C lets a layer read / write a channel slice of a wider tensor (the 320-channel SPP concatenation is never
+// copied: its producers store straight into their slices).
+//   k = 3, stride 1 : MODE_SHIFT — per kh one (128 + 2*dil)-row tile, the three kw taps are descriptors shifted by dil rows
+//   k = 1, stride 1 : MODE_FLAT with a single tap
+//   stride 2 (k 3|1): MODE_BOX over the four (h, w) parity sub-lattices (input rim must be 1)
+// ---------------------------------------------------------------------------------------------
+int conv2d_dispatch(const void* x, const void* w, const float* scale, const float* shift, const void* residual, void* y,
+                    int B, int Cin, int Cout, int H, int W, int ksize, int stride, int dil, int relu,
+                    int ri, int ro, int ldx, int ldy, int ldr, int y_mode, int variant, void* stream) {
+    if (!x || !w || !y || B <= 0 || Cin <= 0 || Cout <= 0 || H <= 0 || W <= 0) return DSM_EINVAL;
+    if ((ksize != 1 && ksize != 3) || (stride != 1 && stride != 2) || dil < 1 || dil > 2 || relu < 0 || relu > 2) return DSM_EINVAL;
+    if (y_mode != 0 && y_mode != 2) return DSM_EINVAL;
+    if (ri < 1 || ri > 2 || ro < 0 || ro > 2 || (ksize == 3 && ri < dil)) return DSM_EINVAL;
+    if (stride == 2 && (ri != 1 || dil != 1)) return DSM_EUNSUPPORTED;
+    if (y_mode == 2 && residual) return DSM_EUNSUPPORTED;
+    if (Cin % 32 != 0 || (Cin > 32 && Cin % 64 != 0)) return DSM_EUNSUPPORTED;
+    if (Cout != 16 && Cout != 32 && Cout != 64 && Cout != 128) return DSM_EUNSUPPORTED;
+    if (ldx < Cin || (ldx & 7) || (y_mode == 0 && (ldy < Cout || (ldy & 7))) || (residual && (ldr < Cout || (ldr & 7)))) return DSM_EINVAL;
+    if (!dsm_aligned16(x) || !dsm_aligned16(w) || !dsm_aligned16(y) || (residual && !dsm_aligned16(residual))) return DSM_EALIGN;
+    g_launch_pdl = (variant & 128) != 0;
+    const int KC = (Cin == 32) ? 32 : 64, NP = Cout;
+    const int row_bytes = KC * 2;
+    const int Hp = H + 2 * ri, Wp = W + 2 * ri;
+    const long long P = (long long)B * Hp * Wp;
+    if (P > 0x7fffff00LL) return DSM_EUNSUPPORTED;
+    const int Ho = stride == 2 ? (H - 1) / 2 + 1 : H, Wo = stride == 2 ? (W - 1) / 2 + 1 : W;
+    const int ntaps = ksize * ksize;
+
+    ConvMaps maps;
+    ConvGeom g;
+    memset(&g, 0, sizeof(g));
+    g.B = B; g.Di = 1; g.Hi = H; g.Wi = W; g.Do = 1; g.Ho = Ho; g.Wo = Wo;
+    g.Cout = Cout; g.transposed = 0; g.relu = relu; g.y_f32 = 0;
+    g.nchunks = Cin / KC; g.P = P;
+    g.dpad = 0; g.ri = ri; g.ro = ro; g.dil = dil; g.ldy = ldy; g.ldr = ldr; g.y_mode = y_mode;
+    {   // weights: [ntaps*NP][Cin]
+        cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)ntaps * NP};
+        cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
+        cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)NP};
+        if (!encode_map(&maps.w, w, 2, dims, strides, box, row_bytes)) return DSM_EDRIVER;
+    }
+    g.cls_begin[0] = 0; g.cls_begin[1] = ntaps;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (stride == 2) {
+        for (int q = 0; q < 4; ++q) {
+            const int ph = (q >> 1) & 1, pw = q & 1;
+            const char* basep = reinterpret_cast<const char*>(x) + ((size_t)ph * Wp + pw) * (size_t)ldx * 2;
+            cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)((Wp - pw + 1) / 2), (cuuint64_t)((Hp - ph + 1) / 2), 1, (cuuint64_t)B};
+            cuuint64_t strides[4] = {(cuuint64_t)2 * ldx * 2, (cuuint64_t)2 * Wp * ldx * 2,
+                                     (cuuint64_t)Hp * Wp * ldx * 2, (cuuint64_t)Hp * Wp * ldx * 2};
+            cuuint32_t box[5] = {(cuuint32_t)KC, 16, 8, 1, 1};
+            if (!encode_map(&maps.a[q], basep, 5, dims, strides, box, row_bytes)) return DSM_EDRIVER;
+        }
+        for (int q = 4; q < 8; ++q) maps.a[q] = maps.a[q - 4];
+        if (ksize == 3) {
+            for (int kh = 0; kh < 3; ++kh) for (int kw = 0; kw < 3; ++kw) {
+                const int t = kh * 3 + kw;
+                g.a_off[t] = (((kh & 1) << 1) | (kw & 1)) | ((kw >> 1) << 4) | ((kh >> 1) << 5);
+                g.w_row[t] = t * NP;
+            }
+        } else {                                   // 1x1, stride 2: unpadded (2oh, 2ow) = padded (2oh+1, 2ow+1)
+            g.a_off[0] = 3; g.w_row[0] = 0;
+        }
+        g.tiles_w = dsm_ceil_div(Wo, 16); g.tiles_h = dsm_ceil_div(Ho, 8);
+        const long long nt = (long long)B * g.tiles_h * g.tiles_w;
+        if (nt > 0x7fffffffLL) return DSM_EUNSUPPORTED;
+        g.ntiles = (int)nt; g.mtiles = (int)nt;
+        g.tx_bytes = 128 * row_bytes + NP * row_bytes;
+        return launch_mode<MODE_BOX>(KC, NP, maps, g, dim3((unsigned)nt), scale, shift, residual, y, st);
+    }
+    const bool shift_mode = (ksize == 3);
+    const int a_rows = shift_mode ? 128 + 2 * dil : 128;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)P};
+        cuuint64_t strides[1] = {(cuuint64_t)ldx * 2};
+        cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)a_rows};
+        if (!encode_map(&maps.a[0], x, 2, dims, strides, box, row_bytes)) return DSM_EDRIVER;
+        for (int q = 1; q < 8; ++q) maps.a[q] = maps.a[0];
+    }
+    if (ksize == 3) {
+        for (int kh = 0; kh < 3; ++kh) for (int kw = 0; kw < 3; ++kw) {
+            const int t = kh * 3 + kw;
+            g.a_off[t] = ((kh - 1) * Wp + (kw - 1)) * dil;
+            g.w_row[t] = t * NP;
+        }
+    } else {
+        g.a_off[0] = 0; g.w_row[0] = 0;
+    }
+    g.mtiles = (int)dsm_ceil_div_ll(P, 128);
+    g.ntiles = g.mtiles;
+    g.tx_bytes = a_rows * row_bytes + (shift_mode ? 3 : 1) * NP * row_bytes;
+    if (shift_mode) return launch_mode<MODE_SHIFT>(KC, NP, maps, g, dim3((unsigned)g.ntiles), scale, shift, residual, y, st);
+    return launch_mode<MODE_FLAT>(KC, NP, maps, g, dim3((unsigned)g.ntiles), scale, shift, residual, y, st);
 }
 
 }  // namespace
@@ -1435,6 +1572,16 @@ extern "C" int dsm_conv3d_fwd_ex(const void* x, const void* w_packed, const floa
     DsmDeviceGuard dsm_guard_(x);
     return conv3d_dispatch(x, w_packed, scale, shift, residual, y, B, Cin, Cout, D, H, W, stride, transposed, relu,
                            y_dtype, Do, Ho, Wo, variant, stream);
+}
+
+// 2-D convolution block of the feature-extraction trunks; see conv2d_dispatch and include/dsmnet_b200.h
+extern "C" int dsm_conv2d_fwd(const void* x, const void* w_packed, const float* scale, const float* shift,
+                              const void* residual, void* y,
+                              int B, int Cin, int Cout, int H, int W, int ksize, int stride, int dilation, int relu,
+                              int rim_in, int rim_out, int ldx, int ldy, int ldr, int y_mode, int variant, void* stream) {
+    DsmDeviceGuard dsm_guard_(x);
+    return conv2d_dispatch(x, w_packed, scale, shift, residual, y, B, Cin, Cout, H, W, ksize, stride, dilation, relu,
+                           rim_in, rim_out, ldx, ldy, ldr, y_mode, variant, stream);
 }
 
 // bring-up aid: `host_mapped` = device-visible int[4] the kernel writes progress codes into (NULL = off)

@@ -191,3 +191,64 @@ class GCNetHotPath(nn.Module):
             vol = concat_volume(fL, fR, self.D, "gc", padded_bf16=True)
         x37 = self.layer3d.aggregate(vol)
         return softargmin(x37, -1.0).unsqueeze(1)
+
+
+# --------------------------------------------------------------------------------------------
+# 2-D trunk and whole-model drop-in (gcnet.py:14-29, 113-137), reference parameter names.
+# --------------------------------------------------------------------------------------------
+
+class _BasicBlock2d(nn.Module):
+    """util_conv.BasicBlock (models/util_conv.py:180-208): conv-bn-relu-conv-bn, + x, relu."""
+
+    def __init__(self, planes):
+        super().__init__()
+        self.conv1 = nn.Conv2d(planes, planes, 3, 1, 1, bias=False); self.bn1 = nn.BatchNorm2d(planes)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = nn.Conv2d(planes, planes, 3, 1, 1, bias=False); self.bn2 = nn.BatchNorm2d(planes)
+
+    def forward(self, x):
+        out = self.bn2(self.conv2(self.relu(self.bn1(self.conv1(x)))))
+        return self.relu(out + x)
+
+
+class feature2d(nn.Module):
+    """gcnet.py:14-29.  Inference on CUDA: trunk2d.GCNetTrunkPlan (one launch per layer); otherwise stock PyTorch."""
+
+    def __init__(self, num_F=32):
+        super().__init__()
+        self.F = num_F
+        self.conv1 = nn.Sequential(nn.Conv2d(3, 32, 5, 2, 2, bias=True), nn.BatchNorm2d(32), nn.ReLU(inplace=True))
+        self.block1 = nn.Sequential(*[_BasicBlock2d(32) for _ in range(8)])
+        self.conv2 = nn.Conv2d(32, 32, 3, 1, 1)
+
+    def forward(self, x):
+        if x.is_cuda and not self.training and not torch.is_grad_enabled():
+            from .trunk2d import GCNetTrunkPlan, cached_plan
+            return cached_plan(self, GCNetTrunkPlan, x.device)(x)
+        return self.conv2(self.block1(self.conv1(x)))
+
+
+class gcnet(nn.Module):
+    """Drop-in for the reference's gcnet (gcnet.py:113-137): forward(imL, imR, mode) -> ([0], [disparity [B,1,H,W]])."""
+
+    def __init__(self, maxdisparity=192):
+        super().__init__()
+        self.name = "gcnet"
+        self.D = maxdisparity // 2            # gcnet.py:117 (Py2 integer division)
+        self.count_levels = 1
+        self.layer2d = feature2d(32)
+        self.layer3d = feature3d(32)
+
+    def forward(self, imL, imR, mode="train"):
+        assert imL.shape == imR.shape
+        B = imL.size(0)
+        if imL.is_cuda and not self.training and not torch.is_grad_enabled():
+            f = self.layer2d(torch.cat((imL, imR), 0))
+            fL, fR = f[:B], f[B:]
+            vol = concat_volume(fL, fR, self.D, "gc", padded_bf16=True)
+        else:
+            fL, fR = self.layer2d(imL), self.layer2d(imR)
+            vol = concat_volume_padded(fL, fR, self.D, "gc")
+        x37 = self.layer3d.aggregate(vol)
+        oL = softargmin(x37, -1.0).unsqueeze(1)[:, :, :imL.shape[-2], :imL.shape[-1]]
+        return [0], [oL]

@@ -6,7 +6,8 @@ class names, constructor arguments and parameter / buffer names (``dres0.0.0.wei
 ``PSMNet(maxdisp)(left, right, mode)`` returns ``([0, 0, 0], [pred3, pred2, pred1])`` with
 ``pred*`` of shape (B, H, W) exactly like stackhourglass.py:168.
 
-The 2-D feature extractor is a caller of the hot path and stays stock PyTorch (cuDNN); the
+The 2-D feature extractor (a caller of the hot path) runs on the library's 2-D kernels for inference
+(dsmnet_b200/trunk2d.py) and as stock PyTorch under autograd; the
 path from the two feature maps on — concat volume (stackhourglass.py:124-133), dres0..classif3
 (:135-149) and the three upsample+softmax+regression heads (:152-166) — runs as:
   concat_volume (padded NDHWC bf16)  ->  25 fused tcgen05 conv blocks  ->  3 fp32 Cout=1 convs
@@ -303,8 +304,9 @@ class PSMNetHotPath(nn.Module):
 
 
 # --------------------------------------------------------------------------------------------
-# 2-D feature extractor (caller of the hot path; stock PyTorch).  Same parameter names as the
-# reference's feature_extraction (submodule.py:65-140) so that checkpoints load.
+# 2-D feature extractor (caller of the hot path).  Same parameter names as the reference's
+# feature_extraction (submodule.py:65-140) so that checkpoints load.  Inference on CUDA runs on the
+# library's kernels (trunk2d.PSMNetTrunkPlan); with autograd or on CPU the stock-PyTorch graph below runs.
 # --------------------------------------------------------------------------------------------
 
 def convbn(in_planes, out_planes, kernel_size, stride, pad, dilation):
@@ -356,6 +358,10 @@ class feature_extraction(nn.Module):
         return nn.Sequential(*layers)
 
     def forward(self, x):
+        if x.is_cuda and not self.training and not torch.is_grad_enabled():
+            # inference: every layer on the library's kernels (dsmnet_b200/trunk2d.py)
+            from .trunk2d import PSMNetTrunkPlan, cached_plan
+            return cached_plan(self, PSMNetTrunkPlan, x.device)(x)
         out = self.layer1(self.firstconv(x))
         raw = self.layer2(out)
         skip = self.layer4(self.layer3(raw))
@@ -382,7 +388,12 @@ class PSMNet(PSMNetHotPath):
                 m.weight.data.fill_(1); m.bias.data.zero_()
 
     def forward(self, left, right, mode="train"):
-        refimg_fea = self.feature_extraction(left)
-        targetimg_fea = self.feature_extraction(right)
+        B = left.size(0)
+        if left.is_cuda and not self.training and not torch.is_grad_enabled():
+            fea = self.feature_extraction(torch.cat((left, right), 0))     # both images as one batch through the trunk
+            refimg_fea, targetimg_fea = fea[:B], fea[B:]
+        else:
+            refimg_fea = self.feature_extraction(left)
+            targetimg_fea = self.feature_extraction(right)
         preds = PSMNetHotPath.forward(self, refimg_fea.float(), targetimg_fea.float(), (left.size(2), left.size(3)))
         return [0, 0, 0], preds

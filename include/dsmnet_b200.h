@@ -179,6 +179,33 @@ int dsm_pack_weight(const float* w, void* w_packed_bf16, int Cout, int Cin, int 
 int dsm_pack_ndhwc(const float* x_ncdhw, void* y_padded_bf16, int B, int C, int D, int H, int W, void* stream);
 int dsm_unpack_ndhwc(const void* x_padded_bf16, float* y_ncdhw, int B, int C, int D, int H, int W, void* stream);
 
+/* ---- 2-D feature-extraction trunks (callers of the path) ---------------------------------
+ * Replaces the convbn / BasicBlock / SPP stacks of models/psmnet/submodule.py:10-13,21-42,65-140 and the conv2d_bn /
+ * BasicBlock stack of models/gcnet.py:14-29 + models/util_conv.py:119-132,180-208 (eval-mode BatchNorm folded).
+ * Activations: bf16 "padded NHWC" [B][H+2r][W+2r][ld] with a zero rim of r pixels (r >= dilation of every consumer);
+ * ld >= C is the channel pitch, so x / y / residual may be channel slices of a wider tensor (pass the pointer to the first
+ * channel of the slice).  w_packed: bf16 [k*k][Cout][Cin], tap = kh*k + kw.  y = relu?(conv(x)*scale + shift [+ residual]);
+ * relu as in dsm_conv3d_fwd.  Cin in {32, 64, 128, 192, 256, 320, ...}, Cout in {16, 32, 64, 128}; ksize 1|3; stride 1|2
+ * (stride 2: rim_in = 1, dilation 1); dilation 1|2.  y_mode 0: padded NHWC bf16 with rim_out / ldy; y_mode 2: fp32 NCHW
+ * [B][Cout][Ho][Wo] (the layout of the feature maps dsm_concat_volume_fwd / dsm_corr1d_fwd take; no residual).
+ * tcgen05 implicit GEMM: the kernels of dsm_conv3d_fwd on a volume without rim planes.  variant: bit7 as dsm_conv3d_fwd_ex. */
+int dsm_conv2d_fwd(const void* x, const void* w_packed, const float* scale, const float* shift,
+                   const void* residual, void* y,
+                   int B, int Cin, int Cout, int H, int W, int ksize, int stride, int dilation, int relu,
+                   int rim_in, int rim_out, int ldx, int ldy, int ldr, int y_mode, int variant, void* stream);
+/* the image-facing layer: Conv2d(3 -> 32, k 3|5, stride 2, pad k/2) + affine + ReLU, NCHW fp32 image [B][3][H][W] with the
+ * PyTorch fp32 weight [32][3][k][k] -> padded NHWC bf16 [B][Ho+2r][Wo+2r][32] (submodule.py:68, gcnet.py:21); CUDA cores. */
+int dsm_conv2d_first_fwd(const float* img, const float* w, const float* scale, const float* shift, void* out,
+                         int B, int H, int W, int ksize, int relu, int rim_out, void* stream);
+/* PSMNet's SPP branches (submodule.py:84-98,126-136): AvgPool 64/32/16/8 of the 128-channel `skip` slice, 1x1 conv
+ * 128 -> 32 (+BN+ReLU; w fp32 [4][32][128], scale / shift [4][32], branch1..branch4) with the reference's one-pixel
+ * padding ring, bilinear upsampling to H x W, bf16 into channels [coff, coff+128) of `cat` in the order
+ * (branch4, branch3, branch2, branch1).  skip / cat: padded NHWC bf16 with rim / ld (cat may be the same buffer). */
+size_t dsm_spp_workspace_bytes(int B, int H, int W);
+int dsm_spp_fwd(const void* skip, const float* w, const float* scale, const float* shift, void* cat,
+                int B, int H, int W, int rim, int ld, int coff, int align_corners,
+                void* ws, size_t ws_bytes, void* stream);
+
 /* ---- op 4: soft-argmin disparity regression ---------------------------------------------
  * Replaces F.softmax + disparityregression, models/psmnet/submodule.py:56-63 with
  * stackhourglass.py:155-166, and models/gcnet.py:104-111 (sign=-1).

@@ -737,3 +737,137 @@ def dispnetc_forward(p: Dict[str, torch.Tensor], imL: torch.Tensor, imR: torch.T
     if mode == "test":
         out[-1] = out[-1].clamp(1e-6, max(maxdisparity, imL.shape[-1]))
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# 2-D trunks: PSMNet feature_extraction (submodule.py:65-140), GC-Net feature2d (gcnet.py:14-29)
+# ------------------------------------------------------------------------------------------
+
+def _round(t, dtype):
+    return t if dtype is None else t.to(dtype).float()
+
+
+def conv2d_block(x, weight, scale=None, shift=None, stride=1, dilation=1, residual=None, relu=False,
+                 operand_dtype=None, storage_dtype=None, padding=None):
+    """Conv2d(k, stride, padding = dilation*(k//2), dilation, bias folded into `shift`) -> per-channel affine (eval-mode
+    BatchNorm2d) -> [+ residual] -> [ReLU].  convbn (submodule.py:10-13; note its `pad` argument is ignored in favour of
+    `dilation`), BasicBlock (:21-42: NO ReLU after the add), util_conv.conv2d_bn (:119-132) / BasicBlock (:180-208: ReLU
+    after the add).  `operand_dtype` / `storage_dtype` emulate the tensor-core kernel's number format as in conv3d_block."""
+    k = weight.shape[-1]
+    if padding is None:
+        padding = dilation * (k // 2) if k > 1 else 0
+    y = F.conv2d(_round(x, operand_dtype), _round(weight, operand_dtype), None, stride=stride, padding=padding, dilation=dilation)
+    if scale is not None:
+        y = y * scale.view(1, -1, 1, 1)
+    if shift is not None:
+        y = y + shift.view(1, -1, 1, 1)
+    if residual is not None:
+        y = y + residual
+    if relu:
+        y = F.relu(y)
+    return _round(y, storage_dtype)
+
+
+def _fold2d(params, conv_key, bn_prefix, eps=1e-5):
+    w = params[conv_key + ".weight"]
+    b = params.get(conv_key + ".bias")
+    bn = None if bn_prefix is None else {k: params[bn_prefix + "." + k] for k in ("weight", "bias", "running_mean", "running_var")}
+    scale, shift = fold_bn(w.shape[0], bn, b, eps)
+    return w, scale, shift
+
+
+def psmnet_feature_extraction(params: Dict[str, torch.Tensor], x: torch.Tensor, align_corners: bool = True,
+                              operand_dtype=None, taps: Optional[dict] = None) -> torch.Tensor:
+    """feature_extraction.forward (submodule.py:119-140), eval-mode BatchNorm.  `params` uses the reference's names without
+    the `feature_extraction.` prefix (firstconv.0.0.weight ...).  operand_dtype = (operand, storage) emulates the CUDA trunk:
+    bf16 conv operands and bf16 activation storage, fp32 accumulation; the SPP pooling / 1x1 convs / bilinear upsampling run
+    in fp32 on the stored bf16 skip tensor and are stored as bf16; the final 32-channel map is fp32.  `taps` (dict) receives
+    intermediate tensors for layer-by-layer debugging."""
+    od, sd = operand_dtype if isinstance(operand_dtype, tuple) else (operand_dtype, None)
+
+    def cb(prefix, t, stride=1, dil=1, residual=None, relu=False, storage=sd):
+        w, sc, sh = _fold2d(params, prefix + ".0", prefix + ".1")
+        return conv2d_block(t, w, sc, sh, stride, dil, residual, relu, od, storage)
+
+    def layer(name, t, blocks, stride, dil):
+        for i in range(blocks):
+            p = "%s.%d" % (name, i)
+            s = stride if i == 0 else 1
+            h = cb(p + ".conv1.0", t, s, dil, relu=True)
+            res = t
+            if (p + ".downsample.0.weight") in params:
+                w, sc, sh = _fold2d(params, p + ".downsample.0", p + ".downsample.1")
+                res = conv2d_block(t, w, sc, sh, s, 1, None, False, od, sd)
+            t = cb(p + ".conv2", h, 1, dil, residual=res)             # BasicBlock: no ReLU after the add (submodule.py:40)
+        return t
+
+    # the first convolution reads the fp32 image with fp32 weights (CUDA-core kernel; K = 27 is no tensor-core shape)
+    w, sc, sh = _fold2d(params, "firstconv.0.0", "firstconv.0.1")
+    t = conv2d_block(x, w, sc, sh, 2, 1, None, True, None, sd)
+    t = cb("firstconv.2", t, relu=True)
+    t = cb("firstconv.4", t, relu=True)
+    if taps is not None: taps["firstconv"] = t
+    t = layer("layer1", t, 3, 1, 1)
+    if taps is not None: taps["layer1"] = t
+    raw = layer("layer2", t, 16, 2, 1)
+    if taps is not None: taps["raw"] = raw
+    t = layer("layer3", raw, 3, 1, 1)
+    if taps is not None: taps["layer3"] = t
+    skip = layer("layer4", t, 3, 1, 2)
+    if taps is not None: taps["skip"] = skip
+    hw = skip.shape[2:]
+    br = []
+    for i, k in ((1, 64), (2, 32), (3, 16), (4, 8)):
+        p = F.avg_pool2d(skip, (k, k), stride=(k, k))
+        w, sc, sh = _fold2d(params, "branch%d.1.0" % i, "branch%d.1.1" % i)
+        # convbn ignores its `pad` argument and pads by `dilation` = 1 even for this 1x1 convolution (submodule.py:12,84-98):
+        # the pooled map grows by a ring whose value is relu(BatchNorm(0)); fp32 on the CUDA cores (a handful of pixels)
+        p = conv2d_block(p, w, sc, sh, 1, 1, None, True, padding=1)
+        br.append(_round(F.interpolate(p, hw, mode="bilinear", align_corners=align_corners), sd))
+        if taps is not None: taps["branch%d" % i] = br[-1]
+    feat = torch.cat((raw, skip, br[3], br[2], br[1], br[0]), 1)
+    t = cb("lastconv.0", feat, relu=True)
+    if taps is not None: taps["lastconv0"] = t
+    return conv2d_block(t, params["lastconv.2.weight"], None, None, 1, 1, None, False, od, None)
+
+
+def gcnet_feature2d(params: Dict[str, torch.Tensor], x: torch.Tensor, operand_dtype=None) -> torch.Tensor:
+    """feature2d.forward (gcnet.py:25-29): conv 5x5 s2 + BN + ReLU, 8 BasicBlocks (util_conv.py:180-208, ReLU after the add),
+    bare conv 3x3 with bias.  `params` without the `layer2d.` prefix."""
+    od, sd = operand_dtype if isinstance(operand_dtype, tuple) else (operand_dtype, None)
+    w, sc, sh = _fold2d(params, "conv1.0", "conv1.1")
+    t = conv2d_block(x, w, sc, sh, 2, 1, None, True, None, sd)
+    for i in range(8):
+        p = "block1.%d" % i
+        w, sc, sh = _fold2d(params, p + ".conv1", p + ".bn1")
+        h = conv2d_block(t, w, sc, sh, 1, 1, None, True, od, sd)
+        w, sc, sh = _fold2d(params, p + ".conv2", p + ".bn2")
+        t = conv2d_block(h, w, sc, sh, 1, 1, t, True, od, sd)
+    w, sc, sh = _fold2d(params, "conv2", None)
+    return conv2d_block(t, w, sc, sh, 1, 1, None, False, od, None)
+
+
+def trunk_random_params(shapes: Dict[str, Sequence[int]], seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Synthetic parameters for a 2-D trunk given {name: shape} (the reference module's state_dict layout): He-normal conv
+    weights (fan-out, as stackhourglass.py:100-114 / util_conv.net_init), small biases, BatchNorm weight ~U(0.8,1.2), bias
+    ~N(0,0.05), running statistics (0, 1) — calibrate with `calibrate_trunk_bn_`.  numpy RNG: identical on every host."""
+    rs = np.random.RandomState(seed)
+    p: Dict[str, torch.Tensor] = {}
+    for name in sorted(shapes):
+        shp = tuple(shapes[name])
+        if name.endswith("num_batches_tracked"):
+            continue
+        if len(shp) == 4:
+            std = math.sqrt(2.0 / (shp[2] * shp[3] * shp[0]))
+            p[name] = torch.from_numpy(rs.standard_normal(size=shp).astype(np.float32) * np.float32(std))
+        elif name.endswith("running_mean"):
+            p[name] = torch.zeros(shp)
+        elif name.endswith("running_var"):
+            p[name] = torch.ones(shp)
+        elif name.endswith(".bias") and (name[: -len(".bias")] + ".running_mean") not in shapes:
+            p[name] = torch.from_numpy(rs.standard_normal(size=shp).astype(np.float32) * np.float32(0.02))     # conv bias
+        elif name.endswith(".weight"):
+            p[name] = torch.from_numpy(rs.uniform(0.8, 1.2, size=shp).astype(np.float32))
+        else:
+            p[name] = torch.from_numpy(rs.standard_normal(size=shp).astype(np.float32) * np.float32(0.05))
+    return p

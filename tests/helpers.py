@@ -45,3 +45,17 @@ def cosine(u, v):
 def psm_train_loss(preds, gt):
     """the reference's weighted L1 pyramid over [pred3, pred2, pred1]"""
     return sum(wt * (p - gt).abs().mean() for wt, p in zip((1.0, 0.7, 0.5), preds))
+
+
+# ---- 2-D trunk fixtures (tests/golden/make_golden_models.py) ---------------------------------------------------------
+
+def trunk_params_from_golden(g, module):
+    """the fixture's parameters: oracle.ops.trunk_random_params(seed) over `module`'s state_dict layout + the calibrated
+    BatchNorm running statistics stored in the fixture"""
+    import oracle.ops as O
+    shapes = {k: tuple(v.shape) for k, v in module.state_dict().items()}
+    p = O.trunk_random_params(shapes, seed=g["seed"])
+    for k in list(p):
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            p[k] = g[k.replace(".", "__")].clone()
+    return p
