@@ -274,6 +274,20 @@ class PSMNetHotPath(nn.Module):
             costs.append(prev)
         return costs
 
+    def host_pipeline(self, B, h, w, out_hw, device=None, use_graph=True):
+        """Streaming host-buffer entry point: a `pipeline.HostPipeline` whose step takes two pinned host feature maps
+        [B, 32, h, w] fp32 and yields the three disparity maps [B, H, W] in pinned host memory (H2D, CUDA-graph replay of
+        the path, D2H; double-buffered).  The module must be in eval mode on a CUDA device."""
+        device = torch.device(device) if device is not None else next(self.parameters()).device
+        key = ("hot", B, h, w, tuple(out_hw), str(device), use_graph)
+        ex = [torch.zeros(B, 32, h, w, device=device) for _ in range(2)]
+        return _host_pipeline(self, key, lambda a, b: PSMNetHotPath.forward(self, a, b, tuple(out_hw)), ex, use_graph)
+
+    def infer_host(self, fL_host, fR_host, out_hw):
+        """One synchronous call with HOST feature maps -> [pred3, pred2, pred1] in pinned host memory."""
+        B, _, h, w = fL_host.shape
+        return self.host_pipeline(B, h, w, out_hw).run(fL_host, fR_host)
+
     def forward(self, fL, fR, out_hw):
         train = self._wants_autograd(fL, fR)
         if CLS_SIDE_STREAM and EARLY_HEADS and not train:
@@ -301,6 +315,15 @@ class PSMNetHotPath(nn.Module):
         stacked = ws["cost_all"].view(3 * B, *ws["cost_all"].shape[2:])
         preds = upsample_softargmin(stacked, size, self.align_corners).view(3, B, out_hw[0], out_hw[1])
         return [preds[0], preds[1], preds[2]]
+
+
+def _host_pipeline(owner, key, step_fn, examples, use_graph=True):
+    pipes = owner.__dict__.setdefault("_host_pipes", {})
+    p = pipes.get(key)
+    if p is None:
+        from .pipeline import HostPipeline
+        p = pipes[key] = HostPipeline(step_fn, examples, use_graph)
+    return p
 
 
 # --------------------------------------------------------------------------------------------
@@ -386,6 +409,18 @@ class PSMNet(PSMNetHotPath):
                 m.weight.data.normal_(0, math.sqrt(2. / n))
             elif isinstance(m, nn.BatchNorm2d):
                 m.weight.data.fill_(1); m.bias.data.zero_()
+
+    def image_pipeline(self, B, H, W, device=None, use_graph=True):
+        """Whole-model host-buffer entry point: step(left, right) with pinned host images [B, 3, H, W] fp32 -> the three
+        disparity maps [B, H, W] in pinned host memory (trunk + hot path as one CUDA graph, copies double-buffered)."""
+        device = torch.device(device) if device is not None else next(self.parameters()).device
+        key = ("img", B, H, W, str(device), use_graph)
+        ex = [torch.zeros(B, 3, H, W, device=device) for _ in range(2)]
+        return _host_pipeline(self, key, lambda a, b: self.forward(a, b, "test")[1], ex, use_graph)
+
+    def infer_host_images(self, left_host, right_host):
+        B, _, H, W = left_host.shape
+        return self.image_pipeline(B, H, W).run(left_host, right_host)
 
     def forward(self, left, right, mode="train"):
         B = left.size(0)
