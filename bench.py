@@ -310,7 +310,6 @@ def stock_torch_hotpath(m, fL, fR, maxdisp, out_hw):
 def torch_gpu_baseline(m, fL, fR, H, W, steps=3):
     """pairs/s of stock_torch_hotpath on this GPU: fp32 with TF32 off (the reference's arithmetic) and bf16 autocast with
     channels_last_3d weights/activations (the fastest stock configuration cuDNN offers for these layers)."""
-    import copy
     res = {}
     tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
     B = fL.shape[0]
@@ -320,7 +319,10 @@ def torch_gpu_baseline(m, fL, fR, H, W, steps=3):
             ms = time_kernel_alone(lambda: stock_torch_hotpath(m, fL, fR, MAXDISP, (H, W)), reps=steps)
         res["fp32_no_tf32"] = {"pairs_per_s": B / (ms / 1e3), "ms_per_step": ms}
         torch.backends.cudnn.allow_tf32 = True; torch.backends.cuda.matmul.allow_tf32 = True
-        m2 = copy.deepcopy(m).to(memory_format=torch.channels_last_3d)
+        from dsmnet_b200.psmnet import PSMNetHotPath
+        m2 = PSMNetHotPath(MAXDISP)
+        m2.load_state_dict(m.state_dict())
+        m2 = m2.to(fL.device).eval().to(memory_format=torch.channels_last_3d)
         with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
             ms = time_kernel_alone(lambda: stock_torch_hotpath(m2, fL.bfloat16(), fR.bfloat16(), MAXDISP, (H, W)), reps=steps)
         res["bf16_autocast_channels_last_3d"] = {"pairs_per_s": B / (ms / 1e3), "ms_per_step": ms}
@@ -427,7 +429,6 @@ def run_psmnet(args, rank, world, device, dist, barrier):
     if sustained:
         sustained["value"] = B * world * sustained["steps"] / sustained["seconds"]
         sustained["unit"] = "pairs/s"
-        flops_step = B * (926.7e9 if (H, W) == (384, 1248) else None) if True else None
         if (H, W) == (384, 1248):
             tfs = B * 926.7e9 / (sustained["ms_per_step"] * 1e-3) / 1e12
             sustained["stack_tflops"] = tfs
@@ -684,8 +685,8 @@ def main():
     ap.add_argument("--no-whole-model", action="store_true")
     ap.add_argument("--no-sustained", action="store_true")
     args = ap.parse_args()
-    if args.batch is None:
-        args.batch = 4 if args.workload == "dispnetc_selfsup_train" else 1
+    if args.batch is None:      # the op chain of iResNet takes 0.2 ms per pair: 8 pairs per step give the clock sampler a region to see
+        args.batch = {"dispnetc_selfsup_train": 4, "iresnet_ops_540x960": 8}.get(args.workload, 1)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":

@@ -52,15 +52,31 @@ def grid_vectors(h0, w0, h, w, LeftTop=(0, 0), scale_factor=1):
     return torch.linspace(x, x1, w), torch.linspace(y, y1, h)
 
 
+_grid_cache = {}
+
+
+def grid_vectors_device(h0, w0, h, w, LeftTop, scale_factor, device):
+    """The two linspace vectors on `device`, built on the host once per geometry and kept (a per-call host->device copy of
+    pageable memory would make the op uncapturable in a CUDA graph and costs more than the kernel for small levels)."""
+    key = (h0, w0, h, w, float(LeftTop[0]), float(LeftTop[1]), float(scale_factor), str(device))
+    rc = _grid_cache.get(key)
+    if rc is None:
+        if len(_grid_cache) > 256:
+            _grid_cache.clear()
+        row, col = grid_vectors(h0, w0, h, w, LeftTop, scale_factor)
+        rc = _grid_cache[key] = (row.to(device), col.to(device))
+    return rc
+
+
 def imwrap_BCHW(im_src, disp, fliplr=False, LeftTop=[0, 0], scale_factor=1, delt=None):
     """``delt=None`` draws it like the reference (1e-4*(U[0,1)+0.1) from the global CPU RNG)."""
     bn, _, h0, w0 = im_src.shape
     bn, c, h, w = disp.shape
     assert c == 1 and min(h, w, h0, w0) > 1
-    row, col = grid_vectors(h0, w0, h, w, LeftTop, scale_factor)
+    _lib.require_cuda(im_src, disp)
+    row, col = grid_vectors_device(h0, w0, h, w, LeftTop, scale_factor, im_src.device)
     if delt is None:
         delt = float(1e-4 * (torch.rand(1)[0] + 0.1))
-    row = row.to(im_src.device, non_blocking=True); col = col.to(im_src.device, non_blocking=True)
     return WarpFunction.apply(im_src, disp, row, col, delt, fliplr)
 
 

