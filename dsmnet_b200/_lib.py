@@ -71,8 +71,23 @@ SIGNATURES = {
     "dsm_warp_fwd": [_P, _P, _P, _P, _F, _I, _P, _I, _I, _I, _I, _I, _I, _P],
     "dsm_warp_indices": [_P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P],
     "dsm_debug_conv_set_progress": [_P],
+    "dsm_warp_fwd_batched": [_P, _I, _P],
+    "dsm_warp_bwd_batched": [_P, _I, _P],
+    "dsm_ssim_fwd": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "dsm_ssim_bwd_workspace_bytes": [_I, _I, _I],
+    "dsm_ssim_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _P, c_size_t, _P],
     "dsm_warp_bwd": [_P, _P, _P, _P, _P, _F, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P],
 }
+
+
+
+class DsmWarpJob(ctypes.Structure):
+    """include/dsmnet_b200.h: one warp of a batched launch"""
+    _fields_ = [("src", _P), ("disp", _P), ("row", _P), ("col", _P), ("out", _P), ("gout", _P), ("gsrc", _P), ("gdisp", _P),
+                ("delt", _F), ("fliplr", _I), ("B", _I), ("C", _I), ("H0", _I), ("W0", _I), ("H", _I), ("W", _I)]
+
+
+WARP_MAX_JOBS = 32
 
 _lib = None
 

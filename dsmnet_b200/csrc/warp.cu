@@ -44,13 +44,10 @@ __device__ __forceinline__ Tap make_tap(float d, float rowv, float colv, float k
     return t;
 }
 
-__global__ void __launch_bounds__(128)
-warp_fwd_kernel(const float* __restrict__ src, const float* __restrict__ disp,
-                const float* __restrict__ row, const float* __restrict__ col,
-                float delt, float k, float* __restrict__ out,
-                int C, int H0, int W0, int H, int W) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y, b = blockIdx.z;
+__device__ __forceinline__ void warp_fwd_body(const float* __restrict__ src, const float* __restrict__ disp,
+                                              const float* __restrict__ row, const float* __restrict__ col,
+                                              float delt, float k, float* __restrict__ out,
+                                              int C, int H0, int W0, int H, int W, int j, int i, int b) {
     if (j >= W) return;
     const Tap t = make_tap(__ldg(disp + ((size_t)b * H + i) * W + j), __ldg(row + j), __ldg(col + i), k, H0, W0);
     const size_t sp = (size_t)H0 * W0, op = (size_t)H * W;
@@ -70,23 +67,28 @@ warp_fwd_kernel(const float* __restrict__ src, const float* __restrict__ disp,
     }
 }
 
+__global__ void __launch_bounds__(128)
+warp_fwd_kernel(const float* __restrict__ src, const float* __restrict__ disp,
+                const float* __restrict__ row, const float* __restrict__ col,
+                float delt, float k, float* __restrict__ out,
+                int C, int H0, int W0, int H, int W) {
+    warp_fwd_body(src, disp, row, col, delt, k, out, C, H0, W0, H, W, blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y, blockIdx.z);
+}
+
 // backward: gsrc[b,c,tap] += w_tap * g   (scatter, fp32 red.global.add)
 //           gdisp[b,i,j]   = -k*(2/(W0-1))*((W0-1)/2) * sum_c g * d(out)/d(ix)
 // with d(out)/d(ix) = (ne_v - nw_v)*(y0+1-iy) + (se_v - sw_v)*(iy-y0) over in-range tap values
 // (tap value = src + delt).  The chain through the normalise/un-normalise pair is applied as the
 // two separate factors ATen and autograd use ((W0-1)/2, then 2.0/(W0-1)).
-__global__ void __launch_bounds__(128)
-warp_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ src, const float* __restrict__ disp,
-                const float* __restrict__ row, const float* __restrict__ col,
-                float delt, float k, float* __restrict__ gsrc, float* __restrict__ gdisp,
-                int C, int H0, int W0, int H, int W) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y, b = blockIdx.z;
+__device__ __forceinline__ void warp_bwd_body(const float* __restrict__ gout, const float* __restrict__ src, const float* __restrict__ disp,
+                                              const float* __restrict__ row, const float* __restrict__ col,
+                                              float delt, float k, float* __restrict__ gsrc, float* __restrict__ gdisp,
+                                              int C, int H0, int W0, int H, int W, int j, int i, int b) {
     if (j >= W) return;
     const Tap t = make_tap(__ldg(disp + ((size_t)b * H + i) * W + j), __ldg(row + j), __ldg(col + i), k, H0, W0);
     const size_t sp = (size_t)H0 * W0, op = (size_t)H * W;
     const float* s = src + (size_t)b * C * sp;
-    float* gs = gsrc + (size_t)b * C * sp;
+    float* gs = gsrc ? gsrc + (size_t)b * C * sp : nullptr;       // NULL: the source needs no gradient (an input image)
     const float* g = gout + (size_t)b * C * op + (size_t)i * W + j;
     const int a00 = t.y0 * W0 + t.x0;
     const bool v00 = t.vy0 && t.vx0, v01 = t.vy0 && t.vx1, v10 = t.vy1 && t.vx0, v11 = t.vy1 && t.vx1;
@@ -97,15 +99,67 @@ warp_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ src, c
         const float* p = s + c * sp + a00;
         float* q = gs + c * sp + a00;
         float nwv = 0.f, nev = 0.f, swv = 0.f, sev = 0.f;
-        if (v00) { nwv = __ldg(p) + delt;          atomicAdd(q, t.nw * gv); }
-        if (v01) { nev = __ldg(p + 1) + delt;      atomicAdd(q + 1, t.ne * gv); }
-        if (v10) { swv = __ldg(p + W0) + delt;     atomicAdd(q + W0, t.sw * gv); }
-        if (v11) { sev = __ldg(p + W0 + 1) + delt; atomicAdd(q + W0 + 1, t.se * gv); }
+        if (v00) { nwv = __ldg(p) + delt;          if (gs) atomicAdd(q, t.nw * gv); }
+        if (v01) { nev = __ldg(p + 1) + delt;      if (gs) atomicAdd(q + 1, t.ne * gv); }
+        if (v10) { swv = __ldg(p + W0) + delt;     if (gs) atomicAdd(q + W0, t.sw * gv); }
+        if (v11) { sev = __ldg(p + W0 + 1) + delt; if (gs) atomicAdd(q + W0 + 1, t.se * gv); }
         gix = fmaf(gv, (nev - nwv) * ey + (sev - swv) * t.ty, gix);
     }
     const float wm1 = (float)(W0 - 1);
     // d(ix)/d(gx) = (W0-1)/2 ; d(gx)/d(disp) = -k*2/(W0-1)
     gdisp[((size_t)b * H + i) * W + j] = -k * (2.0f / wm1) * (gix * (wm1 * 0.5f));
+}
+
+__global__ void __launch_bounds__(128)
+warp_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ src, const float* __restrict__ disp,
+                const float* __restrict__ row, const float* __restrict__ col,
+                float delt, float k, float* __restrict__ gsrc, float* __restrict__ gdisp,
+                int C, int H0, int W0, int H, int W) {
+    warp_bwd_body(gout, src, disp, row, col, delt, k, gsrc, gdisp, C, H0, W0, H, W, blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y, blockIdx.z);
+}
+
+// ---- batched form: all the warps of one training step (losses/loss.py:449-452: 4 warps x 7 pyramid levels) in ONE launch.
+// The jobs are independent (no warp reads another warp's output); a block finds its job by scanning the block-count prefix.
+struct WarpJobs {
+    DsmWarpJob job[DSM_WARP_MAX_JOBS];
+    int first_block[DSM_WARP_MAX_JOBS + 1];
+    int n;
+};
+
+template <bool BWD>
+__global__ void __launch_bounds__(128)
+warp_batched_kernel(const __grid_constant__ WarpJobs J) {
+    int q = 0;
+    while (q + 1 < J.n && (int)blockIdx.x >= J.first_block[q + 1]) ++q;
+    const DsmWarpJob& w = J.job[q];
+    int r = (int)blockIdx.x - J.first_block[q];
+    const int xb = dsm_ceil_div(w.W, 128);
+    const int bx = r % xb; r /= xb;
+    const int i = r % w.H, b = r / w.H;
+    const int j = bx * 128 + (int)threadIdx.x;
+    const float k = w.fliplr ? -1.0f : 1.0f;
+    if (BWD) warp_bwd_body(w.gout, w.src, w.disp, w.row, w.col, w.delt, k, w.gsrc, w.gdisp, w.C, w.H0, w.W0, w.H, w.W, j, i, b);
+    else     warp_fwd_body(w.src, w.disp, w.row, w.col, w.delt, k, w.out, w.C, w.H0, w.W0, w.H, w.W, j, i, b);
+}
+
+int launch_batched(const DsmWarpJob* jobs, int n, bool bwd, void* stream) {
+    if (!jobs || n < 1 || n > DSM_WARP_MAX_JOBS) return DSM_EINVAL;
+    WarpJobs J;
+    long long total = 0;
+    for (int q = 0; q < n; ++q) {
+        const DsmWarpJob& w = jobs[q];
+        if (!w.src || !w.disp || !w.row || !w.col || w.B <= 0 || w.C <= 0) return DSM_EINVAL;
+        if (w.H0 < 2 || w.W0 < 2 || w.H < 2 || w.W < 2) return DSM_EINVAL;
+        if (bwd ? (!w.gout || !w.gdisp) : !w.out) return DSM_EINVAL;
+        J.job[q] = w;
+        J.first_block[q] = (int)total;
+        total += (long long)dsm_ceil_div(w.W, 128) * w.H * w.B;
+        if (total > 0x7fffffffLL) return DSM_EUNSUPPORTED;
+    }
+    J.first_block[n] = (int)total; J.n = n;
+    if (bwd) warp_batched_kernel<true><<<(unsigned)total, 128, 0, (cudaStream_t)stream>>>(J);
+    else     warp_batched_kernel<false><<<(unsigned)total, 128, 0, (cudaStream_t)stream>>>(J);
+    return dsm_launch_status();
 }
 
 __global__ void __launch_bounds__(128)
@@ -148,6 +202,16 @@ extern "C" int dsm_warp_fwd(const float* src, const float* disp, const float* ro
     warp_fwd_kernel<<<dim3(dsm_ceil_div(W, 128), H, B), 128, 0, (cudaStream_t)stream>>>(
         src, disp, row, col, delt, fliplr ? -1.0f : 1.0f, out, C, H0, W0, H, W);
     return dsm_launch_status();
+}
+
+extern "C" int dsm_warp_fwd_batched(const DsmWarpJob* jobs, int n, void* stream) {
+    DsmDeviceGuard dsm_guard_(jobs && n > 0 ? jobs[0].src : nullptr);
+    return launch_batched(jobs, n, false, stream);
+}
+
+extern "C" int dsm_warp_bwd_batched(const DsmWarpJob* jobs, int n, void* stream) {
+    DsmDeviceGuard dsm_guard_(jobs && n > 0 ? jobs[0].src : nullptr);
+    return launch_batched(jobs, n, true, stream);
 }
 
 extern "C" int dsm_warp_bwd(const float* gout, const float* src, const float* disp, const float* row,

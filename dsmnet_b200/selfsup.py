@@ -4,9 +4,11 @@ the `depthmono[-mask]` pyramid loss (losses/loss.py:196-236 `loss_depthmono`, :3
 (mirrored pair, two forwards, loss, backward), plus the multi-GPU form of it: one process per GPU,
 batch sharded by rank, NCCL gradient all-reduce through DistributedDataParallel.
 
-Hot-path ops inside: 28 `imwrap_BCHW` warps per step (7 levels x 4) and DispNetC's 1-D correlation, both on
-the sm_100a kernels with their backward kernels; SSIM / smoothness / masks are stock PyTorch ops as in the
-reference.  `warp_fn` is injectable so that the host logic of the loss is testable on CPU with the oracle's
+Hot-path ops inside: 28 `imwrap_BCHW` warps per step (7 levels x 4) — ONE batched launch forward and one backward
+(`imwrap.imwrap_batched`) — and DispNetC's 1-D correlation, on the sm_100a kernels with their backward kernels; the
+SSIM map (five 11x11 Gaussian convolutions + ~15 elementwise kernels in the reference) is one fused kernel forward and
+two backward (`SsimFunction`, csrc/ssim.cu); the mirrored pair is a device flip.  Smoothness / masks / weights are stock
+elementwise ops.  `warp_fn` is injectable so that the host logic of the loss is testable on CPU with the oracle's
 warp (tests/test_selfsup_cpu.py); the default is the CUDA op and has no fallback.
 """
 from __future__ import annotations
@@ -33,8 +35,42 @@ def _gauss_window(size: int, channel: int, like: torch.Tensor) -> torch.Tensor:
     return w
 
 
+class SsimFunction(torch.autograd.Function):
+    """SSIM.py:24-42 as one fused kernel (dsm_ssim_fwd); the gradient flows to b (the warped image) through two more
+    (dsm_ssim_bwd).  `a` is the real image: asking for its gradient raises (the reference's loss never does)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        from . import _lib
+        _lib.require_cuda(a, b)
+        a = a.contiguous().float(); b = b.contiguous().float()
+        B, C, H, W = a.shape
+        s = torch.empty(B, 1, H, W, device=a.device, dtype=torch.float32)
+        _lib.check(_lib.lib().dsm_ssim_fwd(a.data_ptr(), b.data_ptr(), s.data_ptr(), B, C, H, W, _lib.stream_ptr(a.device)), "dsm_ssim_fwd")
+        ctx.save_for_backward(a, b)
+        return s
+
+    @staticmethod
+    def backward(ctx, gs):
+        from . import _lib
+        a, b = ctx.saved_tensors
+        if ctx.needs_input_grad[0]:
+            raise _lib.DsmError("SsimFunction: gradient w.r.t. the first (real) image is not implemented")
+        B, C, H, W = a.shape
+        gs = gs.contiguous().float()
+        gb = torch.empty_like(b)
+        L = _lib.lib()
+        ws = torch.empty(L.dsm_ssim_bwd_workspace_bytes(B, H, W) // 4, device=a.device, dtype=torch.float32)
+        _lib.check(L.dsm_ssim_bwd(a.data_ptr(), b.data_ptr(), gs.data_ptr(), gb.data_ptr(), B, C, H, W, ws.data_ptr(), ws.numel() * 4,
+                                  _lib.stream_ptr(a.device)), "dsm_ssim_bwd")
+        return None, gb
+
+
 def ssim_map(a: torch.Tensor, b: torch.Tensor, window_size: int = 11) -> torch.Tensor:
-    """SSIM.py:24-42 (`_ssim`): channel-averaged 11x11 Gaussian SSIM map, [B,1,H,W]."""
+    """SSIM.py:24-42 (`_ssim`): channel-averaged 11x11 Gaussian SSIM map, [B,1,H,W].  CUDA tensors take the fused kernels
+    (`SsimFunction`); CPU tensors (the host-logic tests with the oracle's warp) the stock restatement below."""
+    if a.is_cuda and window_size == 11 and not a.requires_grad:
+        return SsimFunction.apply(a, b)
     w = _gauss_window(window_size, a.shape[1], a)
     p = window_size // 2
     mu1, mu2 = F.conv2d(a, w, padding=p), F.conv2d(b, w, padding=p)
@@ -97,6 +133,7 @@ def losses_pyramid1(imR_src, imL, dispLs: Sequence[torch.Tensor], scales: Sequen
                     flag_mask: bool = True, warp_fn: Optional[Callable] = None, align_corners: bool = True) -> torch.Tensor:
     """loss.py:424-466.  Levels above 2 are upsampled to level 2; four warps per level: the two photometric warps of the
     (cropped) left images from the uncropped right sources, and the two left-right disparity warps (fliplr)."""
+    batched = warp_fn is None          # CUDA default: the 4 x len(scales) warps of this call as ONE launch (fwd) + one (bwd)
     warp = warp_fn or _default_warp()
     maxlevel = min(2, max(scales))
     h, w = dispLs[list(scales).index(maxlevel)].shape[-2:]
@@ -104,6 +141,7 @@ def losses_pyramid1(imR_src, imL, dispLs: Sequence[torch.Tensor], scales: Sequen
     for _ in range(maxlevel):
         imLs.append(imLs[-1][:, :, ::2, ::2]); imL1s.append(imL1s[-1][:, :, ::2, ::2])
     loss = 0
+    levels = []
     for i, level in enumerate(scales):
         wl = weight_levels[level]
         if wl <= 0:
@@ -115,10 +153,25 @@ def losses_pyramid1(imR_src, imL, dispLs: Sequence[torch.Tensor], scales: Sequen
         else:
             sf = 2 ** level
             dL, dL1 = dispLs[i], dispL1s[i]
-        imL_w = warp(imR_src, dL, fliplr=False, LeftTop=list(LeftTop), scale_factor=sf)
-        imL1_w = warp(imR1_src, dL1, fliplr=False, LeftTop=list(LeftTop1), scale_factor=sf)
-        dL_w = warp(dL1, dL, fliplr=True, LeftTop=[0, 0], scale_factor=1)
-        dL1_w = warp(dL, dL1, fliplr=True, LeftTop=[0, 0], scale_factor=1)
+        levels.append((level, wl, sf, dL, dL1))
+    warped = None
+    if batched and levels:
+        from .imwrap import imwrap_batched
+        jobs = []
+        for level, wl, sf, dL, dL1 in levels:                       # the reference's call order (its RNG draws follow it)
+            jobs += [dict(im_src=imR_src, disp=dL, fliplr=False, LeftTop=list(LeftTop), scale_factor=sf),
+                     dict(im_src=imR1_src, disp=dL1, fliplr=False, LeftTop=list(LeftTop1), scale_factor=sf),
+                     dict(im_src=dL1, disp=dL, fliplr=True, LeftTop=[0, 0], scale_factor=1),
+                     dict(im_src=dL, disp=dL1, fliplr=True, LeftTop=[0, 0], scale_factor=1)]
+        warped = imwrap_batched(jobs)
+    for n, (level, wl, sf, dL, dL1) in enumerate(levels):
+        if warped is not None:
+            imL_w, imL1_w, dL_w, dL1_w = warped[4 * n:4 * n + 4]
+        else:
+            imL_w = warp(imR_src, dL, fliplr=False, LeftTop=list(LeftTop), scale_factor=sf)
+            imL1_w = warp(imR1_src, dL1, fliplr=False, LeftTop=list(LeftTop1), scale_factor=sf)
+            dL_w = warp(dL1, dL, fliplr=True, LeftTop=[0, 0], scale_factor=1)
+            dL1_w = warp(dL, dL1, fliplr=True, LeftTop=[0, 0], scale_factor=1)
         wc = weight_common(dL, dL_w, sf) if flag_mask else None
         wc1 = weight_common(dL1, dL1_w, sf) if flag_mask else None
         k = min(level, maxlevel)

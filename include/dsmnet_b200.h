@@ -243,6 +243,32 @@ int dsm_warp_bwd(const float* gout, const float* src, const float* disp, const f
                  const float* col, float delt, int fliplr, float* gsrc, float* gdisp,
                  int B, int C, int H0, int W0, int H, int W, void* stream);
 
+/* batched form: every warp of one self-supervised training step (losses/loss.py:449-452: 4 warps x 7 pyramid levels,
+ * all independent) in ONE launch.  `jobs` is a HOST array of n <= DSM_WARP_MAX_JOBS descriptors (device pointers inside);
+ * it travels as a kernel parameter, nothing is copied or retained.  Forward uses src/disp/row/col/out; backward uses
+ * gout/src/disp/row/col/gdisp and gsrc, which may be NULL (no gradient for that source) and is NOT zeroed by the callee
+ * here (the caller zeroes all gsrc buffers with one memset of their common allocation).                            */
+#define DSM_WARP_MAX_JOBS 32
+typedef struct DsmWarpJob {
+    const float *src, *disp, *row, *col;
+    float* out;
+    const float* gout;
+    float *gsrc, *gdisp;
+    float delt;
+    int fliplr;
+    int B, C, H0, W0, H, W;
+} DsmWarpJob;
+int dsm_warp_fwd_batched(const DsmWarpJob* jobs, int n, void* stream);
+int dsm_warp_bwd_batched(const DsmWarpJob* jobs, int n, void* stream);
+
+/* ---- callers of op 5: fused SSIM map of the photometric loss (losses/SSIM.py:24-42 as used by losses/loss.py:196-236) ----
+ * a, b: [B][C][H][W] fp32; s: [B][H][W] = channel-averaged 11x11 Gaussian (sigma 1.5) SSIM, zero padding.  Backward: the
+ * gradient w.r.t. b (the warped image) only: gb [B][C][H][W] from gs [B][H][W]; ws: dsm_ssim_bwd_workspace_bytes.   */
+int dsm_ssim_fwd(const float* a, const float* b, float* s, int B, int C, int H, int W, void* stream);
+size_t dsm_ssim_bwd_workspace_bytes(int B, int H, int W);
+int dsm_ssim_bwd(const float* a, const float* b, const float* gs, float* gb, int B, int C, int H, int W,
+                 void* ws, size_t ws_bytes, void* stream);
+
 /* test hook: the integer north-west source pixel (x0,y0), int32 [B][H][W], that the warp kernels
  * derive for each output pixel — lets a test assert bit-exact sampling indices against the oracle. */
 int dsm_warp_indices(const float* disp, const float* row, const float* col, int fliplr,

@@ -347,3 +347,71 @@ def test_imwrap_rng_stream():
     torch.manual_seed(11); imwrap_BCHW(src, disp); after = torch.rand(1)
     torch.manual_seed(11); torch.rand(1); expect = torch.rand(1)
     assert torch.equal(after, expect)
+
+
+# ---- the self-supervised loss kernels: batched multi-level warp, fused SSIM (losses/loss.py:449-452, losses/SSIM.py:24-42) ----
+
+def test_batched_warp_equals_the_single_warps():
+    """all the warps of a training step in ONE launch: forward bit-identical to consecutive imwrap_BCHW calls (same RNG
+    draws in the same order), backward equal up to the order of the float atomics"""
+    from dsmnet_b200.imwrap import imwrap_BCHW, imwrap_batched
+    torch.manual_seed(11)
+    src = torch.rand(2, 3, 48 + 16, 96 + 16, device="cuda")
+    jobs = []
+    for lvl, sf in ((0, 1), (1, 2), (2, 4)):
+        h, w = 48 >> lvl, 96 >> lvl
+        d = (torch.rand(2, 1, h, w, device="cuda") * 6 / sf).requires_grad_()
+        d1 = (torch.rand(2, 1, h, w, device="cuda") * 6 / sf).requires_grad_()
+        jobs += [dict(im_src=src, disp=d, fliplr=False, LeftTop=[8, 8], scale_factor=sf),
+                 dict(im_src=d1, disp=d, fliplr=True, LeftTop=[0, 0], scale_factor=1),
+                 dict(im_src=d, disp=d1, fliplr=True, LeftTop=[0, 0], scale_factor=1)]
+    torch.manual_seed(5)
+    outs = imwrap_batched(jobs)
+    gs = [torch.randn_like(o) for o in outs]
+    leaves = []
+    for j in jobs:
+        for t in (j["im_src"], j["disp"]):
+            if t.requires_grad and all(t is not u for u in leaves):
+                leaves.append(t)
+    gb = torch.autograd.grad(outs, leaves, gs)
+    torch.manual_seed(5)
+    outs1 = [imwrap_BCHW(j["im_src"], j["disp"], j["fliplr"], j["LeftTop"], j["scale_factor"]) for j in jobs]
+    g1 = torch.autograd.grad(outs1, leaves, gs)
+    for a, b in zip(outs, outs1):
+        assert torch.equal(a, b)
+    for a, b in zip(gb, g1):
+        assert rel_err(a, b) < 1e-5
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 3, 37, 70), (1, 3, 256, 640), (1, 1, 64, 96)])
+def test_fused_ssim_vs_reference_formula(B, C, H, W):
+    """SSIM.py:24-42 in fp64 (five 11x11 Gaussian convolutions) vs the fused kernel, forward and the gradient w.r.t. the
+    second image.  Tolerance: the map is a ratio of cancelling second moments; the fp32 reference itself (stock PyTorch on
+    this GPU) sits ~1e-4 from fp64, the kernel must be at least as close."""
+    import torch.nn.functional as F
+    from dsmnet_b200.selfsup import SsimFunction, _gauss_window
+    torch.manual_seed(12)
+    a = torch.rand(B, C, H, W, device="cuda")
+    b = (a + 0.1 * torch.randn(B, C, H, W, device="cuda")).clamp(0, 1).requires_grad_()
+
+    def ref(a_, b_, dtype):
+        w = _gauss_window(11, C, a_.float()).to(dtype)
+        a_, b_ = a_.to(dtype), b_.to(dtype)
+        mu1, mu2 = F.conv2d(a_, w, padding=5), F.conv2d(b_, w, padding=5)
+        s1 = F.conv2d(a_ * a_, w, padding=5) - mu1 * mu1
+        s2 = F.conv2d(b_ * b_, w, padding=5) - mu2 * mu2
+        s12 = F.conv2d(a_ * b_, w, padding=5) - mu1 * mu2
+        return ((2 * mu1 * mu2 + 1e-4) * (2 * s12 + 9e-4)) / ((mu1 * mu1 + mu2 * mu2 + 1e-4) * (s1 + s2 + 9e-4))
+
+    s = SsimFunction.apply(a, b)
+    g = torch.randn_like(s)
+    (gb,) = torch.autograd.grad(s, b, g)
+    b64 = b.detach().double().requires_grad_()
+    s64 = ref(a.double(), b64, torch.float64)
+    (gb64,) = torch.autograd.grad(s64, b64, g.double())
+    s32 = ref(a, b.detach(), torch.float32)
+    e_mine, e_torch = float((s - s64).abs().max()), float((s32 - s64).abs().max())
+    print("ssim %s: max |ours - fp64| %.2e, |torch fp32 - fp64| %.2e; grad rel err %.2e" % ((B, C, H, W), e_mine, e_torch, rel_err(gb, gb64)))
+    assert s.shape == (B, 1, H, W)
+    assert e_mine <= max(2.0 * e_torch, 2e-4)
+    assert rel_err(gb, gb64) < 2e-3

@@ -78,7 +78,7 @@ def test_deploy_style_whole_model_odd_size():
             mod.running_var.fill_(2.0)
     m = m.cuda().eval()
     disp = io.disp_predict(m, L, Rr, use_cuda=True)
-    assert disp.shape == (375, 1242) and np.isfinite(disp).all() and disp.min() >= 0 and disp.max() <= 191
+    assert disp.shape == (375, 1242) and np.isfinite(disp).all() and disp.min() >= 0 and disp.max() <= 191.001
     # the same trunk as stock PyTorch (fp32), then the same hot path: only the trunk's number format differs
     imgL = io.normalize_imagenet(torch.from_numpy(L.transpose(2, 0, 1)[None].copy()).float().cuda() / 255)
     imgR = io.normalize_imagenet(torch.from_numpy(Rr.transpose(2, 0, 1)[None].copy()).float().cuda() / 255)

@@ -23,9 +23,19 @@ def main():
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
+    seen = {}
+    for r in rows[2:]:                                  # count the launches of each (kernel, grid); print the first of each
+        d = dict(zip(hdr, r))
+        key = (d.get("Kernel Name"), d.get("launch__grid_size"))
+        seen[key] = seen.get(key, 0) + 1
+    done = set()
     for r in rows[2:]:
         d = dict(zip(hdr, r)); u = dict(zip(hdr, units))
-        print("== %s" % d.get("Kernel Name"))
+        key = (d.get("Kernel Name"), d.get("launch__grid_size"))
+        if key in done:
+            continue
+        done.add(key)
+        print("== %s   [%d captured launch(es) with this grid; first shown]" % (d.get("Kernel Name"), seen[key]))
         for k in KEYS:
             if k in d:
                 print("   %-95s %s %s" % (k, d[k], u.get(k, "")))
