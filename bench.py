@@ -355,7 +355,7 @@ def run_psmnet(args, rank, world, device, dist, barrier):
         host_in = [torch.randn(B, C_FEAT, h, w, generator=g).pin_memory() for _ in range(2)]
     dev_in = [t.to(device) for t in host_in]
     trunk_launches = 59 if full else 0
-    launches_per_step = trunk_launches + 1 + 28 + 3      # (trunk,) concat volume, 28 conv blocks, three head launches
+    launches_per_step = trunk_launches + (0 if full else 2) + 28 + 3      # (trunk | two feature-map packs), 28 conv blocks (the first builds its volume tiles itself), three heads
 
     def step():
         with torch.no_grad():
@@ -482,7 +482,7 @@ def run_psmnet(args, rank, world, device, dist, barrier):
     def nbytes(v):
         t = v if isinstance(v, torch.Tensor) else v.data
         return t.numel() * t.element_size()
-    act_bytes = sum(nbytes(v) for k, v in ws.items() if not isinstance(v, list)) + \
+    act_bytes = sum(nbytes(v) for k, v in ws.items() if v is not None and not isinstance(v, list)) + \
         sum(nbytes(x) for k in ("out", "pre", "post") for x in ws[k])
     line = {"metric": METRIC, "value": pairs / (t_ms / 1e3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -154,6 +154,39 @@ class FusedConv3d:
         return out
 
 
+def pack_features_nhwc(f: torch.Tensor) -> torch.Tensor:
+    """NCHW fp32 feature map -> bf16 NHWC [B, H, W, C] (RNE), the operand layout of `FusedConv3d.from_features`."""
+    _lib.require_cuda(f)
+    f = f.contiguous().float()
+    B, C, H, W = f.shape
+    out = torch.empty(B, H, W, C, device=f.device, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().dsm_pack_nhwc_bf16(f.data_ptr(), out.data_ptr(), B, C, H, W, _lib.stream_ptr(f.device)), "dsm_pack_nhwc_bf16")
+    return out
+
+
+def conv_from_features(layer: "FusedConv3d", featL: torch.Tensor, featR: torch.Tensor, D: int, mode: str,
+                       out: Optional[PaddedVolume] = None) -> PaddedVolume:
+    """y = layer(concat_volume(fL, fR, D, mode)) without materialising the volume (dsm_conv3d_volume_fwd): `layer` is the
+    64 -> 32 stride-1 block that reads the volume (PSMNet dres0.0, GC-Net l19); featL / featR: bf16 NHWC [B, H, W, 32]."""
+    _lib.require_cuda(featL, featR, layer.w)
+    if layer.cin != 64 or layer.cout != 32 or layer.stride != 1 or layer.transposed:
+        raise _lib.DsmError("conv_from_features: the fused volume convolution is the 64 -> 32 stride-1 layer")
+    if featL.dtype != torch.bfloat16 or featL.shape != featR.shape or featL.dim() != 4 or featL.shape[3] != 32:
+        raise _lib.DsmError("conv_from_features: two bf16 NHWC [B, H, W, 32] feature maps expected")
+    featL = featL.contiguous(); featR = featR.contiguous()
+    B, H, W, _ = featL.shape
+    if out is None:
+        out = PaddedVolume.empty(B, 32, D, H, W, featL.device)
+    elif out.shape5 != (B, 32, D, H, W):
+        raise _lib.DsmError("conv_from_features: output geometry mismatch")
+    _lib.check(_lib.lib().dsm_conv3d_volume_fwd(
+        featL.data_ptr(), featR.data_ptr(), layer.w.data_ptr(),
+        0 if layer.identity_affine else layer.scale.data_ptr(), 0 if layer.identity_affine else layer.shift.data_ptr(),
+        out.data.data_ptr(), B, 32, 32, int(D), H, W, _lib.VOLUME_MODES[mode], int(layer.relu), layer.variant,
+        _lib.stream_ptr(featL.device)), "dsm_conv3d_volume_fwd")
+    return out
+
+
 def conv_timeouts() -> int:
     """Pipeline waits that timed out inside conv kernels since load (0 in a healthy run)."""
     return _lib.lib().dsm_debug_conv_timeouts()

@@ -466,6 +466,10 @@ struct RsGeom {
     int dbg;                 // timing experiments only (variant bits 4..6): 1 = no epilogue work, 2 = no TMA traffic, 4 = no MMAs
     int ngroups;             // output-channel groups of NP channels (Cout = ngroups*NP when > 1): CTA c owns group c % ngroups
     int w_row[27];           // first row of tap (kd*3+kh)*3+kw in the packed weights
+    // fused concat volume (FUSED instantiation only): the A operand is built in shared memory from the two feature maps
+    const __nv_bfloat16* featL;   // bf16 NHWC [B][H][W][32]
+    const __nv_bfloat16* featR;
+    int vol_mode;                 // DSM_VOL_PSM / DSM_VOL_GC / DSM_VOL_GC_RIGHT
 };
 
 template <int KC, int NP>
@@ -502,8 +506,14 @@ __device__ __forceinline__ RsItem rs_decode(const RsGeom& g, int t, int R) {
     return it;
 }
 
-template <int KC, int NP>
-__global__ void __launch_bounds__(384, 1)
+// FUSED (KC = 64 only): the input IS the concatenation cost volume of two 32-channel feature maps
+// (stackhourglass.py:124-133, gcnet.py:131-135,156-164) and is never materialised: four extra warps build every
+// 130-row x 128-byte A tile straight from the bf16 NHWC feature maps — left half of voxel (d, y, x) = fL[y][x], right
+// half = fR[y][x - d] (fL[y][x + d] for the right-reference volume), zero where the reference leaves the volume zero —
+// writing the SWIZZLE_128B pattern TMA would have produced (16-byte chunk c of row r at chunk c ^ (r & 7)), then
+// fence.proxy.async + one mbarrier arrival per warp.  The MMA and epilogue roles cannot tell the difference.
+template <int KC, int NP, bool FUSED = false>
+__global__ void __launch_bounds__(FUSED ? 512 : 384, 1)
 conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                  const __grid_constant__ RsGeom g, const float* __restrict__ scale, const float* __restrict__ shift,
                  const void* __restrict__ residual, void* __restrict__ y) {
@@ -545,7 +555,7 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_w);
         ptx::prefetch_tensormap(&map_a);
-        for (int s = 0; s < C::STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < C::STAGES; ++s) { ptx::mbar_init(full_bar(s), FUSED ? 4 : 1); ptx::mbar_init(empty_bar(s), 1); }
         for (int a = 0; a < 2; ++a) { ptx::mbar_init(tfull_bar(a), 3); ptx::mbar_init(tempty_bar(a), 8); }
         ptx::mbar_init(wfull_bar, 1);
         ptx::fence_mbar_init();
@@ -570,7 +580,7 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         __syncwarp();
         ptx::griddep_wait();                                    // weights are parameters; the activations are the previous kernel's output
         int s = 0; uint32_t ph = 0;                              // ring slot and its phase
-        for (int t = item0; t < g.nitems; t += item_step) {
+        for (int t = item0; !FUSED && t < g.nitems; t += item_step) {
             const RsItem item = rs_decode(g, t, C::R);
             for (int i = -1; i <= item.nb; ++i) {
                 const int zp = item.z0 + 1 + i;                  // padded input plane
@@ -682,6 +692,62 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             // all MMAs this warp issued for the item are in flight: its share of "accumulators complete"
             if (ptx::elect_one_sync()) ptx::umma_commit(tfull_bar(acc));
             __syncwarp();
+        }
+    } else if (FUSED && warp >= 12) {
+        // ================= volume builders: 4 warps fill the activation ring from the feature maps =================
+        ptx::griddep_wait();                                    // the feature maps are the previous kernel's output
+        const int pt = tid - 12 * 32;                            // 0..127
+        const int c16 = pt & 7;                                  // 16-byte chunk of the 128-byte row: 0-3 left half, 4-7 right half
+        const int r0 = pt >> 3;                                  // rows r0, r0 + 16, ... of the tile
+        const bool right_half = c16 >= 4;
+        const uint4* fsrc = reinterpret_cast<const uint4*>((right_half != (g.vol_mode == DSM_VOL_GC_RIGHT)) ? g.featR : g.featL);
+        // first half of a voxel: fL (fR for the right-reference volume), copied at x; second half: the other map, shifted
+        const int sgn = (g.vol_mode == DSM_VOL_GC_RIGHT) ? 1 : -1;
+        int s = 0; uint32_t ph = 0;
+        for (int t = item0; t < g.nitems; t += item_step) {
+            const RsItem item = rs_decode(g, t, C::R);
+            const size_t img = (size_t)item.b * g.H * g.W;
+            for (int i = -1; i <= item.nb; ++i) {
+                const int zp = item.z0 + 1 + i;
+                if (zp <= 0 || zp >= Dp - 1) continue;
+                const int d = zp - 1;
+#pragma unroll 1
+                for (int kh = 0; kh < 3; ++kh) {
+                    wait_bar(empty_bar(s), ph ^ 1u);
+                    const uint32_t dst0 = ring + s * C::STAGE_BYTES;
+                    const int q0 = item.tile * 128 - Wp - 1 + kh * Wp;       // padded (h,w) position of row 0
+                    constexpr int NIT = (C::A_ROWS + 15) / 16;
+                    uint4 v[NIT];
+#pragma unroll
+                    for (int k = 0; k < NIT; ++k) {
+                        const int r = r0 + 16 * k;
+                        const int q = q0 + r;
+                        v[k] = make_uint4(0u, 0u, 0u, 0u);
+                        if (r < C::A_ROWS && q >= 0 && q < plane && !(g.dbg & 2)) {
+                            const int hp = q / Wp, wp = q - hp * Wp;
+                            const int x = wp - 1, y = hp - 1;
+                            if (hp >= 1 && hp <= g.H && wp >= 1 && wp <= g.W) {
+                                bool ok; int xs = x;
+                                if (!right_half) ok = (g.vol_mode != DSM_VOL_PSM) || x >= d;
+                                else { xs = x + sgn * d; ok = (sgn < 0) ? (x >= d) : (xs < g.W); }
+                                if (ok) v[k] = __ldg(fsrc + ((img + (size_t)y * g.W + xs) << 2) + (c16 & 3));
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < NIT; ++k) {
+                        const int r = r0 + 16 * k;
+                        if (r < C::A_ROWS) {
+                            const uint32_t a = dst0 + (uint32_t)r * 128u + (uint32_t)((c16 ^ (r & 7)) << 4);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(a), "r"(v[k].x), "r"(v[k].y), "r"(v[k].z), "r"(v[k].w) : "memory");
+                        }
+                    }
+                    ptx::fence_proxy_async();                    // generic-proxy writes -> visible to the tensor core's async proxy
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(full_bar(s));
+                    if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+                }
+            }
         }
     } else {
         // ================= epilogue: 8 warps, two per TMEM lane quadrant =================
@@ -1211,11 +1277,11 @@ int launch_mode(int KC, int NP, const ConvMaps& maps, const ConvGeom& g, dim3 gr
     return DSM_EUNSUPPORTED;
 }
 
-template <int KC, int NP>
+template <int KC, int NP, bool FUSED = false>
 int launch_rs(const CUtensorMap& map_a, const CUtensorMap& map_w, const RsGeom& g, const float* scale, const float* shift,
               const void* residual, void* y, cudaStream_t st) {
     using C = RsCfg<KC, NP>;
-    auto kern = conv3d_rs_kernel<KC, NP>;
+    auto kern = conv3d_rs_kernel<KC, NP, FUSED>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) return (int)e;
     int nsm = DSM_NUM_SMS_B200, dev = 0;
@@ -1223,7 +1289,7 @@ int launch_rs(const CUtensorMap& map_a, const CUtensorMap& map_w, const RsGeom& 
     int per_group = nsm / g.ngroups;                            // persistent: one CTA per SM, split evenly over the channel groups
     if (per_group > g.nitems) per_group = g.nitems;
     const int nblocks = per_group * g.ngroups;
-    launch_kernel(kern, dim3(nblocks), dim3(C::THREADS), C::SMEM, st, map_a, map_w, g, scale, shift, residual, y);
+    launch_kernel(kern, dim3(nblocks), dim3(C::THREADS + (FUSED ? 128 : 0)), C::SMEM, st, map_a, map_w, g, scale, shift, residual, y);
     return dsm_launch_status();
 }
 
@@ -1572,6 +1638,41 @@ extern "C" int dsm_conv3d_fwd_ex(const void* x, const void* w_packed, const floa
     DsmDeviceGuard dsm_guard_(x);
     return conv3d_dispatch(x, w_packed, scale, shift, residual, y, B, Cin, Cout, D, H, W, stride, transposed, relu,
                            y_dtype, Do, Ho, Wo, variant, stream);
+}
+
+// The first 3-D convolution of PSMNet / GC-Net (dres0.0, l19: 64 -> 32, stride 1) fused with the concatenation cost volume
+// it reads: see conv3d_rs_kernel<64, 32, FUSED>.  featL / featR: bf16 NHWC [B][H][W][32].
+extern "C" int dsm_conv3d_volume_fwd(const void* featL, const void* featR, const void* w_packed, const float* scale, const float* shift,
+                                     void* y, int B, int C, int Cout, int D, int H, int W, int mode, int relu, int variant, void* stream) {
+    DsmDeviceGuard dsm_guard_(featL);
+    if (!featL || !featR || !w_packed || !y || B <= 0 || D <= 0 || H <= 0 || W <= 0) return DSM_EINVAL;
+    if (mode < DSM_VOL_PSM || mode > DSM_VOL_GC_RIGHT || relu < 0 || relu > 2) return DSM_EINVAL;
+    if (C != 32 || Cout != 32) return DSM_EUNSUPPORTED;                  // 2C = 64 input channels, one 128-byte row per voxel
+    if (!dsm_aligned16(featL) || !dsm_aligned16(featR) || !dsm_aligned16(w_packed) || !dsm_aligned32(y)) return DSM_EALIGN;
+    const int Hp = H + 2, Wp = W + 2;
+    if ((long long)B * (D + 2) * Hp * Wp > 0x7fffff00LL) return DSM_EUNSUPPORTED;
+    g_launch_pdl = (variant & 128) != 0;
+    CUtensorMap map_w;
+    {
+        cuuint64_t dims[2] = {64, (cuuint64_t)27 * 32};
+        cuuint64_t strides[1] = {64 * 2};
+        cuuint32_t box[2] = {64, 32};
+        if (!encode_map(&map_w, w_packed, 2, dims, strides, box, 128)) return DSM_EDRIVER;
+    }
+    RsGeom rg;
+    memset(&rg, 0, sizeof(rg));
+    rg.B = B; rg.D = D; rg.H = H; rg.W = W; rg.Do = D; rg.Ho = H; rg.Wo = W;
+    rg.Cout = 32; rg.relu = relu; rg.y_f32 = 0;
+    rg.plane_tiles = dsm_ceil_div(Hp * Wp, 128);
+    rg.nbands = dsm_ceil_div(D, 8);
+    const long long ni = (long long)B * rg.nbands * rg.plane_tiles;
+    if (ni > 0x7fffffffLL) return DSM_EUNSUPPORTED;
+    rg.nitems = (int)ni;
+    rg.dbg = (variant >> 4) & 7;
+    rg.ngroups = 1;
+    for (int t = 0; t < 27; ++t) rg.w_row[t] = t * 32;
+    rg.featL = static_cast<const __nv_bfloat16*>(featL); rg.featR = static_cast<const __nv_bfloat16*>(featR); rg.vol_mode = mode;
+    return launch_rs<64, 32, true>(map_w /*unused: no activation tensor map*/, map_w, rg, scale, shift, nullptr, y, (cudaStream_t)stream);
 }
 
 // 2-D convolution block of the feature-extraction trunks; see conv2d_dispatch and include/dsmnet_b200.h

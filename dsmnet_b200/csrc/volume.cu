@@ -299,7 +299,38 @@ unpack_ndhwc_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, 
     }
 }
 
+// NCHW fp32 -> NHWC bf16 [B][H][W][C] (the feature-map layout of the fused volume convolution); CTA = one image row
+__global__ void __launch_bounds__(256)
+pack_nhwc_kernel(const float* __restrict__ x, uint4* __restrict__ y, int C, int H, int W) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __nv_bfloat16* s = reinterpret_cast<__nv_bfloat16*>(smem_raw);            // [W][C]
+    const int yy = blockIdx.x, b = blockIdx.y;
+    const float* src = x + ((size_t)b * C * H + yy) * W;
+    const size_t cstride = (size_t)H * W;
+    for (int i = threadIdx.x; i < C * W; i += blockDim.x) {
+        const int c = i / W, xx = i - c * W;
+        s[xx * C + c] = __float2bfloat16_rn(__ldg(src + c * cstride + xx));
+    }
+    __syncthreads();
+    const uint4* v = reinterpret_cast<const uint4*>(s);
+    uint4* orow = y + ((size_t)b * H + yy) * (size_t)(W * C / 8);
+    for (int i = threadIdx.x; i < W * C / 8; i += blockDim.x) orow[i] = v[i];
+}
+
 }  // namespace
+
+extern "C" int dsm_pack_nhwc_bf16(const float* x, void* y, int B, int C, int H, int W, void* stream) {
+    DsmDeviceGuard dsm_guard_(x);
+    if (!x || !y || B <= 0 || C <= 0 || H <= 0 || W <= 0) return DSM_EINVAL;
+    if (C % 8 != 0 || H > 65535 * 32 || B > 65535) return DSM_EUNSUPPORTED;
+    if (!dsm_aligned16(y)) return DSM_EALIGN;
+    const size_t smem = (size_t)W * C * sizeof(__nv_bfloat16);
+    if (smem > 200 * 1024) return DSM_EUNSUPPORTED;
+    cudaError_t e = cudaFuncSetAttribute(pack_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    pack_nhwc_kernel<<<dim3(H, B), 256, smem, (cudaStream_t)stream>>>(x, (uint4*)y, C, H, W);
+    return dsm_launch_status();
+}
 
 extern "C" int dsm_concat_volume_fwd(const float* fL, const float* fR, void* out,
                                      int B, int C, int D, int H, int W,

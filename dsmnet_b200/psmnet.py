@@ -10,8 +10,8 @@ The 2-D feature extractor (a caller of the hot path) runs on the library's 2-D k
 (dsmnet_b200/trunk2d.py) and as stock PyTorch under autograd; the
 path from the two feature maps on — concat volume (stackhourglass.py:124-133), dres0..classif3
 (:135-149) and the three upsample+softmax+regression heads (:152-166) — runs as:
-  concat_volume (padded NDHWC bf16)  ->  25 fused tcgen05 conv blocks  ->  3 fp32 Cout=1 convs
-  ->  3 fused upsample+soft-argmin kernels.
+  dres0.0 fused with the concat volume it reads (the volume is never written; csrc/conv3d.cu, FUSED plane-sharing
+  kernel)  ->  24 more fused tcgen05 conv blocks  ->  3 fp32 Cout=1 convs  ->  3 fused upsample+soft-argmin kernels.
 Inference: eval-mode BatchNorm folded into the conv epilogue, everything fused.  With gradients enabled
 (train mode, or eval-mode with parameters/inputs that require grad) the same graph runs through
 ``aggregate_train``: convolutions forward/backward on the sm_100a kernels, BatchNorm (batch statistics or frozen) +
@@ -29,7 +29,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib
-from .conv3d import FusedConv3d
+from .conv3d import FusedConv3d, conv_from_features, pack_features_nhwc
 from .cost_volume import concat_volume, concat_volume_padded
 from .softargmin import upsample_softargmin
 from .volume_layout import PaddedVolume
@@ -64,6 +64,8 @@ PDL_VARIANT = 0 if os.environ.get("DSM_NO_PDL") == "1" else 128
 CLS_SIDE_STREAM = os.environ.get("DSM_CLS_STREAM", "1") != "0"
 # with the second stream: launch each head as soon as its cost exists (DSM_EARLY_HEADS=0: one stacked launch at the end)
 EARLY_HEADS = os.environ.get("DSM_EARLY_HEADS", "1") != "0"
+# dres0.0 reads the two feature maps and builds its volume tiles on the fly (DSM_FUSED_VOLUME=0: materialise the volume)
+FUSED_VOLUME = os.environ.get("DSM_FUSED_VOLUME", "1") != "0"
 
 
 class _Plan:
@@ -164,7 +166,7 @@ class PSMNetHotPath(nn.Module):
         D4, H4, W4 = half(D2), half(H2), half(W2)
         P = PaddedVolume.empty
         ws = dict(
-            vol=P(B, 64, D, H, W, device, zero_rim=False),
+            vol=None,                 # only the unfused route (DSM_FUSED_VOLUME=0) materialises the volume
             a=P(B, 32, D, H, W, device), c0=P(B, 32, D, H, W, device), t=P(B, 32, D, H, W, device),
             cost0=P(B, 32, D, H, W, device),
             out=[P(B, 32, D, H, W, device) for _ in range(3)],
@@ -220,12 +222,25 @@ class PSMNetHotPath(nn.Module):
         True if it was used (the caller then skips its own head launch)."""
         if self._wants_autograd(fL, fR):
             return self.aggregate_train(fL, fR)
-        B, C, H, W = fL.shape
+        nhwc = fL.dtype == torch.bfloat16                 # bf16 NHWC [B, H, W, 32] straight from the 2-D trunk's last layer
+        if nhwc:
+            B, H, W, C = fL.shape
+        else:
+            B, C, H, W = fL.shape
         D = self.maxdisp // 4
         plan = self._get_plan(fL.device)
         ws = self._workspace(B, D, H, W, fL.device)
-        vol = concat_volume(fL, fR, D, "psm", padded_bf16=True, out=ws["vol"])
-        plan.dres0_0(vol, ws["a"])
+        if nhwc and not (FUSED_VOLUME and C == 32):
+            fL = fL.permute(0, 3, 1, 2).float().contiguous(); fR = fR.permute(0, 3, 1, 2).float().contiguous(); nhwc = False
+        if FUSED_VOLUME and C == 32:
+            # the 196 MB volume is never written: dres0.0 builds its operand tiles from the (L2-resident) feature maps
+            conv_from_features(plan.dres0_0, fL if nhwc else pack_features_nhwc(fL), fR if nhwc else pack_features_nhwc(fR),
+                               D, "psm", ws["a"])
+        else:
+            if ws["vol"] is None:
+                ws["vol"] = PaddedVolume.empty(B, 64, D, H, W, fL.device, zero_rim=False)
+            vol = concat_volume(fL, fR, D, "psm", padded_bf16=True, out=ws["vol"])
+            plan.dres0_0(vol, ws["a"])
         plan.dres0_2(ws["a"], ws["c0"])
         plan.dres1_0(ws["c0"], ws["t"])
         cost0 = plan.dres1_2(ws["t"], ws["cost0"], residual=ws["c0"])            # :136
@@ -290,6 +305,8 @@ class PSMNetHotPath(nn.Module):
 
     def forward(self, fL, fR, out_hw):
         train = self._wants_autograd(fL, fR)
+        if fL.dtype == torch.bfloat16 and train:
+            raise _lib.DsmError("bf16 NHWC feature maps are an inference-only input of the hot path")
         if CLS_SIDE_STREAM and EARLY_HEADS and not train:
             # each head is launched on the classifier stream as soon as its cost exists: only the head of cost3 is left
             # on the critical path (one stacked launch of all three after the last classifier cost ~95 us more)
@@ -308,7 +325,7 @@ class PSMNetHotPath(nn.Module):
             B = c1.shape[0]
             preds = upsample_softargmin(torch.cat((c3, c2, c1), 0), (self.maxdisp, out_hw[0], out_hw[1]), self.align_corners)
             return [preds[:B], preds[B:2 * B], preds[2 * B:]]
-        B, _, H, W = fL.shape
+        B, H, W = (fL.shape[0], fL.shape[1], fL.shape[2]) if fL.dtype == torch.bfloat16 else (fL.shape[0], fL.shape[2], fL.shape[3])
         ws = self._workspace(B, self.maxdisp // 4, H, W, fL.device)
         size = (self.maxdisp, out_hw[0], out_hw[1])
         # heads of stackhourglass.py:152-166 for (cost3, cost2, cost1) in ONE launch over the stacked costs
@@ -380,11 +397,15 @@ class feature_extraction(nn.Module):
         layers += [BasicBlock(planes, planes, 1, None, pad, dilation) for _ in range(1, blocks)]
         return nn.Sequential(*layers)
 
-    def forward(self, x):
+    def forward(self, x, nhwc_bf16=False):
+        """`nhwc_bf16` (CUDA inference only): return the feature map as bf16 [B, H/4, W/4, 32], the operand layout of the fused
+        volume convolution, instead of the reference's fp32 NCHW."""
         if x.is_cuda and not self.training and not torch.is_grad_enabled():
             # inference: every layer on the library's kernels (dsmnet_b200/trunk2d.py)
             from .trunk2d import PSMNetTrunkPlan, cached_plan
-            return cached_plan(self, PSMNetTrunkPlan, x.device)(x)
+            return cached_plan(self, PSMNetTrunkPlan, x.device)(x, nhwc_bf16)
+        if nhwc_bf16:
+            raise _lib.DsmError("feature_extraction: the bf16 NHWC output exists on the CUDA inference path only")
         out = self.layer1(self.firstconv(x))
         raw = self.layer2(out)
         skip = self.layer4(self.layer3(raw))
@@ -425,10 +446,11 @@ class PSMNet(PSMNetHotPath):
     def forward(self, left, right, mode="train"):
         B = left.size(0)
         if left.is_cuda and not self.training and not torch.is_grad_enabled():
-            fea = self.feature_extraction(torch.cat((left, right), 0))     # both images as one batch through the trunk
+            # both images as one batch through the trunk; its last layer writes the bf16 NHWC maps dres0.0 reads
+            fea = self.feature_extraction(torch.cat((left, right), 0), nhwc_bf16=FUSED_VOLUME)
             refimg_fea, targetimg_fea = fea[:B], fea[B:]
         else:
-            refimg_fea = self.feature_extraction(left)
-            targetimg_fea = self.feature_extraction(right)
-        preds = PSMNetHotPath.forward(self, refimg_fea.float(), targetimg_fea.float(), (left.size(2), left.size(3)))
+            refimg_fea = self.feature_extraction(left).float()
+            targetimg_fea = self.feature_extraction(right).float()
+        preds = PSMNetHotPath.forward(self, refimg_fea, targetimg_fea, (left.size(2), left.size(3)))
         return [0, 0, 0], preds

@@ -218,7 +218,7 @@ class PSMNetTrunkPlan:
             free = [b for b in pool if b is not x]
         return x, x_c0
 
-    def __call__(self, img: torch.Tensor) -> torch.Tensor:
+    def __call__(self, img: torch.Tensor, nhwc_bf16: bool = False) -> torch.Tensor:
         _lib.require_cuda(img)
         img = img.contiguous().float()
         B, _, H, W = img.shape
@@ -242,6 +242,10 @@ class PSMNetTrunkPlan:
                                           cat.ptr(0), B, H4, W4, cat.rim, cat.C, 192, int(bool(self.align_corners)),
                                           ws["spp"].data_ptr(), ws["spp"].numel() * 4, _lib.stream_ptr(img.device)), "dsm_spp_fwd")
         self.last0(cat, q128[0])
+        if nhwc_bf16:                                   # bf16 [B][H/4][W/4][32]: what the fused volume convolution reads
+            feat = PaddedImage(torch.empty(B * H4 * W4 * 32, device=img.device, dtype=torch.bfloat16), B, 32, H4, W4, 0)
+            self.last2(q128[0], feat)
+            return feat.view5()
         out = torch.empty(B, 32, H4, W4, device=img.device, dtype=torch.float32)
         self.last2(q128[0], out)
         return out

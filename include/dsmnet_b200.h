@@ -156,6 +156,15 @@ int dsm_conv3d_c1_bwd(const void* x, const float* gy, const float* w, void* gx, 
                       int B, int D, int H, int W, int Do, int Ho, int Wo, int transposed,
                       void* ws, size_t ws_bytes, void* stream);
 
+/* The volume is never materialised: the first 3-D convolution of the stack (PSMNet dres0.0,
+ * stackhourglass.py:73,135; GC-Net l19, gcnet.py:38,94 — Conv3d(64 -> 32, k3, s1) + BN + ReLU) computed straight from the two
+ * 32-channel feature maps.  featL / featR: bf16 NHWC [B][H][W][32] (dsm_pack_nhwc_bf16, or the 2-D trunk's last layer);
+ * y: padded NDHWC bf16 [B][D+2][H+2][W+2][32]; mode as dsm_concat_volume_fwd; w_packed / scale / shift / relu / variant as
+ * dsm_conv3d_fwd_ex.  Same result as dsm_concat_volume_fwd (bf16, padded) followed by dsm_conv3d_fwd.               */
+int dsm_conv3d_volume_fwd(const void* featL, const void* featR, const void* w_packed, const float* scale, const float* shift,
+                          void* y, int B, int C, int Cout, int D, int H, int W, int mode, int relu, int variant, void* stream);
+int dsm_pack_nhwc_bf16(const float* x_nchw, void* y_nhwc_bf16, int B, int C, int H, int W, void* stream);
+
 /* cropped skip add of the training path (myadd_3d / myAdd3d crop-to-min, stackhourglass.py:10-20, util_fun.py:41-51):
  * `full` is a padded bf16 volume of extent (Dn,Hn,Wn) (the BatchNorm'ed deconv output, statistics over all of it as in
  * the reference), residual / z have the smaller extent (Do,Ho,Wo): z = act(crop(full) + residual), relu 0/1 (after the

@@ -320,3 +320,45 @@ def test_pack_weight_kernel_matches_host_packing(cout, cin):
     if cout >= 16:
         ref = pack_weight(w.flip(2, 3, 4).transpose(0, 1).contiguous(), False)                        # stride-1 dgrad filter
         assert torch.equal(pack_weight_device(w.cuda(), 2).cpu(), ref)
+
+
+@pytest.mark.parametrize("mode", ["psm", "gc", "gc_right"])
+@pytest.mark.parametrize("B,D,H,W", [(2, 5, 7, 19), (1, 12, 9, 150), (1, 6, 20, 10)])
+def test_fused_volume_conv_equals_volume_then_conv(mode, B, D, H, W):
+    """dsm_conv3d_volume_fwd (the volume is never written) vs dsm_concat_volume_fwd + dsm_conv3d_fwd on the same weights, and
+    vs the oracle: every mode, batch > 1, D > a tile row, W < 16 (row wraps inside one 16-row step of the builder warps)"""
+    from dsmnet_b200.conv3d import FusedConv3d, conv_from_features, pack_features_nhwc, conv_timeouts
+    from dsmnet_b200.cost_volume import concat_volume
+    torch.manual_seed(21)
+    fL = torch.randn(B, 32, H, W); fR = torch.randn(B, 32, H, W)
+    w = torch.randn(32, 64, 3, 3, 3) * (2.0 / (27 * 64)) ** 0.5
+    scale = torch.rand(32) + 0.5; shift = torch.randn(32) * 0.3
+    layer = FusedConv3d(w.cuda(), None, None, 1, False, 1)
+    layer.set_affine(scale, shift)
+    fused = conv_from_features(layer, pack_features_nhwc(fL.cuda()), pack_features_nhwc(fR.cuda()), D, mode).to_ncdhw().cpu()
+    plain = layer(concat_volume(fL.cuda(), fR.cuda(), D, mode, padded_bf16=True)).to_ncdhw().cpu()
+    torch.cuda.synchronize()
+    assert conv_timeouts() == 0
+    vol = O.concat_volume(fL, fR, D, mode)
+    ref = O.conv3d_block(vol, w, scale, shift, 1, False, None, True, torch.bfloat16)
+    tol = 2.0 ** -7 * float(ref.abs().max())
+    assert float((fused - ref).abs().max()) <= tol
+    # same operands, same MMAs: only the order in which the three issuing warps reach the accumulator may differ
+    assert float((fused - plain).abs().max()) <= 2.0 ** -8 * float(ref.abs().max())
+    assert float((fused != plain).float().mean()) < 0.01
+
+
+def test_fused_volume_conv_full_size():
+    """BASELINE size (volume 64x48x96x312): the fused first layer against the materialised route"""
+    from dsmnet_b200.conv3d import FusedConv3d, conv_from_features, pack_features_nhwc, conv_timeouts
+    from dsmnet_b200.cost_volume import concat_volume
+    torch.manual_seed(22)
+    fL = torch.randn(1, 32, 96, 312, device="cuda"); fR = torch.randn(1, 32, 96, 312, device="cuda")
+    w = torch.randn(32, 64, 3, 3, 3) * (2.0 / (27 * 64)) ** 0.5
+    layer = FusedConv3d(w.cuda(), None, None, 1, False, 1)
+    fused = conv_from_features(layer, pack_features_nhwc(fL), pack_features_nhwc(fR), 48, "psm").to_ncdhw()
+    plain = layer(concat_volume(fL, fR, 48, "psm", padded_bf16=True)).to_ncdhw()
+    torch.cuda.synchronize()
+    assert conv_timeouts() == 0
+    assert float((fused - plain).abs().max()) <= 2.0 ** -8 * float(plain.abs().max())
+    assert float((fused != plain).float().mean()) < 0.01
