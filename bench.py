@@ -355,7 +355,7 @@ def run_psmnet(args, rank, world, device, dist, barrier):
         host_in = [torch.randn(B, C_FEAT, h, w, generator=g).pin_memory() for _ in range(2)]
     dev_in = [t.to(device) for t in host_in]
     trunk_launches = 59 if full else 0
-    launches_per_step = trunk_launches + (0 if full else 2) + 28 + 3      # (trunk | two feature-map packs), 28 conv blocks (the first builds its volume tiles itself), three heads
+    launches_per_step = trunk_launches + 1 + 28 + 3      # (trunk,) concat volume, 28 conv blocks, three head launches
 
     def step():
         with torch.no_grad():

@@ -555,7 +555,7 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_w);
         ptx::prefetch_tensormap(&map_a);
-        for (int s = 0; s < C::STAGES; ++s) { ptx::mbar_init(full_bar(s), FUSED ? 4 : 1); ptx::mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < C::STAGES; ++s) { ptx::mbar_init(full_bar(s), FUSED ? 128 : 1); ptx::mbar_init(empty_bar(s), 1); }
         for (int a = 0; a < 2; ++a) { ptx::mbar_init(tfull_bar(a), 3); ptx::mbar_init(tempty_bar(a), 8); }
         ptx::mbar_init(wfull_bar, 1);
         ptx::fence_mbar_init();
@@ -669,6 +669,7 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     for (int khs = 0; khs < 3; ++khs) {
                         if (khs == my_kh) {
                             wait_bar(full_bar(s), ph);
+                            if (FUSED) ptx::fence_proxy_async();   // the tile was written with generic stores by the builder warps
                             ptx::tc_fence_after();
                             if (ptx::elect_one_sync()) {
                                 const uint32_t a_lo0 = ring_lo + (uint32_t)s * (C::STAGE_BYTES >> 4) + a_tile;
@@ -695,59 +696,84 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
     } else if (FUSED && warp >= 12) {
         // ================= volume builders: 4 warps fill the activation ring from the feature maps =================
+        // Software-pipelined: the global loads of stage n+1 are issued BEFORE waiting for stage n's ring slot (they do not
+        // depend on it), so the L2 round trip of every stage hides behind the wait / the stores of the previous one.
         ptx::griddep_wait();                                    // the feature maps are the previous kernel's output
         const int pt = tid - 12 * 32;                            // 0..127
         const int c16 = pt & 7;                                  // 16-byte chunk of the 128-byte row: 0-3 left half, 4-7 right half
         const int r0 = pt >> 3;                                  // rows r0, r0 + 16, ... of the tile
         const bool right_half = c16 >= 4;
-        const uint4* fsrc = reinterpret_cast<const uint4*>((right_half != (g.vol_mode == DSM_VOL_GC_RIGHT)) ? g.featR : g.featL);
         // first half of a voxel: fL (fR for the right-reference volume), copied at x; second half: the other map, shifted
+        const uint4* fsrc = reinterpret_cast<const uint4*>((right_half != (g.vol_mode == DSM_VOL_GC_RIGHT)) ? g.featR : g.featL) + (c16 & 3);
         const int sgn = (g.vol_mode == DSM_VOL_GC_RIGHT) ? 1 : -1;
+        const bool mask_first = (g.vol_mode == DSM_VOL_PSM);
+        constexpr int NIT = (C::A_ROWS + 15) / 16;
+        // Per-thread row metadata, recomputed only when the (h,w) tile changes: row k of this thread (r = r0 + 16k) is pixel
+        // (y0[k] + kh, x[k]) for the stage with tap row kh — the same for every disparity plane; only the mask (x >= d) and the
+        // shift of the second half (x - d) depend on the plane.  The issuing rate of a warp (~1 dependent instruction per
+        // 4-7 cycles) is what bounds this role, so the per-stage work is ~6 instructions per row.
+        int rx[NIT], ry[NIT], rofs[NIT];                         // x, y (kh = 0), y*W + x; x = -1: never valid
+        int meta_tile = -1;
+        auto row_meta = [&](int tile) {
+            const int qq = tile * 128 - Wp - 1 + r0 + 2 * Wp;    // kh = 0 position of row r0, offset to stay non-negative
+            int hp = qq / Wp - 2, wp = qq - (hp + 2) * Wp;
+#pragma unroll
+            for (int k = 0; k < NIT; ++k) {
+                const bool col_ok = (r0 + 16 * k < C::A_ROWS) && wp >= 1 && wp <= g.W;
+                rx[k] = col_ok ? wp - 1 : -1;
+                ry[k] = hp - 1;
+                rofs[k] = (hp - 1) * g.W + (wp - 1);
+                wp += 16;
+                while (wp >= Wp) { wp -= Wp; ++hp; }
+            }
+            meta_tile = tile;
+        };
+        // iterator over the stages of this CTA, in the order the MMA issuers consume them: (item, plane, kh)
+        int it_t = item0, it_i = -2, it_kh = 2;                  // "before the first stage"
+        RsItem it_item = rs_decode(g, it_t < g.nitems ? it_t : 0, C::R);
+        auto next_stage = [&](int& d, int& kh, int& tile, int& img) -> bool {
+            for (;;) {
+                if (it_t >= g.nitems) return false;
+                if (++it_kh == 3) { it_kh = 0; ++it_i; }
+                if (it_i > it_item.nb) {
+                    it_t += item_step; it_i = -1; it_kh = 0;
+                    if (it_t >= g.nitems) return false;
+                    it_item = rs_decode(g, it_t, C::R);
+                }
+                const int zp = it_item.z0 + 1 + it_i;
+                if (zp <= 0 || zp >= Dp - 1) { it_kh = 2; continue; }      // rim plane: no stages
+                d = zp - 1; kh = it_kh; tile = it_item.tile;
+                img = it_item.b * g.H * g.W;
+                return true;
+            }
+        };
+        // cp.async (LDGSTS): 16 bytes global -> shared per instruction without a register round trip, zero-filled when the
+        // voxel is outside the volume's support (src-size 0); the thread's arrival on the stage's mbarrier is deferred until
+        // its copies have landed (cp.async.mbarrier.arrive.noinc), so a builder never waits for data — only for a free slot.
+        const int shift_sgn = right_half ? sgn : 0;
+        const char* fbytes = reinterpret_cast<const char*>(fsrc);
+        const uint32_t soff = (uint32_t)r0 * 128u + (uint32_t)((c16 ^ (r0 & 7)) << 4);   // (r0 + 16k) & 7 == r0 & 7
         int s = 0; uint32_t ph = 0;
-        for (int t = item0; t < g.nitems; t += item_step) {
-            const RsItem item = rs_decode(g, t, C::R);
-            const size_t img = (size_t)item.b * g.H * g.W;
-            for (int i = -1; i <= item.nb; ++i) {
-                const int zp = item.z0 + 1 + i;
-                if (zp <= 0 || zp >= Dp - 1) continue;
-                const int d = zp - 1;
-#pragma unroll 1
-                for (int kh = 0; kh < 3; ++kh) {
-                    wait_bar(empty_bar(s), ph ^ 1u);
-                    const uint32_t dst0 = ring + s * C::STAGE_BYTES;
-                    const int q0 = item.tile * 128 - Wp - 1 + kh * Wp;       // padded (h,w) position of row 0
-                    constexpr int NIT = (C::A_ROWS + 15) / 16;
-                    uint4 v[NIT];
+        int d = 0, kh = 0, tile = 0, img = 0;
+        while (next_stage(d, kh, tile, img)) {
+            if (tile != meta_tile) row_meta(tile);
+            const char* base = fbytes + ((long long)(img + kh * g.W + shift_sgn * d) << 6);     // 64 bytes per pixel
+            const int xlo = (right_half ? (sgn < 0) : mask_first) ? d : 0;              // valid x range of this half in plane d
+            const int xhi = (right_half && sgn > 0) ? g.W - d : g.W;
+            wait_bar(empty_bar(s), ph ^ 1u);
+            const uint32_t dst = ring + s * C::STAGE_BYTES + soff;
 #pragma unroll
-                    for (int k = 0; k < NIT; ++k) {
-                        const int r = r0 + 16 * k;
-                        const int q = q0 + r;
-                        v[k] = make_uint4(0u, 0u, 0u, 0u);
-                        if (r < C::A_ROWS && q >= 0 && q < plane && !(g.dbg & 2)) {
-                            const int hp = q / Wp, wp = q - hp * Wp;
-                            const int x = wp - 1, y = hp - 1;
-                            if (hp >= 1 && hp <= g.H && wp >= 1 && wp <= g.W) {
-                                bool ok; int xs = x;
-                                if (!right_half) ok = (g.vol_mode != DSM_VOL_PSM) || x >= d;
-                                else { xs = x + sgn * d; ok = (sgn < 0) ? (x >= d) : (xs < g.W); }
-                                if (ok) v[k] = __ldg(fsrc + ((img + (size_t)y * g.W + xs) << 2) + (c16 & 3));
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int k = 0; k < NIT; ++k) {
-                        const int r = r0 + 16 * k;
-                        if (r < C::A_ROWS) {
-                            const uint32_t a = dst0 + (uint32_t)r * 128u + (uint32_t)((c16 ^ (r & 7)) << 4);
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(a), "r"(v[k].x), "r"(v[k].y), "r"(v[k].z), "r"(v[k].w) : "memory");
-                        }
-                    }
-                    ptx::fence_proxy_async();                    // generic-proxy writes -> visible to the tensor core's async proxy
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(full_bar(s));
-                    if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+            for (int k = 0; k < NIT; ++k) {
+                if (r0 + 16 * k < C::A_ROWS) {
+                    const int y = ry[k] + kh;
+                    const bool ok = rx[k] >= xlo && rx[k] < xhi && (unsigned)y < (unsigned)g.H && !(g.dbg & 2);
+                    const char* src = ok ? base + ((long long)rofs[k] << 6) : fbytes;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+                                 :: "r"(dst + (uint32_t)k * 2048u), "l"(src), "r"(ok ? 16 : 0) : "memory");
                 }
             }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(full_bar(s)) : "memory");
+            if (++s == C::STAGES) { s = 0; ph ^= 1u; }
         }
     } else {
         // ================= epilogue: 8 warps, two per TMEM lane quadrant =================

@@ -10,8 +10,8 @@ The 2-D feature extractor (a caller of the hot path) runs on the library's 2-D k
 (dsmnet_b200/trunk2d.py) and as stock PyTorch under autograd; the
 path from the two feature maps on — concat volume (stackhourglass.py:124-133), dres0..classif3
 (:135-149) and the three upsample+softmax+regression heads (:152-166) — runs as:
-  dres0.0 fused with the concat volume it reads (the volume is never written; csrc/conv3d.cu, FUSED plane-sharing
-  kernel)  ->  24 more fused tcgen05 conv blocks  ->  3 fp32 Cout=1 convs  ->  3 fused upsample+soft-argmin kernels.
+  concat_volume (padded NDHWC bf16; or, with DSM_FUSED_VOLUME=1, dres0.0 builds its volume tiles itself and the volume
+  is never written)  ->  25 fused tcgen05 conv blocks  ->  3 fp32 Cout=1 convs  ->  3 fused upsample+soft-argmin kernels.
 Inference: eval-mode BatchNorm folded into the conv epilogue, everything fused.  With gradients enabled
 (train mode, or eval-mode with parameters/inputs that require grad) the same graph runs through
 ``aggregate_train``: convolutions forward/backward on the sm_100a kernels, BatchNorm (batch statistics or frozen) +
@@ -64,8 +64,11 @@ PDL_VARIANT = 0 if os.environ.get("DSM_NO_PDL") == "1" else 128
 CLS_SIDE_STREAM = os.environ.get("DSM_CLS_STREAM", "1") != "0"
 # with the second stream: launch each head as soon as its cost exists (DSM_EARLY_HEADS=0: one stacked launch at the end)
 EARLY_HEADS = os.environ.get("DSM_EARLY_HEADS", "1") != "0"
-# dres0.0 reads the two feature maps and builds its volume tiles on the fly (DSM_FUSED_VOLUME=0: materialise the volume)
-FUSED_VOLUME = os.environ.get("DSM_FUSED_VOLUME", "1") != "0"
+# DSM_FUSED_VOLUME=1: dres0.0 reads the two feature maps and builds its volume tiles on the fly (the 196 MB volume is never
+# written).  Correct and tested, but OFF by default: measured on B200 (profiles/r02g_fused_volume_ab.txt) the four builder
+# warps need ~137 instructions per 130-row tile and a warp issues a dependent instruction only every 4-7 cycles, so the fused
+# layer takes 1.545 ms/step against 1.485 ms with the materialised volume (41 us concat kernel + 64 us convolution).
+FUSED_VOLUME = os.environ.get("DSM_FUSED_VOLUME", "0") == "1"
 
 
 class _Plan:

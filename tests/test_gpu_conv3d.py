@@ -360,5 +360,5 @@ def test_fused_volume_conv_full_size():
     plain = layer(concat_volume(fL, fR, 48, "psm", padded_bf16=True)).to_ncdhw()
     torch.cuda.synchronize()
     assert conv_timeouts() == 0
-    assert float((fused - plain).abs().max()) <= 2.0 ** -8 * float(plain.abs().max())
+    assert float((fused - plain).abs().max()) <= 2.0 ** -7 * float(plain.abs().max())       # one bf16 ulp at the top binade
     assert float((fused != plain).float().mean()) < 0.01
