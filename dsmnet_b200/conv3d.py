@@ -154,27 +154,39 @@ class FusedConv3d:
         return out
 
 
-def pack_features_nhwc(f: torch.Tensor) -> torch.Tensor:
-    """NCHW fp32 feature map -> bf16 NHWC [B, H, W, C] (RNE), the operand layout of `FusedConv3d.from_features`."""
+def pack_features_nhwc(f: torch.Tensor, rim: int = 1) -> torch.Tensor:
+    """NCHW fp32 feature map -> bf16 NHWC with a zero rim, [B, H+2r, W+2r, C] (RNE): the operand layout of `conv_from_features`."""
     _lib.require_cuda(f)
     f = f.contiguous().float()
     B, C, H, W = f.shape
-    out = torch.empty(B, H, W, C, device=f.device, dtype=torch.bfloat16)
-    _lib.check(_lib.lib().dsm_pack_nhwc_bf16(f.data_ptr(), out.data_ptr(), B, C, H, W, _lib.stream_ptr(f.device)), "dsm_pack_nhwc_bf16")
+    out = torch.empty(B, H + 2 * rim, W + 2 * rim, C, device=f.device, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().dsm_pack_nhwc_bf16(f.data_ptr(), out.data_ptr(), B, C, H, W, rim, _lib.stream_ptr(f.device)), "dsm_pack_nhwc_bf16")
     return out
+
+
+def pack_feature_pair_nhwc(fL: torch.Tensor, fR: torch.Tensor, rim: int = 1):
+    """both maps of a pair in one launch (dsm_pack_nhwc_bf16_pair)"""
+    _lib.require_cuda(fL, fR)
+    fL = fL.contiguous().float(); fR = fR.contiguous().float()
+    B, C, H, W = fL.shape
+    out = torch.empty(2, B, H + 2 * rim, W + 2 * rim, C, device=fL.device, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().dsm_pack_nhwc_bf16_pair(fL.data_ptr(), fR.data_ptr(), out[0].data_ptr(), out[1].data_ptr(), B, C, H, W, rim,
+                                                  _lib.stream_ptr(fL.device)), "dsm_pack_nhwc_bf16_pair")
+    return out[0], out[1]
 
 
 def conv_from_features(layer: "FusedConv3d", featL: torch.Tensor, featR: torch.Tensor, D: int, mode: str,
                        out: Optional[PaddedVolume] = None) -> PaddedVolume:
     """y = layer(concat_volume(fL, fR, D, mode)) without materialising the volume (dsm_conv3d_volume_fwd): `layer` is the
-    64 -> 32 stride-1 block that reads the volume (PSMNet dres0.0, GC-Net l19); featL / featR: bf16 NHWC [B, H, W, 32]."""
+    64 -> 32 stride-1 block that reads the volume (PSMNet dres0.0, GC-Net l19); featL / featR: bf16 NHWC with a zero rim of
+    one pixel, [B, H+2, W+2, 32] (`pack_features_nhwc`, or the 2-D trunk's last layer)."""
     _lib.require_cuda(featL, featR, layer.w)
     if layer.cin != 64 or layer.cout != 32 or layer.stride != 1 or layer.transposed:
         raise _lib.DsmError("conv_from_features: the fused volume convolution is the 64 -> 32 stride-1 layer")
     if featL.dtype != torch.bfloat16 or featL.shape != featR.shape or featL.dim() != 4 or featL.shape[3] != 32:
-        raise _lib.DsmError("conv_from_features: two bf16 NHWC [B, H, W, 32] feature maps expected")
+        raise _lib.DsmError("conv_from_features: two zero-rimmed bf16 NHWC [B, H+2, W+2, 32] feature maps expected")
     featL = featL.contiguous(); featR = featR.contiguous()
-    B, H, W, _ = featL.shape
+    B, H, W = featL.shape[0], featL.shape[1] - 2, featL.shape[2] - 2
     if out is None:
         out = PaddedVolume.empty(B, 32, D, H, W, featL.device)
     elif out.shape5 != (B, 32, D, H, W):

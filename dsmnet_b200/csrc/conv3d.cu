@@ -507,17 +507,25 @@ __device__ __forceinline__ RsItem rs_decode(const RsGeom& g, int t, int R) {
 }
 
 // FUSED (KC = 64 only): the input IS the concatenation cost volume of two 32-channel feature maps
-// (stackhourglass.py:124-133, gcnet.py:131-135,156-164) and is never materialised: four extra warps build every
-// 130-row x 128-byte A tile straight from the bf16 NHWC feature maps — left half of voxel (d, y, x) = fL[y][x], right
-// half = fR[y][x - d] (fL[y][x + d] for the right-reference volume), zero where the reference leaves the volume zero —
-// writing the SWIZZLE_128B pattern TMA would have produced (16-byte chunk c of row r at chunk c ^ (r & 7)), then
-// fence.proxy.async + one mbarrier arrival per warp.  The MMA and epilogue roles cannot tell the difference.
+// (stackhourglass.py:124-133, gcnet.py:131-135,156-164) and is never materialised.  A voxel's 64 channels are two K chunks:
+// first half = map A at the voxel's (y, x), second half = map B at (y, x -/+ d).  With the feature maps stored like every
+// other activation (bf16 NHWC with a zero rim, the pitch of the volume's planes) each half of a tap-row tile is a plain
+// TMA box of 130 consecutive padded pixels — the second one read d pixels further left (right) — landing as a 64-byte-row
+// SWIZZLE_64B tile; TMA stays the data mover.  What TMA cannot express is the reference's zero region (x < d: both
+// halves for PSMNet, the second half for GC-Net; rim positions of the shifted half): four "masking" warps wait for the
+// stage's loads, zero those rows (a few per tile, most tiles none) and only then release the stage to the MMA issuers,
+// which run the K steps of the first half from one tile and those of the second half from the other, against the same
+// resident 128-byte-row weight tiles.  (A first version built the whole tile with cp.async from four warps: correct, but
+// bound by their instruction stream — profiles/r02g_fused_volume_ab.txt.)
 template <int KC, int NP, bool FUSED = false>
 __global__ void __launch_bounds__(FUSED ? 512 : 384, 1)
-conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
+                 const __grid_constant__ CUtensorMap map_w,
                  const __grid_constant__ RsGeom g, const float* __restrict__ scale, const float* __restrict__ shift,
                  const void* __restrict__ residual, void* __restrict__ y) {
     using C = RsCfg<KC, NP>;
+    constexpr int HALF_BYTES = ((C::A_ROWS * 64 + 511) / 512) * 512;       // FUSED: one 130-row x 64-byte (SWIZZLE_64B) half tile
+    static_assert(!FUSED || (KC == 64 && 2 * HALF_BYTES <= C::STAGE_BYTES), "two half tiles must fit one stage");
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Dp = g.D + 2, Hp = g.H + 2, Wp = g.W + 2;
     const int plane = Hp * Wp;
@@ -545,6 +553,8 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     constexpr int NBARS = 2 * C::STAGES + 5;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + RING_END + 8 * NBARS);
     const uint32_t scratch_smem = bars + 8u * NBARS + 8u;
+    auto ready_bar = [&](int s) { return bars + 8u * (NBARS + 2 + s); };        // FUSED: stage masked, MMAs may read it
+    static_assert(8 * (NBARS + 2 + C::STAGES) <= C::BAR_BYTES, "barrier block too small");
     float* s_scale = reinterpret_cast<float*>(base_ptr + RING_END + C::BAR_BYTES);
     float* s_shift = s_scale + NP;
 
@@ -555,7 +565,9 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_w);
         ptx::prefetch_tensormap(&map_a);
-        for (int s = 0; s < C::STAGES; ++s) { ptx::mbar_init(full_bar(s), FUSED ? 128 : 1); ptx::mbar_init(empty_bar(s), 1); }
+        if (FUSED) ptx::prefetch_tensormap(&map_a2);
+        for (int s = 0; s < C::STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+        if (FUSED) for (int s = 0; s < C::STAGES; ++s) ptx::mbar_init(ready_bar(s), 4);
         for (int a = 0; a < 2; ++a) { ptx::mbar_init(tfull_bar(a), 3); ptx::mbar_init(tempty_bar(a), 8); }
         ptx::mbar_init(wfull_bar, 1);
         ptx::fence_mbar_init();
@@ -567,6 +579,12 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const uint32_t tmem = *tmem_slot;
 
     ptx::griddep_launch_dependents();
+    if (FUSED) {
+        // 512 threads cap the kernel at 128 registers per thread, but the epilogue wants ~170 (the unfused build has them):
+        // the two light warpgroups (TMA + MMA issuers, masking warps) hand registers to the two epilogue warpgroups
+        if (warp < 4 || warp >= 12) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
+        else                        asm volatile("setmaxnreg.inc.sync.aligned.u32 192;" ::: "memory");
+    }
     if (warp == 0) {
         // ================= TMA producer =================
         if (ptx::elect_one_sync()) {                            // all 27 weight tiles, once
@@ -580,17 +598,23 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         __syncwarp();
         ptx::griddep_wait();                                    // weights are parameters; the activations are the previous kernel's output
         int s = 0; uint32_t ph = 0;                              // ring slot and its phase
-        for (int t = item0; !FUSED && t < g.nitems; t += item_step) {
+        for (int t = item0; t < g.nitems; t += item_step) {
             const RsItem item = rs_decode(g, t, C::R);
             for (int i = -1; i <= item.nb; ++i) {
                 const int zp = item.z0 + 1 + i;                  // padded input plane
                 if (zp <= 0 || zp >= Dp - 1) continue;           // zero rim plane: contributes nothing
-                const int row0 = (item.b * Dp + zp) * plane + item.tile * 128 - Wp - 1;
+                const int row0 = FUSED ? item.b * plane + item.tile * 128 - Wp - 1        // feature maps have no D dimension
+                                       : (item.b * Dp + zp) * plane + item.tile * 128 - Wp - 1;
                 for (int khs = 0; khs < 3 / C::KHS; ++khs) {
                     wait_bar(empty_bar(s), ph ^ 1u);
                     if (ptx::elect_one_sync()) {
                         if (g.dbg & 2) {
                             ptx::mbar_arrive(full_bar(s));
+                        } else if (FUSED) {
+                            const int dshift = (g.vol_mode == DSM_VOL_GC_RIGHT) ? (zp - 1) : -(zp - 1);
+                            ptx::mbar_arrive_expect_tx(full_bar(s), 2 * C::A_ROWS * 64);
+                            ptx::tma_load_2d(ring + s * C::STAGE_BYTES, &map_a, full_bar(s), 0, row0 + khs * Wp);
+                            ptx::tma_load_2d(ring + s * C::STAGE_BYTES + HALF_BYTES, &map_a2, full_bar(s), 0, row0 + khs * Wp + dshift);
                         } else {
                             ptx::mbar_arrive_expect_tx(full_bar(s), C::TX_BYTES);
 #pragma unroll
@@ -668,18 +692,35 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
                     for (int khs = 0; khs < 3; ++khs) {
                         if (khs == my_kh) {
-                            wait_bar(full_bar(s), ph);
-                            if (FUSED) ptx::fence_proxy_async();   // the tile was written with generic stores by the builder warps
+                            wait_bar(FUSED ? ready_bar(s) : full_bar(s), ph);
+                            if (FUSED) ptx::fence_proxy_async();   // the masking warps zeroed rows with generic stores
                             ptx::tc_fence_after();
                             if (ptx::elect_one_sync()) {
                                 const uint32_t a_lo0 = ring_lo + (uint32_t)s * (C::STAGE_BYTES >> 4) + a_tile;
                                 if (!(g.dbg & 4)) {
+                                    if (FUSED) {
+                                        // K steps 0,1: first-half tile; 2,3: second-half tile (64-byte rows, SWIZZLE_64B);
+                                        // the weight rows stay 128 bytes (SWIZZLE_128B): two different descriptor high words
+                                        const uint64_t adsc = ptx::make_kmajor_desc(0u, 64, 0u);
+                                        const uint64_t bdsc = ((uint64_t)desc_hi << 32);
+                                        const uint32_t a_base = (uint32_t)adsc | ((ring + (uint32_t)s * C::STAGE_BYTES) >> 4);
+#pragma unroll
+                                        for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+                                            for (int k = 0; k < 4; ++k) {
+                                                const uint32_t a_lo = a_base + (uint32_t)(((k >> 1) * HALF_BYTES + kw * 64 + (k & 1) * 32) >> 4);
+                                                ptx::umma_bf16(d_lo, (adsc & 0xffffffff00000000ull) | a_lo,
+                                                               bdsc | (uint64_t)(b_lo0 + ((kw * C::W_TILE + k * 32) >> 4)), idesc, 1u);
+                                            }
+                                        }
+                                    } else {
 #pragma unroll
                                     for (int kw = 0; kw < 3; ++kw) {
 #pragma unroll
                                         for (int k = 0; k < KC / 16; ++k)
                                             ptx::umma_bf16_lohi(d_lo, a_lo0 + ((kw * C::ROWB + k * 32) >> 4),
                                                                 b_lo0 + ((kw * C::W_TILE + k * 32) >> 4), desc_hi, idesc, 1u);
+                                    }
                                     }
                                 }
                                 ptx::umma_commit(empty_bar(s));
@@ -695,85 +736,56 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             __syncwarp();
         }
     } else if (FUSED && warp >= 12) {
-        // ================= volume builders: 4 warps fill the activation ring from the feature maps =================
-        // Software-pipelined: the global loads of stage n+1 are issued BEFORE waiting for stage n's ring slot (they do not
-        // depend on it), so the L2 round trip of every stage hides behind the wait / the stores of the previous one.
-        ptx::griddep_wait();                                    // the feature maps are the previous kernel's output
-        const int pt = tid - 12 * 32;                            // 0..127
-        const int c16 = pt & 7;                                  // 16-byte chunk of the 128-byte row: 0-3 left half, 4-7 right half
-        const int r0 = pt >> 3;                                  // rows r0, r0 + 16, ... of the tile
-        const bool right_half = c16 >= 4;
-        // first half of a voxel: fL (fR for the right-reference volume), copied at x; second half: the other map, shifted
-        const uint4* fsrc = reinterpret_cast<const uint4*>((right_half != (g.vol_mode == DSM_VOL_GC_RIGHT)) ? g.featR : g.featL) + (c16 & 3);
+        // ================= masking warps: zero what the reference leaves zero, then release the stage =================
+        const int pt = tid - 12 * 32;                            // row pt of the tile (and row 128 + pt for pt < 2)
         const int sgn = (g.vol_mode == DSM_VOL_GC_RIGHT) ? 1 : -1;
         const bool mask_first = (g.vol_mode == DSM_VOL_PSM);
-        constexpr int NIT = (C::A_ROWS + 15) / 16;
-        // Per-thread row metadata, recomputed only when the (h,w) tile changes: row k of this thread (r = r0 + 16k) is pixel
-        // (y0[k] + kh, x[k]) for the stage with tap row kh — the same for every disparity plane; only the mask (x >= d) and the
-        // shift of the second half (x - d) depend on the plane.  The issuing rate of a warp (~1 dependent instruction per
-        // 4-7 cycles) is what bounds this role, so the per-stage work is ~6 instructions per row.
-        int rx[NIT], ry[NIT], rofs[NIT];                         // x, y (kh = 0), y*W + x; x = -1: never valid
-        int meta_tile = -1;
-        auto row_meta = [&](int tile) {
-            const int qq = tile * 128 - Wp - 1 + r0 + 2 * Wp;    // kh = 0 position of row r0, offset to stay non-negative
-            int hp = qq / Wp - 2, wp = qq - (hp + 2) * Wp;
-#pragma unroll
-            for (int k = 0; k < NIT; ++k) {
-                const bool col_ok = (r0 + 16 * k < C::A_ROWS) && wp >= 1 && wp <= g.W;
-                rx[k] = col_ok ? wp - 1 : -1;
-                ry[k] = hp - 1;
-                rofs[k] = (hp - 1) * g.W + (wp - 1);
-                wp += 16;
-                while (wp >= Wp) { wp -= Wp; ++hp; }
-            }
-            meta_tile = tile;
-        };
-        // iterator over the stages of this CTA, in the order the MMA issuers consume them: (item, plane, kh)
-        int it_t = item0, it_i = -2, it_kh = 2;                  // "before the first stage"
-        RsItem it_item = rs_decode(g, it_t < g.nitems ? it_t : 0, C::R);
-        auto next_stage = [&](int& d, int& kh, int& tile, int& img) -> bool {
-            for (;;) {
-                if (it_t >= g.nitems) return false;
-                if (++it_kh == 3) { it_kh = 0; ++it_i; }
-                if (it_i > it_item.nb) {
-                    it_t += item_step; it_i = -1; it_kh = 0;
-                    if (it_t >= g.nitems) return false;
-                    it_item = rs_decode(g, it_t, C::R);
-                }
-                const int zp = it_item.z0 + 1 + it_i;
-                if (zp <= 0 || zp >= Dp - 1) { it_kh = 2; continue; }      // rim plane: no stages
-                d = zp - 1; kh = it_kh; tile = it_item.tile;
-                img = it_item.b * g.H * g.W;
-                return true;
-            }
-        };
-        // cp.async (LDGSTS): 16 bytes global -> shared per instruction without a register round trip, zero-filled when the
-        // voxel is outside the volume's support (src-size 0); the thread's arrival on the stage's mbarrier is deferred until
-        // its copies have landed (cp.async.mbarrier.arrive.noinc), so a builder never waits for data — only for a free slot.
-        const int shift_sgn = right_half ? sgn : 0;
-        const char* fbytes = reinterpret_cast<const char*>(fsrc);
-        const uint32_t soff = (uint32_t)r0 * 128u + (uint32_t)((c16 ^ (r0 & 7)) << 4);   // (r0 + 16k) & 7 == r0 & 7
         int s = 0; uint32_t ph = 0;
-        int d = 0, kh = 0, tile = 0, img = 0;
-        while (next_stage(d, kh, tile, img)) {
-            if (tile != meta_tile) row_meta(tile);
-            const char* base = fbytes + ((long long)(img + kh * g.W + shift_sgn * d) << 6);     // 64 bytes per pixel
-            const int xlo = (right_half ? (sgn < 0) : mask_first) ? d : 0;              // valid x range of this half in plane d
-            const int xhi = (right_half && sgn > 0) ? g.W - d : g.W;
-            wait_bar(empty_bar(s), ph ^ 1u);
-            const uint32_t dst = ring + s * C::STAGE_BYTES + soff;
+        for (int t = item0; t < g.nitems; t += item_step) {
+            const RsItem item = rs_decode(g, t, C::R);
+            // padded position of this thread's rows for kh = 0 (the three tap rows differ by whole image rows)
+            int hp0[2], wp0[2];
 #pragma unroll
-            for (int k = 0; k < NIT; ++k) {
-                if (r0 + 16 * k < C::A_ROWS) {
-                    const int y = ry[k] + kh;
-                    const bool ok = rx[k] >= xlo && rx[k] < xhi && (unsigned)y < (unsigned)g.H && !(g.dbg & 2);
-                    const char* src = ok ? base + ((long long)rofs[k] << 6) : fbytes;
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
-                                 :: "r"(dst + (uint32_t)k * 2048u), "l"(src), "r"(ok ? 16 : 0) : "memory");
+            for (int u = 0; u < 2; ++u) {
+                const int qq = item.tile * 128 - Wp - 1 + pt + 128 * u + 2 * Wp;      // >= 0
+                hp0[u] = qq / Wp - 2; wp0[u] = qq - (hp0[u] + 2) * Wp;
+            }
+            for (int i = -1; i <= item.nb; ++i) {
+                const int zp = item.z0 + 1 + i;
+                if (zp <= 0 || zp >= Dp - 1) continue;
+                const int d = zp - 1;
+#pragma unroll 1
+                for (int kh = 0; kh < 3; ++kh) {
+                    wait_bar(full_bar(s), ph);                   // both half tiles have landed
+                    const uint32_t tile0 = ring + s * C::STAGE_BYTES;
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int r = pt + 128 * u;
+                        if (r < C::A_ROWS) {
+                            const int hp = hp0[u] + kh, wp = wp0[u], x = wp - 1;
+                            const bool interior = hp >= 1 && hp <= g.H && wp >= 1 && wp <= g.W;
+                            const bool zero2 = !interior || (sgn < 0 ? x < d : x >= g.W - d);
+                            const bool zero1 = mask_first && interior && x < d;
+                            const uint32_t z = 0u;
+                            if (zero1) {
+                                const uint32_t a = tile0 + (uint32_t)r * 64u;
+#pragma unroll
+                                for (int c = 0; c < 4; ++c)
+                                    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" :: "r"(a + 16u * c), "r"(z) : "memory");
+                            }
+                            if (zero2) {
+                                const uint32_t a = tile0 + HALF_BYTES + (uint32_t)r * 64u;
+#pragma unroll
+                                for (int c = 0; c < 4; ++c)
+                                    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" :: "r"(a + 16u * c), "r"(z) : "memory");
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(ready_bar(s));   // release: ordered before the issuer's acquire + proxy fence
+                    if (++s == C::STAGES) { s = 0; ph ^= 1u; }
                 }
             }
-            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(full_bar(s)) : "memory");
-            if (++s == C::STAGES) { s = 0; ph ^= 1u; }
         }
     } else {
         // ================= epilogue: 8 warps, two per TMEM lane quadrant =================
@@ -1305,7 +1317,7 @@ int launch_mode(int KC, int NP, const ConvMaps& maps, const ConvGeom& g, dim3 gr
 
 template <int KC, int NP, bool FUSED = false>
 int launch_rs(const CUtensorMap& map_a, const CUtensorMap& map_w, const RsGeom& g, const float* scale, const float* shift,
-              const void* residual, void* y, cudaStream_t st) {
+              const void* residual, void* y, cudaStream_t st, const CUtensorMap* map_a2 = nullptr) {
     using C = RsCfg<KC, NP>;
     auto kern = conv3d_rs_kernel<KC, NP, FUSED>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
@@ -1315,7 +1327,8 @@ int launch_rs(const CUtensorMap& map_a, const CUtensorMap& map_w, const RsGeom& 
     int per_group = nsm / g.ngroups;                            // persistent: one CTA per SM, split evenly over the channel groups
     if (per_group > g.nitems) per_group = g.nitems;
     const int nblocks = per_group * g.ngroups;
-    launch_kernel(kern, dim3(nblocks), dim3(C::THREADS + (FUSED ? 128 : 0)), C::SMEM, st, map_a, map_w, g, scale, shift, residual, y);
+    launch_kernel(kern, dim3(nblocks), dim3(C::THREADS + (FUSED ? 128 : 0)), C::SMEM, st, map_a, map_a2 ? *map_a2 : map_a, map_w, g, scale, shift,
+                  residual, y);
     return dsm_launch_status();
 }
 
@@ -1667,7 +1680,7 @@ extern "C" int dsm_conv3d_fwd_ex(const void* x, const void* w_packed, const floa
 }
 
 // The first 3-D convolution of PSMNet / GC-Net (dres0.0, l19: 64 -> 32, stride 1) fused with the concatenation cost volume
-// it reads: see conv3d_rs_kernel<64, 32, FUSED>.  featL / featR: bf16 NHWC [B][H][W][32].
+// it reads: see conv3d_rs_kernel<64, 32, FUSED>.  featL / featR: bf16 NHWC with a zero rim, [B][H+2][W+2][32].
 extern "C" int dsm_conv3d_volume_fwd(const void* featL, const void* featR, const void* w_packed, const float* scale, const float* shift,
                                      void* y, int B, int C, int Cout, int D, int H, int W, int mode, int relu, int variant, void* stream) {
     DsmDeviceGuard dsm_guard_(featL);
@@ -1698,7 +1711,17 @@ extern "C" int dsm_conv3d_volume_fwd(const void* featL, const void* featR, const
     rg.ngroups = 1;
     for (int t = 0; t < 27; ++t) rg.w_row[t] = t * 32;
     rg.featL = static_cast<const __nv_bfloat16*>(featL); rg.featR = static_cast<const __nv_bfloat16*>(featR); rg.vol_mode = mode;
-    return launch_rs<64, 32, true>(map_w /*unused: no activation tensor map*/, map_w, rg, scale, shift, nullptr, y, (cudaStream_t)stream);
+    // first half of a voxel: fL (fR for the right-reference volume); second half: the other map, read d pixels to the left (right)
+    const void* first = (mode == DSM_VOL_GC_RIGHT) ? featR : featL;
+    const void* second = (mode == DSM_VOL_GC_RIGHT) ? featL : featR;
+    CUtensorMap map1, map2;
+    {
+        cuuint64_t dims[2] = {32, (cuuint64_t)B * Hp * Wp};
+        cuuint64_t strides[1] = {64};
+        cuuint32_t box[2] = {32, 130};
+        if (!encode_map(&map1, first, 2, dims, strides, box, 64) || !encode_map(&map2, second, 2, dims, strides, box, 64)) return DSM_EDRIVER;
+    }
+    return launch_rs<64, 32, true>(map1, map_w, rg, scale, shift, nullptr, y, (cudaStream_t)stream, &map2);
 }
 
 // 2-D convolution block of the feature-extraction trunks; see conv2d_dispatch and include/dsmnet_b200.h

@@ -299,36 +299,60 @@ unpack_ndhwc_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, 
     }
 }
 
-// NCHW fp32 -> NHWC bf16 [B][H][W][C] (the feature-map layout of the fused volume convolution); CTA = one image row
+// NCHW fp32 -> NHWC bf16 with a zero rim of `rim` pixels, [B][H+2r][W+2r][C] (the feature-map layout of the fused volume
+// convolution and of the 2-D trunk); CTA = one padded image row, rim included
 __global__ void __launch_bounds__(256)
-pack_nhwc_kernel(const float* __restrict__ x, uint4* __restrict__ y, int C, int H, int W) {
+pack_nhwc_kernel(const float* __restrict__ x, uint4* __restrict__ y, const float* __restrict__ x2, uint4* __restrict__ y2,
+                 int C, int H, int W, int rim) {
+    if (blockIdx.z == 1) { x = x2; y = y2; }                                  // the second map of a pair (one launch for both)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __nv_bfloat16* s = reinterpret_cast<__nv_bfloat16*>(smem_raw);            // [W][C]
-    const int yy = blockIdx.x, b = blockIdx.y;
-    const float* src = x + ((size_t)b * C * H + yy) * W;
-    const size_t cstride = (size_t)H * W;
-    for (int i = threadIdx.x; i < C * W; i += blockDim.x) {
-        const int c = i / W, xx = i - c * W;
-        s[xx * C + c] = __float2bfloat16_rn(__ldg(src + c * cstride + xx));
+    const int yp = blockIdx.x, b = blockIdx.y;
+    const int yy = yp - rim, Wp = W + 2 * rim, cpv = C / 8;
+    const bool row_ok = yy >= 0 && yy < H;
+    if (row_ok) {
+        const float* src = x + ((size_t)b * C * H + yy) * W;
+        const size_t cstride = (size_t)H * W;
+        for (int i = threadIdx.x; i < C * W; i += blockDim.x) {
+            const int c = i / W, xx = i - c * W;
+            s[xx * C + c] = __float2bfloat16_rn(__ldg(src + c * cstride + xx));
+        }
     }
     __syncthreads();
     const uint4* v = reinterpret_cast<const uint4*>(s);
-    uint4* orow = y + ((size_t)b * H + yy) * (size_t)(W * C / 8);
-    for (int i = threadIdx.x; i < W * C / 8; i += blockDim.x) orow[i] = v[i];
+    uint4* orow = y + ((size_t)b * (H + 2 * rim) + yp) * (size_t)(Wp * cpv);
+    for (int i = threadIdx.x; i < Wp * cpv; i += blockDim.x) {
+        const int xp = i / cpv, k = i - xp * cpv;
+        const int xx = xp - rim;
+        orow[i] = (row_ok && xx >= 0 && xx < W) ? v[xx * cpv + k] : make_uint4(0u, 0u, 0u, 0u);
+    }
 }
 
 }  // namespace
 
-extern "C" int dsm_pack_nhwc_bf16(const float* x, void* y, int B, int C, int H, int W, void* stream) {
+extern "C" int dsm_pack_nhwc_bf16(const float* x, void* y, int B, int C, int H, int W, int rim, void* stream) {
     DsmDeviceGuard dsm_guard_(x);
-    if (!x || !y || B <= 0 || C <= 0 || H <= 0 || W <= 0) return DSM_EINVAL;
+    if (!x || !y || B <= 0 || C <= 0 || H <= 0 || W <= 0 || rim < 0 || rim > 8) return DSM_EINVAL;
     if (C % 8 != 0 || H > 65535 * 32 || B > 65535) return DSM_EUNSUPPORTED;
     if (!dsm_aligned16(y)) return DSM_EALIGN;
     const size_t smem = (size_t)W * C * sizeof(__nv_bfloat16);
     if (smem > 200 * 1024) return DSM_EUNSUPPORTED;
     cudaError_t e = cudaFuncSetAttribute(pack_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    pack_nhwc_kernel<<<dim3(H, B), 256, smem, (cudaStream_t)stream>>>(x, (uint4*)y, C, H, W);
+    pack_nhwc_kernel<<<dim3(H + 2 * rim, B), 256, smem, (cudaStream_t)stream>>>(x, (uint4*)y, nullptr, nullptr, C, H, W, rim);
+    return dsm_launch_status();
+}
+
+extern "C" int dsm_pack_nhwc_bf16_pair(const float* xL, const float* xR, void* yL, void* yR, int B, int C, int H, int W, int rim, void* stream) {
+    DsmDeviceGuard dsm_guard_(xL);
+    if (!xL || !xR || !yL || !yR || B <= 0 || C <= 0 || H <= 0 || W <= 0 || rim < 0 || rim > 8) return DSM_EINVAL;
+    if (C % 8 != 0 || H > 65535 * 32 || B > 65535) return DSM_EUNSUPPORTED;
+    if (!dsm_aligned16(yL) || !dsm_aligned16(yR)) return DSM_EALIGN;
+    const size_t smem = (size_t)W * C * sizeof(__nv_bfloat16);
+    if (smem > 200 * 1024) return DSM_EUNSUPPORTED;
+    cudaError_t e = cudaFuncSetAttribute(pack_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    pack_nhwc_kernel<<<dim3(H + 2 * rim, B, 2), 256, smem, (cudaStream_t)stream>>>(xL, (uint4*)yL, xR, (uint4*)yR, C, H, W, rim);
     return dsm_launch_status();
 }
 

@@ -29,7 +29,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib
-from .conv3d import FusedConv3d, conv_from_features, pack_features_nhwc
+from .conv3d import FusedConv3d, conv_from_features, pack_feature_pair_nhwc
 from .cost_volume import concat_volume, concat_volume_padded
 from .softargmin import upsample_softargmin
 from .volume_layout import PaddedVolume
@@ -64,11 +64,9 @@ PDL_VARIANT = 0 if os.environ.get("DSM_NO_PDL") == "1" else 128
 CLS_SIDE_STREAM = os.environ.get("DSM_CLS_STREAM", "1") != "0"
 # with the second stream: launch each head as soon as its cost exists (DSM_EARLY_HEADS=0: one stacked launch at the end)
 EARLY_HEADS = os.environ.get("DSM_EARLY_HEADS", "1") != "0"
-# DSM_FUSED_VOLUME=1: dres0.0 reads the two feature maps and builds its volume tiles on the fly (the 196 MB volume is never
-# written).  Correct and tested, but OFF by default: measured on B200 (profiles/r02g_fused_volume_ab.txt) the four builder
-# warps need ~137 instructions per 130-row tile and a warp issues a dependent instruction only every 4-7 cycles, so the fused
-# layer takes 1.545 ms/step against 1.485 ms with the materialised volume (41 us concat kernel + 64 us convolution).
-FUSED_VOLUME = os.environ.get("DSM_FUSED_VOLUME", "0") == "1"
+# dres0.0 reads the two feature maps and assembles its volume tiles itself (the 196 MB volume is never written);
+# DSM_FUSED_VOLUME=0 materialises the volume instead (A/B: tools/ab_fused_volume.py)
+FUSED_VOLUME = os.environ.get("DSM_FUSED_VOLUME", "1") != "0"
 
 
 class _Plan:
@@ -225,20 +223,21 @@ class PSMNetHotPath(nn.Module):
         True if it was used (the caller then skips its own head launch)."""
         if self._wants_autograd(fL, fR):
             return self.aggregate_train(fL, fR)
-        nhwc = fL.dtype == torch.bfloat16                 # bf16 NHWC [B, H, W, 32] straight from the 2-D trunk's last layer
+        nhwc = fL.dtype == torch.bfloat16                 # zero-rimmed bf16 NHWC [B, H+2, W+2, 32] from the 2-D trunk's last layer
         if nhwc:
-            B, H, W, C = fL.shape
+            B, H, W, C = fL.shape[0], fL.shape[1] - 2, fL.shape[2] - 2, fL.shape[3]
         else:
             B, C, H, W = fL.shape
         D = self.maxdisp // 4
         plan = self._get_plan(fL.device)
         ws = self._workspace(B, D, H, W, fL.device)
         if nhwc and not (FUSED_VOLUME and C == 32):
-            fL = fL.permute(0, 3, 1, 2).float().contiguous(); fR = fR.permute(0, 3, 1, 2).float().contiguous(); nhwc = False
+            fL = fL[:, 1:-1, 1:-1].permute(0, 3, 1, 2).float().contiguous(); fR = fR[:, 1:-1, 1:-1].permute(0, 3, 1, 2).float().contiguous()
+            nhwc = False
         if FUSED_VOLUME and C == 32:
             # the 196 MB volume is never written: dres0.0 builds its operand tiles from the (L2-resident) feature maps
-            conv_from_features(plan.dres0_0, fL if nhwc else pack_features_nhwc(fL), fR if nhwc else pack_features_nhwc(fR),
-                               D, "psm", ws["a"])
+            hL, hR = (fL, fR) if nhwc else pack_feature_pair_nhwc(fL, fR)
+            conv_from_features(plan.dres0_0, hL, hR, D, "psm", ws["a"])
         else:
             if ws["vol"] is None:
                 ws["vol"] = PaddedVolume.empty(B, 64, D, H, W, fL.device, zero_rim=False)
@@ -328,7 +327,7 @@ class PSMNetHotPath(nn.Module):
             B = c1.shape[0]
             preds = upsample_softargmin(torch.cat((c3, c2, c1), 0), (self.maxdisp, out_hw[0], out_hw[1]), self.align_corners)
             return [preds[:B], preds[B:2 * B], preds[2 * B:]]
-        B, H, W = (fL.shape[0], fL.shape[1], fL.shape[2]) if fL.dtype == torch.bfloat16 else (fL.shape[0], fL.shape[2], fL.shape[3])
+        B, H, W = (fL.shape[0], fL.shape[1] - 2, fL.shape[2] - 2) if fL.dtype == torch.bfloat16 else (fL.shape[0], fL.shape[2], fL.shape[3])
         ws = self._workspace(B, self.maxdisp // 4, H, W, fL.device)
         size = (self.maxdisp, out_hw[0], out_hw[1])
         # heads of stackhourglass.py:152-166 for (cost3, cost2, cost1) in ONE launch over the stacked costs
@@ -401,8 +400,9 @@ class feature_extraction(nn.Module):
         return nn.Sequential(*layers)
 
     def forward(self, x, nhwc_bf16=False):
-        """`nhwc_bf16` (CUDA inference only): return the feature map as bf16 [B, H/4, W/4, 32], the operand layout of the fused
-        volume convolution, instead of the reference's fp32 NCHW."""
+        """`nhwc_bf16` (CUDA inference only): return the feature map as zero-rimmed bf16 [B, H/4+2, W/4+2, 32], the operand
+        layout of the fused volume convolution, instead of the reference's fp32 NCHW (the tensor is the plan's own
+        workspace: consume it before the next call)."""
         if x.is_cuda and not self.training and not torch.is_grad_enabled():
             # inference: every layer on the library's kernels (dsmnet_b200/trunk2d.py)
             from .trunk2d import PSMNetTrunkPlan, cached_plan

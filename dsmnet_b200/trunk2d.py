@@ -242,8 +242,10 @@ class PSMNetTrunkPlan:
                                           cat.ptr(0), B, H4, W4, cat.rim, cat.C, 192, int(bool(self.align_corners)),
                                           ws["spp"].data_ptr(), ws["spp"].numel() * 4, _lib.stream_ptr(img.device)), "dsm_spp_fwd")
         self.last0(cat, q128[0])
-        if nhwc_bf16:                                   # bf16 [B][H/4][W/4][32]: what the fused volume convolution reads
-            feat = PaddedImage(torch.empty(B * H4 * W4 * 32, device=img.device, dtype=torch.bfloat16), B, 32, H4, W4, 0)
+        if nhwc_bf16:                                   # zero-rimmed bf16 [B][H/4+2][W/4+2][32]: what the fused volume convolution reads
+            feat = ws.get("feat")
+            if feat is None:
+                feat = ws["feat"] = PaddedImage.zeros(B, 32, H4, W4, 1, self.device)
             self.last2(q128[0], feat)
             return feat.view5()
         out = torch.empty(B, 32, H4, W4, device=img.device, dtype=torch.float32)

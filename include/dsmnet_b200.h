@@ -158,12 +158,16 @@ int dsm_conv3d_c1_bwd(const void* x, const float* gy, const float* w, void* gx, 
 
 /* The volume is never materialised: the first 3-D convolution of the stack (PSMNet dres0.0,
  * stackhourglass.py:73,135; GC-Net l19, gcnet.py:38,94 — Conv3d(64 -> 32, k3, s1) + BN + ReLU) computed straight from the two
- * 32-channel feature maps.  featL / featR: bf16 NHWC [B][H][W][32] (dsm_pack_nhwc_bf16, or the 2-D trunk's last layer);
+ * 32-channel feature maps.  featL / featR: bf16 NHWC with a zero rim of one pixel, [B][H+2][W+2][32] (dsm_pack_nhwc_bf16 with
+ * rim = 1, or the 2-D trunk's last layer);
  * y: padded NDHWC bf16 [B][D+2][H+2][W+2][32]; mode as dsm_concat_volume_fwd; w_packed / scale / shift / relu / variant as
  * dsm_conv3d_fwd_ex.  Same result as dsm_concat_volume_fwd (bf16, padded) followed by dsm_conv3d_fwd.               */
 int dsm_conv3d_volume_fwd(const void* featL, const void* featR, const void* w_packed, const float* scale, const float* shift,
                           void* y, int B, int C, int Cout, int D, int H, int W, int mode, int relu, int variant, void* stream);
-int dsm_pack_nhwc_bf16(const float* x_nchw, void* y_nhwc_bf16, int B, int C, int H, int W, void* stream);
+/* NCHW fp32 -> NHWC bf16 (RNE) with a zero rim of `rim` pixels: y [B][H+2*rim][W+2*rim][C], rim written too            */
+int dsm_pack_nhwc_bf16(const float* x_nchw, void* y_nhwc_bf16, int B, int C, int H, int W, int rim, void* stream);
+/* both feature maps of a stereo pair in one launch                                                                 */
+int dsm_pack_nhwc_bf16_pair(const float* xL_nchw, const float* xR_nchw, void* yL, void* yR, int B, int C, int H, int W, int rim, void* stream);
 
 /* cropped skip add of the training path (myadd_3d / myAdd3d crop-to-min, stackhourglass.py:10-20, util_fun.py:41-51):
  * `full` is a padded bf16 volume of extent (Dn,Hn,Wn) (the BatchNorm'ed deconv output, statistics over all of it as in

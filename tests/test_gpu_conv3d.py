@@ -326,7 +326,7 @@ def test_pack_weight_kernel_matches_host_packing(cout, cin):
 @pytest.mark.parametrize("B,D,H,W", [(2, 5, 7, 19), (1, 12, 9, 150), (1, 6, 20, 10)])
 def test_fused_volume_conv_equals_volume_then_conv(mode, B, D, H, W):
     """dsm_conv3d_volume_fwd (the volume is never written) vs dsm_concat_volume_fwd + dsm_conv3d_fwd on the same weights, and
-    vs the oracle: every mode, batch > 1, D > a tile row, W < 16 (row wraps inside one 16-row step of the builder warps)"""
+    vs the oracle: every mode, batch > 1, D larger than the rows of a tile, W < 16 (several image rows inside one tile)"""
     from dsmnet_b200.conv3d import FusedConv3d, conv_from_features, pack_features_nhwc, conv_timeouts
     from dsmnet_b200.cost_volume import concat_volume
     torch.manual_seed(21)
