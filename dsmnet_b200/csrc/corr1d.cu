@@ -296,9 +296,8 @@ __device__ __forceinline__ void corr_bwd_chunk(const float* sF, float* red, int 
 }
 
 template <int S, int RIGHT>
-__global__ void __launch_bounds__(288, 1)
-corr1d_bwd_flat_kernel(const __grid_constant__ CUtensorMap mapF, const float* __restrict__ gout, float* __restrict__ gfeat,
-                       int C, int HW, int W, int D, int NW) {
+__device__ __forceinline__ void corr1d_bwd_flat_body(const CUtensorMap& mapF, const float* __restrict__ gout, float* __restrict__ gfeat,
+                                                     int C, int HW, int W, int D, int NW) {
     extern __shared__ uint8_t smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t raw = ptx::smem_u32(smem_raw);
@@ -378,14 +377,27 @@ corr1d_bwd_flat_kernel(const __grid_constant__ CUtensorMap mapF, const float* __
     }
 }
 
-template <int S, int RIGHT>
-int launch_corr_bwd_flat(const CUtensorMap& map, const float* gout, float* gfeat, int B, int C, long long HW, int W, int D, int NW,
-                         cudaStream_t st) {
+// Both gradients in ONE launch: blockIdx.z = 0 computes gL (reads fR), 1 computes gR (reads fL).  A CTA of the backward
+// is latency-bound (three compute warps, one per sub-partition, IPC ~0.36 in the r01 capture) and at B = 1 each gradient
+// alone fills only 117 of 148 SMs; the 234 CTAs of the pair fit the machine at two per SM (99 KB shared memory, 168
+// registers x 128 threads each), so the two problems hide each other's latencies instead of running back to back.
+template <int S>
+__global__ void __launch_bounds__(288, 1)
+corr1d_bwd_flat_kernel(const __grid_constant__ CUtensorMap mapR, const __grid_constant__ CUtensorMap mapL,
+                       const float* __restrict__ gout, float* __restrict__ gL, float* __restrict__ gR,
+                       int C, int HW, int W, int D, int NW) {
+    if (blockIdx.z == 0) corr1d_bwd_flat_body<S, 0>(mapR, gout, gL, C, HW, W, D, NW);
+    else                 corr1d_bwd_flat_body<S, 1>(mapL, gout, gR, C, HW, W, D, NW);
+}
+
+template <int S>
+int launch_corr_bwd_flat(const CUtensorMap& mapR, const CUtensorMap& mapL, const float* gout, float* gL, float* gR,
+                         int B, int C, long long HW, int W, int D, int NW, cudaStream_t st) {
     const size_t smem = (size_t)(FSTAGES * FCC * FRW + 2 * NW * FCC * FT) * sizeof(float) + 1024 + 2 * FSTAGES * 8;
-    cudaError_t e = cudaFuncSetAttribute(corr1d_bwd_flat_kernel<S, RIGHT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(corr1d_bwd_flat_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    dim3 grid((unsigned)dsm_ceil_div_ll(HW, FT), B), block((NW + 1) * 32);
-    corr1d_bwd_flat_kernel<S, RIGHT><<<grid, block, smem, st>>>(map, gout, gfeat, C, (int)HW, W, D, NW);
+    dim3 grid((unsigned)dsm_ceil_div_ll(HW, FT), B, 2), block((NW + 1) * 32);
+    corr1d_bwd_flat_kernel<S><<<grid, block, smem, st>>>(mapR, mapL, gout, gL, gR, C, (int)HW, W, D, NW);
     return dsm_launch_status();
 }
 
@@ -556,15 +568,8 @@ extern "C" int dsm_corr1d_bwd(const float* gout, const float* fL, const float* f
             if (!tma_host::encode(&mapL, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, fL, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B) ||
                 !tma_host::encode(&mapR, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, fR, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B))
                 return DSM_EDRIVER;
-            int rc;
-            if (stride == 1) {
-                rc = launch_corr_bwd_flat<1, 0>(mapR, gout, gL, B, C, HW, W, D, NWF, st);
-                if (rc == 0) rc = launch_corr_bwd_flat<1, 1>(mapL, gout, gR, B, C, HW, W, D, NWF, st);
-            } else {
-                rc = launch_corr_bwd_flat<2, 0>(mapR, gout, gL, B, C, HW, W, D, NWF, st);
-                if (rc == 0) rc = launch_corr_bwd_flat<2, 1>(mapL, gout, gR, B, C, HW, W, D, NWF, st);
-            }
-            return rc;
+            return stride == 1 ? launch_corr_bwd_flat<1>(mapR, mapL, gout, gL, gR, B, C, HW, W, D, NWF, st)
+                               : launch_corr_bwd_flat<2>(mapR, mapL, gout, gL, gR, B, C, HW, W, D, NWF, st);
         }
     }
     const int HT = (D - 1) * stride;
