@@ -17,6 +17,7 @@ from . import _lib
 from .volume_layout import PaddedVolume
 
 BN_EPS = 1e-5
+KWFOLD = __import__("os").environ.get("DSM_KWFOLD", "1") != "0"
 
 
 def pack_weight(weight: torch.Tensor, transposed: bool) -> torch.Tensor:
@@ -91,7 +92,18 @@ class FusedConv3d:
         else:
             self.cout, self.cin = weight.shape[0], weight.shape[1]
         device = device if device is not None else weight.device
-        if weight.is_cuda and torch.device(device) == weight.device:
+        # single-output-channel stride-1 layers with 32 inputs (PSMNet classif*.2): kw folded into the output columns
+        # (dsm_conv3d_fwd_ex variant bit 8; a third of the MMAs); DSM_KWFOLD=0 keeps the plain 32 -> 16 mapping
+        self.kwfold = (KWFOLD and self.cout == 1 and self.cin == 32 and not self.transposed and not dgrad_flip and self.stride == 1)
+        if self.kwfold:
+            variant |= 256
+            wk = weight.detach().float().to(device).contiguous()
+            self.w = torch.empty(27, 16, 32, device=device, dtype=torch.bfloat16)
+            if wk.is_cuda:
+                _lib.check(_lib.lib().dsm_pack_weight(wk.data_ptr(), self.w.data_ptr(), 1, 32, 3, _lib.stream_ptr(wk.device)), "dsm_pack_weight")
+            else:
+                raise _lib.DsmError("FusedConv3d: the packed weights live on a CUDA device")
+        elif weight.is_cuda and torch.device(device) == weight.device:
             self.w = pack_weight_device(weight, 2 if dgrad_flip else (1 if self.transposed else 0))
         elif dgrad_flip:
             self.w = pack_weight(weight.detach().flip(2, 3, 4).transpose(0, 1).contiguous(), False).to(device)

@@ -465,6 +465,7 @@ struct RsGeom {
     int nitems;              // B * nbands * plane_tiles
     int dbg;                 // timing experiments only (variant bits 4..6): 1 = no epilogue work, 2 = no TMA traffic, 4 = no MMAs
     int ngroups;             // output-channel groups of NP channels (Cout = ngroups*NP when > 1): CTA c owns group c % ngroups
+    int kwfold;              // single-output-channel layers (KC = 32, fp32 output): the kw taps are output COLUMNS (see below)
     int w_row[27];           // first row of tap (kd*3+kh)*3+kw in the packed weights
     // fused concat volume (FUSED instantiation only): the A operand is built in shared memory from the two feature maps
     const __nv_bfloat16* featL;   // bf16 NHWC [B][H][W][32]
@@ -517,6 +518,12 @@ __device__ __forceinline__ RsItem rs_decode(const RsGeom& g, int t, int R) {
 // which run the K steps of the first half from one tile and those of the second half from the other, against the same
 // resident 128-byte-row weight tiles.  (A first version built the whole tile with cp.async from four warps: correct, but
 // bound by their instruction stream — profiles/r02g_fused_volume_ab.txt.)
+// kw-fold mode (classif*.2 of PSMNet: Conv3d 32 -> 1).  Run as a 32 -> 16 layer, 15 of the 16 accumulator columns and two
+// thirds of the MMAs are wasted on zeros.  Here the three kw taps become three output COLUMNS of a 3x3x1 convolution —
+// Z[v][kw] = sum over (kd, kh, c) of x[v + (kd,kh) offset][c] * w[kd][kh][kw][c] — which needs one MMA per (kh, K step)
+// instead of three, and the epilogue adds the shifted columns, out[v] = Z[v-1][0] + Z[v][1] + Z[v+1][2], with two warp
+// shuffles.  So that no lane needs a neighbour from another warp, each 32-lane quadrant of a tile covers 32 consecutive padded
+// positions of which the inner 30 are outputs: a tile advances by 120 positions and its A operand is four 32-row TMA boxes.
 template <int KC, int NP, bool FUSED = false>
 __global__ void __launch_bounds__(FUSED ? 512 : 384, 1)
 conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
@@ -615,6 +622,16 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             ptx::mbar_arrive_expect_tx(full_bar(s), 2 * C::A_ROWS * 64);
                             ptx::tma_load_2d(ring + s * C::STAGE_BYTES, &map_a, full_bar(s), 0, row0 + khs * Wp);
                             ptx::tma_load_2d(ring + s * C::STAGE_BYTES + HALF_BYTES, &map_a2, full_bar(s), 0, row0 + khs * Wp + dshift);
+                        } else if (KC == 32 && g.kwfold) {
+                            // lane l of quadrant q <-> padded position tile*120 + 30q - 1 + l: four 32-row boxes per tap row
+                            const int r0f = (item.b * Dp + zp) * plane + item.tile * 120 - 1 - Wp;
+                            ptx::mbar_arrive_expect_tx(full_bar(s), C::KHS * 128 * C::ROWB);
+#pragma unroll
+                            for (int kk = 0; kk < C::KHS; ++kk)
+#pragma unroll
+                                for (int qd = 0; qd < 4; ++qd)
+                                    ptx::tma_load_2d(ring + s * C::STAGE_BYTES + kk * C::A_BYTES + qd * 32 * C::ROWB, &map_a2, full_bar(s), 0,
+                                                     r0f + (khs * C::KHS + kk) * Wp + qd * 30);
                         } else {
                             ptx::mbar_arrive_expect_tx(full_bar(s), C::TX_BYTES);
 #pragma unroll
@@ -675,6 +692,7 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                     const uint32_t b_kh = w_base + (uint32_t)((kh * 3 * C::W_TILE + brow * C::ROWB) >> 4);
 #pragma unroll
                                     for (int kw = 0; kw < 3; ++kw) {
+                                        if (kw > 0 && g.kwfold) break;       // kw-fold: the three kw taps are columns of ONE MMA
 #pragma unroll
                                         for (int k = 0; k < KC / 16; ++k)
                                             ptx::umma_bf16_lohi(d_lo, a_lo0 + ((kw * C::ROWB + k * 32) >> 4),
@@ -817,9 +835,11 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         int tcount = 0;
         for (int t = item0; t < g.nitems; t += item_step) {
             const RsItem item = rs_decode(g, t, C::R);
-            const int pq = item.tile * 128 + r;                   // position in the padded (h,w) plane
+            const bool fold = g.kwfold != 0;
+            const int pq = fold ? item.tile * 120 + q * 30 - 1 + lane : item.tile * 128 + r;   // position in the padded (h,w) plane
             const int hp = pq / Wp, wp = pq - hp * Wp;
-            const bool valid = (pq < plane) && hp >= 1 && hp <= g.Ho && wp >= 1 && wp <= g.Wo;
+            const bool valid = (pq >= 0) && (pq < plane) && hp >= 1 && hp <= g.Ho && wp >= 1 && wp <= g.Wo &&
+                               (!fold || (lane >= 1 && lane <= 30));
             const int acc = tcount & 1;
             const uint32_t acc_ph = (uint32_t)(tcount >> 1) & 1u;
             ++tcount;
@@ -864,9 +884,15 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         consume_tmem_load(v[0], scratch_smem);
                         ptx::tmem_zero16(taddr0 + j * NP);
                         if (j == my_last) release();
+                        float acc0 = __uint_as_float(v[0]);
+                        if (fold) {                                  // out[p] = Z[p-1][kw 0] + Z[p][kw 1] + Z[p+1][kw 2]
+                            const float zl = __shfl_up_sync(0xffffffffu, __uint_as_float(v[0]), 1);
+                            const float zr = __shfl_down_sync(0xffffffffu, __uint_as_float(v[2]), 1);
+                            acc0 = (zl + __uint_as_float(v[1])) + zr;
+                        }
                         if (valid) {
                             reinterpret_cast<float*>(y)[o0 + j * ostep] =
-                                fuse_act(fmaf(__uint_as_float(v[0]), s_scale[0], s_shift[0]), rf[jj], g.relu);
+                                fuse_act(fmaf(acc0, s_scale[0], s_shift[0]), rf[jj], g.relu);
                         }
                     }
                 }
@@ -1466,7 +1492,11 @@ int conv3d_dispatch(const void* x, const void* w, const float* scale, const floa
         memset(&rg, 0, sizeof(rg));
         rg.B = B; rg.D = D; rg.H = H; rg.W = W; rg.Do = Do; rg.Ho = Ho; rg.Wo = Wo;
         rg.Cout = Cout; rg.relu = relu; rg.y_f32 = (y_dtype == DSM_F32);
-        rg.plane_tiles = dsm_ceil_div(Hp * Wp, 128);
+        // variant bit 8: the weights of this single-output-channel layer are packed with kw folded into the output columns
+        // (dsm_pack_weight mode 3): one MMA per (kh, K step), tiles of 120 positions (see conv3d_rs_kernel)
+        rg.kwfold = ((variant & 256) && KC == 32 && y_dtype == DSM_F32 && Cout == 1) ? 1 : 0;
+        if ((variant & 256) && !rg.kwfold) return DSM_EINVAL;
+        rg.plane_tiles = dsm_ceil_div(Hp * Wp, rg.kwfold ? 120 : 128);
         rg.nbands = dsm_ceil_div(Do, 8);
         const long long ni = (long long)B * rg.nbands * rg.plane_tiles;
         if (ni > 0x7fffffffLL) return DSM_EUNSUPPORTED;
@@ -1482,6 +1512,12 @@ int conv3d_dispatch(const void* x, const void* w, const float* scale, const floa
             if (!encode_map(&map_w, w, 2, wdims, wstrides, wbox, row_bytes)) return DSM_EDRIVER;
         }
         cudaStream_t st = (cudaStream_t)stream;
+        if (rg.kwfold) {
+            CUtensorMap map_q;                                       // the same activation tensor, boxes of 32 rows
+            cuuint32_t qbox[2] = {(cuuint32_t)KC, 32u};
+            if (!encode_map(&map_q, x, 2, dims, strides, qbox, row_bytes)) return DSM_EDRIVER;
+            return launch_rs<32, 16>(map_a, map_w, rg, scale, shift, residual, y, st, &map_q);
+        }
         if (KC == 32 && NPk == 16) return launch_rs<32, 16>(map_a, map_w, rg, scale, shift, residual, y, st);
         if (KC == 32 && NPk == 32) return launch_rs<32, 32>(map_a, map_w, rg, scale, shift, residual, y, st);
         if (KC == 64 && NPk == 16) return launch_rs<64, 16>(map_a, map_w, rg, scale, shift, residual, y, st);

@@ -420,6 +420,8 @@ extern "C" int dsm_concat_volume_bwd(const void* gout, float* gL, float* gR,
 //   mode 0: w is [Cout][Cin][27]  (nn.Conv3d)                      out[t][co][ci] = w[co][ci][t]
 //   mode 1: w is [Cin][Cout][27]  (nn.ConvTranspose3d)             out[t][co][ci] = w[ci][co][t]
 //   mode 2: w is [Cin][Cout][27] read as the stride-1 dgrad filter out[t][co][ci] = w[ci][co][26-t]   (flipped taps)
+//   mode 3: w is [1][Cin][27] (nn.Conv3d with ONE output channel), kw folded into the output columns for the plane-sharing
+//           kernel's kw-fold mode (dsm_conv3d_fwd_ex variant bit 8): out[(kd,kh,0)][c'][ci] = w[0][ci][(kd,kh,c')] for c' < 3, else 0
 // Rows co >= Cout (CoutP = max(16, Cout)) are zero.
 __global__ void __launch_bounds__(256)
 pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int CoutP, int Cin, int mode) {
@@ -429,7 +431,10 @@ pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
     const int ci = i % Cin; int r = i / Cin;
     const int co = r % CoutP; const int t = r / CoutP;
     float v = 0.f;
-    if (co < Cout) {
+    if (mode == 3) {
+        // single-output-channel Conv3d, kw folded into the output columns: tile (kd, kh, kw = 0) row c' < 3 = w[0][ci][kd][kh][c']
+        if (t % 3 == 0 && co < 3) v = w[(size_t)ci * 27 + t + co];
+    } else if (co < Cout) {
         if (mode == 0) v = w[((size_t)co * Cin + ci) * 27 + t];
         else v = w[((size_t)ci * Cout + co) * 27 + (mode == 2 ? 26 - t : t)];
     }
@@ -438,7 +443,7 @@ pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
 
 extern "C" int dsm_pack_weight(const float* w, void* out, int Cout, int Cin, int mode, void* stream) {
     DsmDeviceGuard dsm_guard_(w);
-    if (!w || !out || Cout < 1 || Cin < 1 || mode < 0 || mode > 2) return DSM_EINVAL;
+    if (!w || !out || Cout < 1 || Cin < 1 || mode < 0 || mode > 3 || (mode == 3 && Cout != 1)) return DSM_EINVAL;
     const int CoutP = Cout < 16 ? 16 : Cout;
     const long long n = 27LL * CoutP * Cin;
     if (n > 0x7fffffffLL) return DSM_EUNSUPPORTED;

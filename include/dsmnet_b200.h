@@ -187,7 +187,8 @@ int dsm_debug_wgrad_timeouts(void);
 /* layout converters at the reference boundary (NCDHW fp32 <-> padded NDHWC bf16)             */
 /* filter repacking fp32 -> bf16 [27][CoutP][Cin] (CoutP = max(16, Cout), extra rows zero), w has 27 taps innermost:
  * mode 0: w[Cout][Cin][27] (nn.Conv3d); mode 1: w[Cin][Cout][27] (nn.ConvTranspose3d);
- * mode 2: w[Cin][Cout][27] with flipped taps (the stride-1 dgrad filter: pass the Conv3d weight, Cout/Cin exchanged) */
+ * mode 2: w[Cin][Cout][27] with flipped taps (the stride-1 dgrad filter: pass the Conv3d weight, Cout/Cin exchanged)
+ * mode 3: w[1][Cin][27], one output channel, kw folded into the output columns (for dsm_conv3d_fwd_ex variant bit 8) */
 int dsm_pack_weight(const float* w, void* w_packed_bf16, int Cout, int Cin, int mode, void* stream);
 int dsm_pack_ndhwc(const float* x_ncdhw, void* y_padded_bf16, int B, int C, int D, int H, int W, void* stream);
 int dsm_unpack_ndhwc(const void* x_padded_bf16, float* y_ncdhw, int B, int C, int D, int H, int W, void* stream);
@@ -295,7 +296,8 @@ int dsm_warp_indices(const float* disp, const float* row, const float* col, int 
  * default row-shifted-descriptor kernel for stride-1 convolutions, bit7: launch with programmatic stream
  * serialization - the kernel's prologue overlaps the previous kernel's tail, its dependent accesses wait on
  * griddepcontrol.wait; only for parameters (weights, scale, shift) that were written before the previous kernel
- * started; 0 = default).                                  */
+ * started; bit8: the weights of a single-output-channel stride-1 layer with 32 inputs are packed by dsm_pack_weight
+ * mode 3 (kw folded into the output columns: a third of the MMAs); 0 = default).                                  */
 int dsm_conv3d_fwd_ex(const void* x, const void* w_packed, const float* scale, const float* shift,
                       const void* residual, void* y,
                       int B, int Cin, int Cout, int D, int H, int W,

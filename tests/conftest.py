@@ -47,6 +47,16 @@ def golden():
 
 
 def rel_err(a, b):
-    """max |a-b| / max(|b|_inf, tiny): the 'relative error' used for the fp32 ops."""
+    """NORM-WISE relative error: max |a-b| / max |b| over the whole tensor (an error bound relative to the tensor's
+    scale, not per element — see rel_err_elem for the element-wise reading of north_star's "1e-4 relative")."""
     a = a.detach().double().cpu(); b = b.detach().double().cpu()
     return float((a - b).abs().max() / max(float(b.abs().max()), 1e-12))
+
+
+def rel_err_elem(a, b, floor_frac=1e-2):
+    """ELEMENT-WISE relative error with an absolute floor: max_i |a_i - b_i| / max(|b_i|, floor_frac * max |b|).
+    Elements smaller than 1 % of the tensor's scale (results of cancellation, which no fp32 summation order can hold to a
+    relative 1e-4) are judged against that floor; every other element against its own magnitude."""
+    a = a.detach().double().cpu(); b = b.detach().double().cpu()
+    floor = max(float(b.abs().max()) * floor_frac, 1e-30)
+    return float(((a - b).abs() / b.abs().clamp_min(floor)).max())
