@@ -368,11 +368,15 @@ def run_psmnet(args, rank, world, device, dist, barrier):
     barrier()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     sampler.active = True
+    if args.profile_range:                       # ncu --profile-from-start off: only the timed steps are captured
+        torch.cuda.profiler.start()
     e0.record()
     for _ in range(args.steps):
         run()
     e1.record()
     barrier()
+    if args.profile_range:
+        torch.cuda.profiler.stop()
     sampler.active = False
     t_ms = e0.elapsed_time(e1)
     n_burst = len(sampler.samples)
@@ -684,6 +688,7 @@ def main():
     ap.add_argument("--no-torch-baseline", action="store_true")
     ap.add_argument("--no-whole-model", action="store_true")
     ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--profile-range", action="store_true", help="cudaProfilerStart/Stop around the timed steps (for ncu --profile-from-start off)")
     args = ap.parse_args()
     if args.batch is None:      # the op chain of iResNet takes 0.2 ms per pair: 8 pairs per step give the clock sampler a region to see
         args.batch = {"dispnetc_selfsup_train": 4, "iresnet_ops_540x960": 8}.get(args.workload, 1)

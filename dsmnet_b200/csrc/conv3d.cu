@@ -987,7 +987,8 @@ struct DcGeom {
     int nops;
     short op_begin[6];       // MMAs of tile a are ops[op_begin[a] .. op_begin[a+1])
     DcOp ops[12];
-    short w_dst[27], w_src[27];   // weight block -> first smem row, first packed-weight row
+    short w_dst[27], w_src[27];   // weight block -> first smem row, first packed-weight row (of channel group 0)
+    int ngroups;                  // output-channel groups of NP channels (Cout = ngroups * NP)
     int dbg;                 // timing experiments only (variant bits 4..6): 1 = no epilogue global traffic, 2 = no TMA traffic, 4 = no MMAs
 };
 
@@ -1027,6 +1028,11 @@ conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Dp = g.D + 2, Hp = g.H + 2, Wp = g.W + 2;
     const long long plane = (long long)Hp * Wp, vol = plane * Dp;
+    // Cout > NP (hourglass conv5: 64 -> 64): output-channel groups of NP; a CTA keeps ONE group's 27 weight blocks resident
+    // and walks the tiles with the CTAs of its group (the input tiles are read once per group, from L2)
+    const int grp = (int)blockIdx.x % g.ngroups;
+    const int tile0 = (int)blockIdx.x / g.ngroups, tile_step = (int)gridDim.x / g.ngroups;
+    const int ch0 = grp * NP;
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = ptx::smem_u32(smem_raw);
@@ -1048,8 +1054,8 @@ conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     float* s_shift = s_scale + NP;
 
     if (tid < NP) {
-        s_scale[tid] = scale ? __ldg(scale + tid) : 1.f;
-        s_shift[tid] = shift ? __ldg(shift + tid) : 0.f;
+        s_scale[tid] = scale ? __ldg(scale + ch0 + tid) : 1.f;
+        s_shift[tid] = shift ? __ldg(shift + ch0 + tid) : 0.f;
     }
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_w);
@@ -1071,12 +1077,12 @@ conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (ptx::elect_one_sync()) {
             ptx::mbar_arrive_expect_tx(wfull_bar, C::W_BYTES);
             for (int i = 0; i < 27; ++i)
-                ptx::tma_load_2d(wsm + g.w_dst[i] * C::ROWB, &map_w, wfull_bar, 0, g.w_src[i]);
+                ptx::tma_load_2d(wsm + g.w_dst[i] * C::ROWB, &map_w, wfull_bar, 0, g.w_src[i] + ch0);
         }
         __syncwarp();
         ptx::griddep_wait();
         int s = 0; uint32_t ph = 0;
-        for (int t = blockIdx.x; t < g.ntiles; t += gridDim.x) {
+        for (int t = tile0; t < g.ntiles; t += tile_step) {
             const long long p0 = (long long)t * 128;
             if (dc_skip(p0, g.P, plane, vol, Dp)) continue;
 #pragma unroll 1
@@ -1105,7 +1111,7 @@ conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const uint32_t w_lo = (uint32_t)dsc | (wsm >> 4);
         int s = 0; uint32_t ph = 0;
         int tcount = 0;
-        for (int t = blockIdx.x; t < g.ntiles; t += gridDim.x) {
+        for (int t = tile0; t < g.ntiles; t += tile_step) {
             const long long p0 = (long long)t * 128;
             if (dc_skip(p0, g.P, plane, vol, Dp)) continue;
             const int acc = tcount & 1;
@@ -1153,7 +1159,7 @@ conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             if (half == 0) {
                 int tcount = 0;
                 const bool pair_ok = (g.Wo & 1) == 0;
-                for (int t = blockIdx.x; t < g.ntiles; t += gridDim.x) {
+                for (int t = tile0; t < g.ntiles; t += tile_step) {
                     const long long p0 = (long long)t * 128;
                     if (dc_skip(p0, g.P, plane, vol, Dp)) continue;
                     const long long p = p0 + r;
@@ -1205,7 +1211,7 @@ conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const float4* sc4 = reinterpret_cast<const float4*>(s_scale);
         const float4* sh4 = reinterpret_cast<const float4*>(s_shift);
         int tcount = 0;
-        for (int t = blockIdx.x; t < g.ntiles; t += gridDim.x) {
+        for (int t = tile0; t < g.ntiles; t += tile_step) {
             const long long p0 = (long long)t * 128;
             if (dc_skip(p0, g.P, plane, vol, Dp)) continue;
             const long long p = p0 + r;
@@ -1229,7 +1235,7 @@ conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 const int od = dz + ((c >> 2) & 1), oh = hy + ((c >> 1) & 1), ow = wx + (c & 1);
                 valid[jj] = interior && od < g.Do && oh < g.Ho && ow < g.Wo && !(g.dbg & 1);
                 off[jj] = g.y_f32 ? (((size_t)ob * g.Do + od) * g.Ho + oh) * g.Wo + ow
-                                  : ((((size_t)ob * (g.Do + 2) + od + 1) * (g.Ho + 2) + oh + 1) * (g.Wo + 2) + ow + 1) * (size_t)g.Cout;
+                                  : ((((size_t)ob * (g.Do + 2) + od + 1) * (g.Ho + 2) + oh + 1) * (g.Wo + 2) + ow + 1) * (size_t)g.Cout + ch0;
             }
             auto release = [&]() {
                 ptx::tc_fence_before();
@@ -1367,7 +1373,9 @@ int launch_dc(const CUtensorMap& map_a, const CUtensorMap& map_w, const DcGeom& 
     if (e != cudaSuccess) return (int)e;
     int nsm = DSM_NUM_SMS_B200, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    const int nblocks = g.ntiles < nsm ? g.ntiles : nsm;
+    int per_group = nsm / g.ngroups;
+    if (per_group > g.ntiles) per_group = g.ntiles;
+    const int nblocks = per_group * g.ngroups;
     launch_kernel(kern, dim3(nblocks), dim3(C::THREADS), C::SMEM, st, map_a, map_w, g, scale, shift, residual, y);
     return dsm_launch_status();
 }
@@ -1375,7 +1383,7 @@ int launch_dc(const CUtensorMap& map_a, const CUtensorMap& map_w, const DcGeom& 
 // MMA schedule of the class-sharing transposed conv: for every input offset o in {0,1}^3 (grouped by the
 // (od,oh) tile that is loaded, ow is a descriptor shift) the accumulator blocks (Gray-code class order) whose
 // class needs that offset, split into contiguous runs; weight blocks are laid out in the same order.
-void build_dc_schedule(DcGeom& g, int NP) {
+void build_dc_schedule(DcGeom& g, int NP, int CoutTotal) {
     static const int pos_class[8] = {0, 1, 3, 2, 6, 7, 5, 4};
     int nops = 0, nblk = 0;
     for (int a = 0; a < 4; ++a) for (int ow = 0; ow < 2; ++ow) {
@@ -1399,7 +1407,7 @@ void build_dc_schedule(DcGeom& g, int NP) {
                 auto tap = [](int par, int off) { return par == 0 ? 1 : (off == 1 ? 0 : 2); };
                 const int kd = tap((c >> 2) & 1, od), kh = tap((c >> 1) & 1, oh), kw = tap(c & 1, ow);
                 g.w_dst[nblk] = (short)(nblk * NP);
-                g.w_src[nblk] = (short)(((kd * 3 + kh) * 3 + kw) * NP);
+                g.w_src[nblk] = (short)(((kd * 3 + kh) * 3 + kw) * CoutTotal);
                 ++nblk;
             }
             pos = end + 1;
@@ -1456,7 +1464,10 @@ int conv3d_dispatch(const void* x, const void* w, const float* scale, const floa
         if (!encode_map(&maps.w, w, 2, dims, strides, box, row_bytes)) return DSM_EDRIVER;
     }
     // transposed, Cout <= 32: the class-sharing kernel (variant bit3 set = keep the per-class kernel, for A/B runs)
-    if (transposed && NP <= 32 && Cin <= 64 && al32 && !(variant & 8)) {
+    // Cout = 64 (hourglass conv5) runs as two 32-channel groups on the same kernel (variant bit 2 keeps the per-class kernel)
+    const bool dc_grouped = transposed && y_dtype == DSM_BF16 && Cout == 64 && !(variant & 4);
+    if (transposed && (NP <= 32 || dc_grouped) && Cin <= 64 && al32 && !(variant & 8)) {
+        const int NPd = dc_grouped ? 32 : NP;
         CUtensorMap map_a;
         cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)P};
         cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
@@ -1468,12 +1479,20 @@ int conv3d_dispatch(const void* x, const void* w, const float* scale, const floa
         dg.Cout = Cout; dg.relu = relu; dg.y_f32 = (y_dtype == DSM_F32);
         dg.P = P; dg.ntiles = (int)dsm_ceil_div_ll(P, 128);
         dg.dbg = (variant >> 4) & 7;
-        build_dc_schedule(dg, NP);
+        dg.ngroups = dc_grouped ? Cout / 32 : 1;
+        build_dc_schedule(dg, NPd, NP);                          // packed weights are [27][NP = CoutP][Cin]
+        CUtensorMap map_wd = maps.w;
+        if (dc_grouped) {                                        // weight boxes of 32 rows instead of CoutP
+            cuuint64_t wdims[2] = {(cuuint64_t)Cin, (cuuint64_t)27 * NP};
+            cuuint64_t wstrides[1] = {(cuuint64_t)Cin * 2};
+            cuuint32_t wbox[2] = {(cuuint32_t)KC, 32u};
+            if (!encode_map(&map_wd, w, 2, wdims, wstrides, wbox, row_bytes)) return DSM_EDRIVER;
+        }
         cudaStream_t st = (cudaStream_t)stream;
-        if (KC == 32 && NP == 16) return launch_dc<32, 16>(map_a, maps.w, dg, scale, shift, residual, y, st);
-        if (KC == 32 && NP == 32) return launch_dc<32, 32>(map_a, maps.w, dg, scale, shift, residual, y, st);
-        if (KC == 64 && NP == 16) return launch_dc<64, 16>(map_a, maps.w, dg, scale, shift, residual, y, st);
-        if (KC == 64 && NP == 32) return launch_dc<64, 32>(map_a, maps.w, dg, scale, shift, residual, y, st);
+        if (KC == 32 && NPd == 16) return launch_dc<32, 16>(map_a, map_wd, dg, scale, shift, residual, y, st);
+        if (KC == 32 && NPd == 32) return launch_dc<32, 32>(map_a, map_wd, dg, scale, shift, residual, y, st);
+        if (KC == 64 && NPd == 16) return launch_dc<64, 16>(map_a, map_wd, dg, scale, shift, residual, y, st);
+        if (KC == 64 && NPd == 32) return launch_dc<64, 32>(map_a, map_wd, dg, scale, shift, residual, y, st);
         return DSM_EUNSUPPORTED;
     }
     // stride-1, Cout <= 32: the plane-sharing kernel (variant bit3 set = keep the per-tile kernels, for A/B runs)

@@ -12,7 +12,7 @@ for r in rows:
             if d.get('Metric Unit')=='us': v*=1000
             seq.append((d['Kernel Name'],d.get('Grid Size',''),v))
 # take the last step: find last occurrence of concat kernel
-idx=[i for i,(k,g,v) in enumerate(seq) if 'concat_ndhwc' in k]
+idx=[i for i,(k,g,v) in enumerate(seq) if 'concat_ndhwc' in k or 'pack_nhwc' in k]
 print('launches',len(seq),'concat at',idx[-6:])
 # the last COMPLETE step: from the second-to-last concat launch to the last one (the capture may end mid-step)
 step=seq[idx[-2]:idx[-1]] if len(idx) >= 2 else seq[idx[-1]:]
