@@ -362,3 +362,21 @@ def test_fused_volume_conv_full_size():
     assert conv_timeouts() == 0
     assert float((fused - plain).abs().max()) <= 2.0 ** -7 * float(plain.abs().max())       # one bf16 ulp at the top binade
     assert float((fused != plain).float().mean()) < 0.01
+
+
+@pytest.mark.parametrize("kwfold", [True, False])
+@pytest.mark.parametrize("dims,B", [((4, 6, 20), 2), ((9, 13, 131), 1), ((3, 40, 7), 1)])
+def test_single_channel_conv_kwfold_and_plain(kwfold, dims, B, monkeypatch):
+    """classif*.2 (Conv3d 32 -> 1, fp32 output, cumulative residual): the kw-fold mode (three kw taps as output columns, tiles
+    of 120 positions, shuffled column sum) and the plain 32 -> 16 mapping against the oracle — rows longer and shorter than a
+    30-position quadrant, several image rows per tile"""
+    import dsmnet_b200.conv3d as C3
+    monkeypatch.setattr(C3, "KWFOLD", kwfold)
+    torch.manual_seed(31)
+    x = torch.randn(B, 32, *dims)
+    w = torch.randn(1, 32, 3, 3, 3) * (2.0 / (27 * 32)) ** 0.5
+    res = torch.randn(B, 1, *dims)
+    ref = O.conv3d_block(x, w, None, None, 1, False, res, False, torch.bfloat16)
+    out = run_layer(x, w, None, None, 1, False, res, False)
+    assert out.shape == ref.shape
+    assert float((out - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
