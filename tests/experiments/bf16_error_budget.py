@@ -5,14 +5,14 @@ rounding points switched to bf16, on (a) purely random BN-calibrated weights —
 192 candidate disparities with broad, multi-modal weights — and (b) the `psmnet_matcher_params` stack that really matches.
 Prints mean |disparity - fp32 disparity| per variant.  Runs in about a minute at the default size.
 
-    python tools/bf16_error_budget.py [H W maxdisp]
+    python tests/experiments/bf16_error_budget.py [H W maxdisp]
 """
 import os
 import sys
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import oracle.ops as O  # noqa: E402
 

@@ -4,7 +4,7 @@ against the CPU oracle in fp32.  Also the whole drop-in model on the odd-sized 3
 
 What is asserted, and why the statement is per confidence bucket: the disparity is the MEAN of the
 soft-argmin distribution over 192 candidates, so its sensitivity to a cost perturbation grows with the distribution's
-spread.  Measured with the oracle's bf16 emulation on this pair (tools/bf16_error_budget.py): pixels whose
+spread.  Measured with the oracle's bf16 emulation on this pair (tests/experiments/bf16_error_budget.py): pixels whose
 distribution has std < 1 px differ from fp32 by 0.002 px, std >= 16 px (sky, road, repetitive texture under this crude
 SAD matcher) by 0.56 px.  A trained PSMNet is trained to make the distribution unimodal everywhere; the bf16 tolerance of
 BASELINE.json (mean delta < 0.01 px) is therefore asserted where the matcher is confident, and bounded elsewhere."""

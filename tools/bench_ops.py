@@ -61,7 +61,7 @@ def main():
     from dsmnet_b200.imwrap import WarpFunction
     from dsmnet_b200.conv3d import FusedConv3d
     from dsmnet_b200.volume_layout import PaddedVolume
-    import oracle.ops as O    # only imwrap_rowcol (host-side linspace vectors), no compute
+    from dsmnet_b200.imwrap import grid_vectors
     _lib.lib()
     hbm, tf, which = peaks()
     dev = torch.device("cuda")
@@ -118,7 +118,7 @@ def main():
     # ---- op 5: imwrap ----------------------------------------------------------------------------
     for (B, C, H0, W0, tag) in [(1, 32, 540, 960, "cfg4 iResNet"), (8, 3, 384, 768, "self-sup level 0 B=8")]:
         src = torch.rand(B, C, H0, W0, device=dev); disp = torch.rand(B, 1, H0, W0, device=dev) * 0.1 * W0
-        row, col = O.imwrap_rowcol(H0, W0, H0, W0)
+        row, col = grid_vectors(H0, W0, H0, W0)
         row, col = row.to(dev), col.to(dev)
         t = timeit(lambda i: WarpFunction.apply(src, disp, row, col, 5e-5, False))
         mem("imwrap fwd %s (%d,%d,%d,%d)" % (tag, B, C, H0, W0), 4.0 * B * (2 * C * H0 * W0 + H0 * W0), t)

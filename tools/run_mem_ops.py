@@ -7,7 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dsmnet_b200.corr1d import corr1d
 from dsmnet_b200.softargmin import softargmin
 from dsmnet_b200.imwrap import WarpFunction
-import oracle.ops as O   # host-side linspace vectors only
+from dsmnet_b200.imwrap import grid_vectors
 
 dev = torch.device("cuda")
 torch.manual_seed(0)
@@ -17,7 +17,7 @@ for _ in range(3):
     c = (torch.randn(1, 192, 256, 512, device=dev) * 2).requires_grad_()
     softargmin(c, -1.0).backward(torch.randn(1, 256, 512, device=dev))
     src = torch.rand(1, 32, 540, 960, device=dev, requires_grad=True); disp = (torch.rand(1, 1, 540, 960, device=dev) * 96).requires_grad_()
-    row, col = O.imwrap_rowcol(540, 960, 540, 960)
+    row, col = grid_vectors(540, 960, 540, 960)
     WarpFunction.apply(src, disp, row.to(dev), col.to(dev), 5e-5, False).backward(torch.randn(1, 32, 540, 960, device=dev))
 torch.cuda.synchronize()
 print("ok")
