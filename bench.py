@@ -447,7 +447,7 @@ def run_psmnet(args, rank, world, device, dist, barrier):
     ms_k = time_kernel_alone(lambda: layer(ws["a"], ws["c0"]))
     flops = 2.0 * 27 * 32 * 32 * B * (MAXDISP // 4) * h * w
     achieved = flops / (ms_k * 1e-3) / 1e12
-    traffic, tsrc = profiled_traffic("conv3d_rs_kernel<32, 32>")
+    traffic, tsrc = profiled_traffic("conv3d_rs_kernel<32, 32, 0>")
     if traffic is not None and (B, H, W) != (1, 384, 1248):
         traffic, tsrc = None, "captured at batch 1, 384x1248 only"
     roofline = {"bound": "tensor", "kernel": "conv3d_rs_kernel<KC=32,NP=32> (Conv3d 32->32 k3 s1 + BN + ReLU, 6 launches/step)",

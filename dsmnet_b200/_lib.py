@@ -61,6 +61,7 @@ SIGNATURES = {
     "dsm_pack_nhwc_bf16": [_P, _P, _I, _I, _I, _I, _I, _P],
     "dsm_pack_nhwc_bf16_pair": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "dsm_conv2d_fwd": [_P, _P, _P, _P, _P, _P] + [_I] * 16 + [_P],
+    "dsm_conv2d_rs_fwd": [_P, _P, _P, _P, _P, _P] + [_I] * 13 + [_P],
     "dsm_conv2d_first_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "dsm_spp_workspace_bytes": [_I, _I, _I],
     "dsm_spp_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, c_size_t, _P],

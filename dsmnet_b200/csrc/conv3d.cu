@@ -1780,11 +1780,19 @@ extern "C" int dsm_conv3d_volume_fwd(const void* featL, const void* featR, const
 }
 
 // 2-D convolution block of the feature-extraction trunks; see conv2d_dispatch and include/dsmnet_b200.h
+extern "C" int dsm_conv2d_rs_fwd(const void* x, const void* w_packed, const float* scale, const float* shift,
+                                 const void* residual, void* y, int B, int Cin, int Cout, int H, int W, int dilation, int relu,
+                                 int rim_in, int rim_out, int ldx, int ldy, int ldr, int variant, void* stream);
 extern "C" int dsm_conv2d_fwd(const void* x, const void* w_packed, const float* scale, const float* shift,
                               const void* residual, void* y,
                               int B, int Cin, int Cout, int H, int W, int ksize, int stride, int dilation, int relu,
                               int rim_in, int rim_out, int ldx, int ldy, int ldr, int y_mode, int variant, void* stream) {
     DsmDeviceGuard dsm_guard_(x);
+    // stride-1 3x3 layers with 32 / 64 channels: the row-sharing kernel (conv2d_rs.cu) unless variant bit 2 asks for the per-tile one
+    if (!(variant & 4) && ksize == 3 && stride == 1 && y_mode == 0 && relu <= 1 && (Cin == 32 || Cin == 64) && (Cout == 32 || Cout == 64) &&
+        !(ldy & 15) && !(ldr & 15) && dsm_aligned32(y) && (!residual || dsm_aligned32(residual)))
+        return dsm_conv2d_rs_fwd(x, w_packed, scale, shift, residual, y, B, Cin, Cout, H, W, dilation, relu, rim_in, rim_out,
+                                 ldx, ldy, ldr, variant, stream);
     return conv2d_dispatch(x, w_packed, scale, shift, residual, y, B, Cin, Cout, H, W, ksize, stride, dilation, relu,
                            rim_in, rim_out, ldx, ldy, ldr, y_mode, variant, stream);
 }

@@ -17,6 +17,7 @@ of this path's scope), on CUDA under ``torch.no_grad()`` they run these plans.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -25,6 +26,9 @@ import torch.nn as nn
 from . import _lib
 
 PDL = 128          # dsm_conv2d_fwd variant bit 7: programmatic dependent launch between consecutive layers
+# dsm_conv2d_fwd variant bit 3: one MMA issuer in the row-sharing kernel -> the trunk is bit-reproducible from run to run
+# (10-20 % slower on the 32 / 64-channel layers).  Read when a plan is built.
+DETERMINISTIC = os.environ.get("DSM_TRUNK_DETERMINISTIC", "0") == "1"
 
 
 class PaddedImage:
@@ -76,7 +80,9 @@ def _fold(cout, bn: Optional[nn.BatchNorm2d], bias: Optional[torch.Tensor], devi
 class FusedConv2d:
     """y = relu?(conv2d(x) * scale + shift [+ residual]) on PaddedImages; one dsm_conv2d_fwd launch."""
 
-    def __init__(self, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d], relu: int, device, variant: int = PDL):
+    def __init__(self, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d], relu: int, device, variant: Optional[int] = None):
+        if variant is None:
+            variant = PDL | (8 if DETERMINISTIC else 0)
         w = conv.weight.detach().float()
         self.cout, self.cin, k, k2 = w.shape
         if k != k2 or k not in (1, 3):

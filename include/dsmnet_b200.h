@@ -207,6 +207,15 @@ int dsm_conv2d_fwd(const void* x, const void* w_packed, const float* scale, cons
                    const void* residual, void* y,
                    int B, int Cin, int Cout, int H, int W, int ksize, int stride, int dilation, int relu,
                    int rim_in, int rim_out, int ldx, int ldy, int ldr, int y_mode, int variant, void* stream);
+/* The row-sharing form of dsm_conv2d_fwd (conv2d_rs.cu) for ksize 3, stride 1, Cin and Cout in {32, 64}, y_mode 0, relu 0|1,
+ * ldy / ldr multiples of 16 and 32-byte aligned y / residual: a CTA keeps all nine weight tiles resident and computes a band of
+ * 4 (Cout 64) or 8 (Cout 32) output rows from each input row loaded once.  dsm_conv2d_fwd routes eligible layers here unless
+ * variant bit 2 (value 4) is set; DSM_EUNSUPPORTED for other channel counts.  Three warps issue the MMAs of one accumulator in
+ * rotation, so the fp32 accumulation order (the last bit) can differ from run to run; variant bit 3 (value 8) uses one issuer:
+ * bit-reproducible, 10-20 % slower. */
+int dsm_conv2d_rs_fwd(const void* x, const void* w_packed, const float* scale, const float* shift,
+                      const void* residual, void* y, int B, int Cin, int Cout, int H, int W, int dilation, int relu,
+                      int rim_in, int rim_out, int ldx, int ldy, int ldr, int variant, void* stream);
 /* the image-facing layer: Conv2d(3 -> 32, k 3|5, stride 2, pad k/2) + affine + ReLU, NCHW fp32 image [B][3][H][W] with the
  * PyTorch fp32 weight [32][3][k][k] -> padded NHWC bf16 [B][Ho+2r][Wo+2r][32] (submodule.py:68, gcnet.py:21); CUDA cores. */
 int dsm_conv2d_first_fwd(const float* img, const float* w, const float* scale, const float* shift, void* out,

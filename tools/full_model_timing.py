@@ -68,18 +68,33 @@ if "--layers" in sys.argv:
     ws = plan._workspace(2, 384, 1248)
     half, q64, q128, cat = ws["half"], ws["q64"], ws["q128"], ws["cat"]
     rows = []
-    def layer(name, fn, fl):
-        ms = t(fn, 20)
+    def layer(name, fn, fl, conv=None):
+        """20 back-to-back launches captured in one CUDA graph (the way the plan runs them)"""
+        def once():
+            gl = torch.cuda.CUDAGraph()
+            fn(); torch.cuda.synchronize()
+            with torch.cuda.graph(gl):
+                for _ in range(20):
+                    fn()
+            return t(lambda: gl.replay(), 10) / 20
+        ms = once()
         rows.append((name, ms * 1e3, fl / ms / 1e9))
+        if conv is not None and conv.k == 3 and conv.stride == 1 and conv.cin <= 64 and conv.cout <= 64:
+            v0 = conv.variant
+            for tag, v in (("  .. per-tile kernel (variant 4)", v0 | 4), ("  .. row-sharing, one MMA issuer (variant 8)", v0 | 8)):
+                conv.variant = v
+                ms = once()
+                rows.append((tag, ms * 1e3, fl / ms / 1e9))
+            conv.variant = v0
     px2, px4 = 2 * 192 * 624, 2 * 96 * 312
     layer("firstconv.0 3->32 s2 (CUDA cores)", lambda: plan.first(LR, half[0]), 2 * 27 * 32 * px2)
-    layer("32->32 k3 @192x624", lambda: plan.fc2(half[0], half[1]), 2 * 9 * 32 * 32 * px2)
+    layer("32->32 k3 @192x624", lambda: plan.fc2(half[0], half[1]), 2 * 9 * 32 * 32 * px2, plan.fc2)
     c1, c2, ds = plan.layers[1][0]
     layer("32->64 k3 s2", lambda: c1(half[0], q64[0]), 2 * 9 * 32 * 64 * px4)
     layer("32->64 k1 s2", lambda: ds(half[0], q64[1]), 2 * 32 * 64 * px4)
     c1, c2, ds = plan.layers[1][1]
-    layer("64->64 k3 @96x312", lambda: c1(q64[0], q64[1]), 2 * 9 * 64 * 64 * px4)
-    layer("64->64 k3 + residual", lambda: c2(q64[0], q64[1], residual=q64[2]), 2 * 9 * 64 * 64 * px4)
+    layer("64->64 k3 @96x312", lambda: c1(q64[0], q64[1]), 2 * 9 * 64 * 64 * px4, c1)
+    layer("64->64 k3 + residual", lambda: c2(q64[0], q64[1], residual=q64[2]), 2 * 9 * 64 * 64 * px4, c2)
     c1, c2, ds = plan.layers[2][0]
     layer("64->128 k3 (from cat slice)", lambda: c1(cat, q128[0]), 2 * 9 * 64 * 128 * px4)
     layer("64->128 k1", lambda: ds(cat, q128[1]), 2 * 64 * 128 * px4)
@@ -90,6 +105,6 @@ if "--layers" in sys.argv:
     layer("320->128 k3 (lastconv.0)", lambda: plan.last0(cat, q128[0]), 2 * 9 * 320 * 128 * px4)
     o = torch.empty(2, 32, 96, 312, device=dev)
     layer("128->32 k1 -> fp32 NCHW", lambda: plan.last2(q128[0], o), 2 * 128 * 32 * px4)
-    print("%-36s %10s %10s" % ("trunk layer (batch 2)", "us", "TFLOP/s"))
+    print("%-44s %10s %10s" % ("trunk layer (batch 2)", "us", "TFLOP/s"))
     for name, us, tf in rows:
-        print("%-36s %10.1f %10.1f" % (name, us, tf))
+        print("%-44s %10.1f %10.1f" % (name, us, tf))
