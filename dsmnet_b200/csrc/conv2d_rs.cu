@@ -56,23 +56,31 @@ struct R2Geom {
     int items_per_image;     // row_tiles * (nbands[0] + nbands[1])
     int nitems;              // B * items_per_image
     int Cout;
+    int ngroups;             // output-channel groups of NP channels (Cout = 128: two groups of 64); a CTA serves ONE group
     int nissue;              // 1: one warp issues every MMA (bit-reproducible accumulation order); 3: the three warps rotate
 };
 
-template <int KC, int NP>
+template <int KC, int NP, int NCH>
 struct R2Cfg {
     static constexpr int R = 256 / NP;                           // output rows per band: 8 (NP = 32) or 4 (NP = 64)
     static constexpr int ROWB = KC * 2;
     static constexpr int A_ROWS = 132;                           // 128 + 2 * max dilation
     static constexpr int A_BYTES = ((A_ROWS * ROWB + 1023) / 1024) * 1024;
-    static constexpr int W_TILE = 3 * NP * ROWB;                  // the three kh taps of one kw, kh = 2, 1, 0
-    static constexpr int W_BYTES = 3 * W_TILE;
+    static constexpr int W_TILE = 3 * NP * ROWB;                  // the three kh taps of one (kw, K chunk), kh = 2, 1, 0
+    static constexpr int W_BYTES = 3 * NCH * W_TILE;              // [kw][chunk] tiles, resident for the whole kernel
     static constexpr int BAR_BYTES = 512;
-    static constexpr int BUDGET = 200 * 1024 - W_BYTES - 1024 - BAR_BYTES - 2 * NP * 4;
+    static constexpr int BUDGET = 225 * 1024 - W_BYTES - 1024 - BAR_BYTES - 2 * NP * 4;
     static constexpr int S_RAW = BUDGET / A_BYTES;
-    static constexpr int STAGES = S_RAW > 8 ? 8 : S_RAW;
+    // The ring depth is a multiple of the number of MMA issuers NI, so that a stage always belongs to the SAME issuer: that
+    // warp then observes every phase of the stage's barrier.  (With rotating ownership a warp looks at a barrier only every
+    // few uses, and a parity wait cannot tell "two phases behind" from "done"; having every issuer wait on every stage is not
+    // safe either — measured: a warp stalled at the MMA queue gets lapped by the ring.)
+    static constexpr int STAGES = S_RAW >= 6 ? 6 : (S_RAW >= 4 ? 4 : S_RAW);
+    static constexpr int NI = (STAGES % 3 == 0) ? 3 : ((STAGES % 2 == 0) ? 2 : 1);
+    static constexpr int NACC = 2;
     static constexpr int ACC_COLS = R * NP;                       // 256
-    static constexpr int TMEM_COLS = 2 * ACC_COLS;                // 512
+    static constexpr int TMEM_COLS = NACC * ACC_COLS;             // 512
+    static constexpr int CW = 32;                                 // accumulator columns per epilogue step
     static constexpr int SMEM = W_BYTES + STAGES * A_BYTES + 1024 + BAR_BYTES + 2 * NP * 4;
     static constexpr int THREADS = 384;                           // warp 0 TMA, warps 1-3 MMA, warps 4-11 epilogue
     static_assert(STAGES >= 4, "activation ring too shallow");
@@ -93,14 +101,16 @@ __device__ __forceinline__ R2Item r2_decode(const R2Geom& g, int t, int R) {
     return it;
 }
 
-template <int KC, int NP>
+template <int KC, int NP, int NCH>
 __global__ void __launch_bounds__(384, 1)
 conv2d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                  const __grid_constant__ R2Geom g, const float* __restrict__ scale, const float* __restrict__ shift,
                  const void* __restrict__ residual, void* __restrict__ y) {
-    using C = R2Cfg<KC, NP>;
+    using C = R2Cfg<KC, NP, NCH>;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Hp = g.H + 2 * g.ri, Wp = g.W + 2 * g.ri;
+    const int grp = blockIdx.x % g.ngroups;                      // this CTA's output-channel group: its weights never change
+    const int t0 = blockIdx.x / g.ngroups, tstep = gridDim.x / g.ngroups;
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = ptx::smem_u32(smem_raw);
@@ -122,14 +132,14 @@ conv2d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     float* s_shift = s_scale + NP;
 
     if (tid < NP) {
-        s_scale[tid] = scale ? __ldg(scale + tid) : 1.f;
-        s_shift[tid] = shift ? __ldg(shift + tid) : 0.f;
+        s_scale[tid] = scale ? __ldg(scale + grp * NP + tid) : 1.f;
+        s_shift[tid] = shift ? __ldg(shift + grp * NP + tid) : 0.f;
     }
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_w);
         ptx::prefetch_tensormap(&map_a);
         for (int s = 0; s < C::STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; ++a) { ptx::mbar_init(tfull_bar(a), 3); ptx::mbar_init(tempty_bar(a), 8); }
+        for (int a = 0; a < C::NACC; ++a) { ptx::mbar_init(tfull_bar(a), 3); ptx::mbar_init(tempty_bar(a), 8); }
         ptx::mbar_init(wfull_bar, 1);
         ptx::fence_mbar_init();
     }
@@ -142,33 +152,38 @@ conv2d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     ptx::griddep_launch_dependents();
     if (warp == 0) {
         // ================= TMA producer =================
-        if (ptx::elect_one_sync()) {                            // the 9 weight tiles, once: [kw][kh = 2, 1, 0][NP rows]
-            ptx::mbar_arrive_expect_tx(wfull_bar, 9 * NP * C::ROWB);
+        if (ptx::elect_one_sync()) {                            // this group's weight tiles, once: [kw][chunk][kh = 2, 1, 0][NP rows]
+            ptx::mbar_arrive_expect_tx(wfull_bar, 9 * NCH * NP * C::ROWB);
             for (int kh = 0; kh < 3; ++kh)
                 for (int kw = 0; kw < 3; ++kw)
-                    ptx::tma_load_2d(wsm + kw * C::W_TILE + (2 - kh) * NP * C::ROWB, &map_w, wfull_bar, 0, (kh * 3 + kw) * g.Cout);
+                    for (int ch = 0; ch < NCH; ++ch)
+                        ptx::tma_load_2d(wsm + (kw * NCH + ch) * C::W_TILE + (2 - kh) * NP * C::ROWB, &map_w, wfull_bar,
+                                         ch * KC, (kh * 3 + kw) * g.Cout + grp * NP);
         }
         __syncwarp();
         ptx::griddep_wait();                                    // the activations are the previous kernel's output
         int s = 0; uint32_t ph = 0;
         const uint32_t tx = (uint32_t)(128 + 2 * g.dil) * C::ROWB;
-        for (int t = blockIdx.x; t < g.nitems; t += gridDim.x) {
+        for (int t = t0; t < g.nitems; t += tstep) {
             const R2Item item = r2_decode(g, t, C::R);
             for (int i = -1; i <= item.nb; ++i) {
                 const int o = item.o0 + g.dil * i;               // input row (image coordinates)
                 if (o < 0 || o >= g.H) continue;                 // a rim row: contributes nothing
-                wait_bar(empty_bar(s), ph ^ 1u);
-                if (ptx::elect_one_sync()) {
-                    ptx::mbar_arrive_expect_tx(full_bar(s), tx);
-                    ptx::tma_load_2d(ring + s * C::A_BYTES, &map_a, full_bar(s), 0,
-                                     (item.b * Hp + g.ri + o) * Wp + item.tile * 128 - g.dil);
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    wait_bar(empty_bar(s), ph ^ 1u);
+                    if (ptx::elect_one_sync()) {
+                        ptx::mbar_arrive_expect_tx(full_bar(s), tx);
+                        ptx::tma_load_2d(ring + s * C::A_BYTES, &map_a, full_bar(s), ch * KC,
+                                         (item.b * Hp + g.ri + o) * Wp + item.tile * 128 - g.dil);
+                    }
+                    __syncwarp();
+                    if (++s == C::STAGES) { s = 0; ph ^= 1u; }
                 }
-                __syncwarp();
-                if (++s == C::STAGES) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp <= 3) {
-        // ================= MMA issuers: the three warps take the input rows in rotation =================
+        // ================= MMA issuers: NI of the three warps take the stages in rotation (stage s <-> warp s % NI) =================
         const int my = warp - 1;
         constexpr uint32_t idesc0 = ptx::make_idesc_bf16(0);
         wait_bar(wfull_bar, 0);
@@ -180,10 +195,10 @@ conv2d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const uint32_t kw_step = (uint32_t)(g.dil * C::ROWB) >> 4;
         int s = 0; uint32_t ph = 0;
         int tcount = 0, rot = 0;
-        for (int t = blockIdx.x; t < g.nitems; t += gridDim.x) {
+        for (int t = t0; t < g.nitems; t += tstep) {
             const R2Item item = r2_decode(g, t, C::R);
-            const int acc = tcount & 1;
-            const uint32_t use_ph = (uint32_t)(tcount >> 1) & 1u;
+            const int acc = tcount % C::NACC;
+            const uint32_t use_ph = (uint32_t)(tcount / C::NACC) & 1u;
             ++tcount;
             wait_bar(tempty_bar(acc), use_ph);                   // drained AND zero-filled by the epilogue warps
             ptx::tc_fence_after();
@@ -191,29 +206,32 @@ conv2d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int i = -1; i <= item.nb; ++i) {
                 const int o = item.o0 + g.dil * i;
                 if (o < 0 || o >= g.H) continue;
-                if ((g.nissue == 1 ? 0 : rot) == my) {
-                    const int jlo = max(i - 1, 0), jhi = min(i + 1, item.nb - 1);
-                    const int brow = (2 - (i - jlo + 1)) * NP;    // weight row of block jlo's tap (kh = i - jlo + 1)
-                    const uint32_t d_lo = d_tmem + jlo * NP;
-                    const uint32_t idesc = idesc0 | ((uint32_t)((jhi - jlo + 1) * NP >> 3) << 17);
-                    wait_bar(full_bar(s), ph);
-                    ptx::tc_fence_after();
-                    if (ptx::elect_one_sync()) {
-                        const uint32_t a_lo0 = ring_lo + (uint32_t)s * (C::A_BYTES >> 4);
-                        const uint32_t b_lo0 = w_lo + ((uint32_t)(brow * C::ROWB) >> 4);
+                const int jlo = max(i - 1, 0), jhi = min(i + 1, item.nb - 1);
+                const int brow = (2 - (i - jlo + 1)) * NP;        // weight row of block jlo's tap (kh = i - jlo + 1)
+                const uint32_t d_lo = d_tmem + jlo * NP;
+                const uint32_t idesc = idesc0 | ((uint32_t)((jhi - jlo + 1) * NP >> 3) << 17);
 #pragma unroll
-                        for (int kw = 0; kw < 3; ++kw) {
+                for (int ch = 0; ch < NCH; ++ch) {
+                    if ((g.nissue == 1 ? 0 : rot) == my) {
+                        wait_bar(full_bar(s), ph);
+                        ptx::tc_fence_after();
+                        if (ptx::elect_one_sync()) {
+                            const uint32_t a_lo0 = ring_lo + (uint32_t)s * (C::A_BYTES >> 4);
+                            const uint32_t b_lo0 = w_lo + ((uint32_t)(brow * C::ROWB + ch * C::W_TILE) >> 4);
 #pragma unroll
-                            for (int k = 0; k < KC / 16; ++k)
-                                ptx::umma_bf16_lohi(d_lo, a_lo0 + kw * kw_step + ((k * 32) >> 4),
-                                                    b_lo0 + ((kw * C::W_TILE + k * 32) >> 4), desc_hi, idesc, 1u);
+                            for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+                                for (int k = 0; k < KC / 16; ++k)
+                                    ptx::umma_bf16_lohi(d_lo, a_lo0 + kw * kw_step + ((k * 32) >> 4),
+                                                        b_lo0 + ((kw * NCH * C::W_TILE + k * 32) >> 4), desc_hi, idesc, 1u);
+                            }
+                            ptx::umma_commit(empty_bar(s));
                         }
-                        ptx::umma_commit(empty_bar(s));
+                        __syncwarp();
                     }
-                    __syncwarp();
+                    if (++rot == C::NI) rot = 0;
+                    if (++s == C::STAGES) { s = 0; ph ^= 1u; }
                 }
-                if (++rot == 3) rot = 0;
-                if (++s == C::STAGES) { s = 0; ph ^= 1u; }
             }
             if (ptx::elect_one_sync()) ptx::umma_commit(tfull_bar(acc));   // this warp's share of "accumulators complete"
             __syncwarp();
@@ -227,7 +245,7 @@ conv2d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         constexpr int JJ = C::R / 2;
         {   // both accumulator buffers start zero-filled; arriving completes phase 0 of their "free" barriers
 #pragma unroll
-            for (int a2 = 0; a2 < 2; ++a2)
+            for (int a2 = 0; a2 < C::NACC; ++a2)
 #pragma unroll
                 for (int jj = 0; jj < JJ; ++jj)
 #pragma unroll
@@ -236,19 +254,22 @@ conv2d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             ptx::tc_wait_st();
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) { ptx::mbar_arrive(tempty_bar(0)); ptx::mbar_arrive(tempty_bar(1)); }
+            if (lane == 0) {
+#pragma unroll
+                for (int a2 = 0; a2 < C::NACC; ++a2) ptx::mbar_arrive(tempty_bar(a2));
+            }
         }
         const float4* sc4 = reinterpret_cast<const float4*>(s_scale);
         const float4* sh4 = reinterpret_cast<const float4*>(s_shift);
         const int Hop = g.H + 2 * g.ro, Wop = g.W + 2 * g.ro;
         int tcount = 0;
-        for (int t = blockIdx.x; t < g.nitems; t += gridDim.x) {
+        for (int t = t0; t < g.nitems; t += tstep) {
             const R2Item item = r2_decode(g, t, C::R);
             const int wp = item.tile * 128 + r;                  // padded column of this lane
             const int x = wp - g.ri;
             const bool valid = x >= 0 && x < g.W;
-            const int acc = tcount & 1;
-            const uint32_t acc_ph = (uint32_t)(tcount >> 1) & 1u;
+            const int acc = tcount % C::NACC;
+            const uint32_t acc_ph = (uint32_t)(tcount / C::NACC) & 1u;
             ++tcount;
             const uint32_t taddr0 = tmem + ((uint32_t)(q * 32) << 16) + acc * C::ACC_COLS;
             int my_last = -1;
@@ -262,7 +283,7 @@ conv2d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             // pixel offset of (row o0, column x) in the output / residual buffers; consecutive band rows are dil rows apart
             const size_t pix0 = ((size_t)item.b * Hop + g.ro + item.o0) * Wop + g.ro + x;
             const size_t pstep = (size_t)g.dil * Wop;
-            const __nv_bfloat16* resb = reinterpret_cast<const __nv_bfloat16*>(residual);
+            const __nv_bfloat16* resb = residual ? reinterpret_cast<const __nv_bfloat16*>(residual) + grp * NP : nullptr;
             wait_bar(tfull_bar(acc), acc_ph);
             __syncwarp();
             ptx::tc_fence_after();
@@ -272,26 +293,27 @@ conv2d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 const int j = 2 * jj + half;
                 if (j < item.nb) {
                     const size_t pix = pix0 + (size_t)j * pstep;
-                    uint4* out = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y) + pix * (size_t)g.ldy);
+                    uint4* out = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y) + pix * (size_t)g.ldy + grp * NP);
                     const __nv_bfloat16* rrow = resb ? resb + pix * (size_t)g.ldr : nullptr;
 #pragma unroll
-                    for (int c0 = 0; c0 < NP; c0 += 32) {
-                        uint4 rv[4];
+                    for (int c0 = 0; c0 < NP; c0 += C::CW) {
+                        constexpr int NV = C::CW / 8;                // 8-channel groups per step
+                        uint4 rv[NV];
 #pragma unroll
-                        for (int c = 0; c < 4; c += 2) {
+                        for (int c = 0; c < NV; c += 2) {
                             rv[c] = rv[c + 1] = make_uint4(0u, 0u, 0u, 0u);
                             if (rrow && valid) ld_nc_v8(rrow + c0 + 8 * c, rv[c], rv[c + 1]);
                         }
-                        uint32_t v[32];
-                        ptx::tmem_ld32(taddr0 + j * NP + c0, v);
+                        uint32_t v[C::CW];
+                        if constexpr (C::CW == 32) ptx::tmem_ld32(taddr0 + j * NP + c0, v); else ptx::tmem_ld16(taddr0 + j * NP + c0, v);
                         ptx::tc_wait_ld();
                         consume_tmem_load(v[0], scratch_smem);
-                        ptx::tmem_zero32(taddr0 + j * NP + c0);
-                        if (j == my_last && c0 + 32 >= NP) release();
+                        if constexpr (C::CW == 32) ptx::tmem_zero32(taddr0 + j * NP + c0); else ptx::tmem_zero16(taddr0 + j * NP + c0);
+                        if (j == my_last && c0 + C::CW >= NP) release();
                         if (valid) {
                             uint4 ovp = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-                            for (int c = 0; c < 4; ++c) {
+                            for (int c = 0; c < NV; ++c) {
                                 const float4 s0 = sc4[(c0 >> 2) + 2 * c], s1 = sc4[(c0 >> 2) + 2 * c + 1];
                                 const float4 h0 = sh4[(c0 >> 2) + 2 * c], h1 = sh4[(c0 >> 2) + 2 * c + 1];
                                 const uint4 rr = rv[c];
@@ -325,16 +347,17 @@ conv2d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (warp == 1) ptx::tmem_dealloc(tmem, C::TMEM_COLS);
 }
 
-template <int KC, int NP>
+template <int KC, int NP, int NCH>
 int launch_r2(const CUtensorMap& map_a, const CUtensorMap& map_w, const R2Geom& g, const float* scale, const float* shift,
               const void* residual, void* y, bool pdl, cudaStream_t st) {
-    using C = R2Cfg<KC, NP>;
-    auto kern = conv2d_rs_kernel<KC, NP>;
+    using C = R2Cfg<KC, NP, NCH>;
+    auto kern = conv2d_rs_kernel<KC, NP, NCH>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) return (int)e;
     int nsm = DSM_NUM_SMS_B200, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    const int nblocks = g.nitems < nsm ? g.nitems : nsm;
+    const long long want = (long long)g.nitems * g.ngroups;        // nitems: per group; a multiple of ngroups CTAs
+    const int nblocks = want < nsm ? (int)want : nsm / g.ngroups * g.ngroups;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(nblocks); cfg.blockDim = dim3(C::THREADS); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -357,18 +380,19 @@ extern "C" int dsm_conv2d_rs_fwd(const void* x, const void* w_packed, const floa
     DsmDeviceGuard dsm_guard_(x);
     if (!x || !w_packed || !y || B <= 0 || H <= 0 || W <= 0) return DSM_EINVAL;
     if (dilation < 1 || dilation > 2 || relu < 0 || relu > 1) return DSM_EINVAL;
-    if ((Cin != 32 && Cin != 64) || (Cout != 32 && Cout != 64)) return DSM_EUNSUPPORTED;
+    if ((Cin != 32 && Cin != 64 && Cin != 128) || (Cout != 32 && Cout != 64 && Cout != 128)) return DSM_EUNSUPPORTED;
+    if (Cin == 128 && Cout == 32) return DSM_EUNSUPPORTED;
     if (rim_in < dilation || rim_in > 2 || rim_out < 0 || rim_out > 2) return DSM_EINVAL;
     if (ldx < Cin || (ldx & 7) || ldy < Cout || (ldy & 15) || (residual && (ldr < Cout || (ldr & 15)))) return DSM_EINVAL;
     if (!dsm_aligned16(x) || !dsm_aligned16(w_packed) || !dsm_aligned32(y) || (residual && !dsm_aligned32(residual))) return DSM_EALIGN;
     const int Hp = H + 2 * rim_in, Wp = W + 2 * rim_in;
     const long long P = (long long)B * Hp * Wp;
     if (P > 0x7fffff00LL) return DSM_EUNSUPPORTED;
-    const int KC = Cin, NP = Cout, row_bytes = KC * 2;
+    const int KC = Cin > 64 ? 64 : Cin, NP = Cout > 64 ? 64 : Cout, row_bytes = KC * 2;
     const int R = 256 / NP;
     R2Geom g;
     memset(&g, 0, sizeof(g));
-    g.B = B; g.H = H; g.W = W; g.ri = rim_in; g.ro = rim_out; g.dil = dilation; g.ldy = ldy; g.ldr = ldr; g.relu = relu; g.Cout = Cout;
+    g.B = B; g.H = H; g.W = W; g.ri = rim_in; g.ro = rim_out; g.dil = dilation; g.ldy = ldy; g.ldr = ldr; g.relu = relu; g.Cout = Cout; g.ngroups = Cout / NP;
     g.row_tiles = dsm_ceil_div(Wp, 128);
     for (int s = 0; s < 2; ++s) {
         const int rows = s < dilation ? (H - s + dilation - 1) / dilation : 0;
@@ -393,8 +417,9 @@ extern "C" int dsm_conv2d_rs_fwd(const void* x, const void* w_packed, const floa
     const bool pdl = (variant & 128) != 0;
     g.nissue = (variant & 8) ? 1 : 3;          // bit 3: one MMA issuer (bit-reproducible), ~10-20 % slower
     cudaStream_t st = (cudaStream_t)stream;
-    if (KC == 32 && NP == 32) return launch_r2<32, 32>(map_a, map_w, g, scale, shift, residual, y, pdl, st);
-    if (KC == 32 && NP == 64) return launch_r2<32, 64>(map_a, map_w, g, scale, shift, residual, y, pdl, st);
-    if (KC == 64 && NP == 32) return launch_r2<64, 32>(map_a, map_w, g, scale, shift, residual, y, pdl, st);
-    return launch_r2<64, 64>(map_a, map_w, g, scale, shift, residual, y, pdl, st);
+    if (Cin == 128) return launch_r2<64, 64, 2>(map_a, map_w, g, scale, shift, residual, y, pdl, st);
+    if (KC == 32 && NP == 32) return launch_r2<32, 32, 1>(map_a, map_w, g, scale, shift, residual, y, pdl, st);
+    if (KC == 32 && NP == 64) return launch_r2<32, 64, 1>(map_a, map_w, g, scale, shift, residual, y, pdl, st);
+    if (KC == 64 && NP == 32) return launch_r2<64, 32, 1>(map_a, map_w, g, scale, shift, residual, y, pdl, st);
+    return launch_r2<64, 64, 1>(map_a, map_w, g, scale, shift, residual, y, pdl, st);
 }

@@ -486,13 +486,16 @@ struct RsCfg {
     static constexpr int BAR_BYTES = 512;
     static constexpr int BUDGET = 225 * 1024 - W_BYTES - 1024 - BAR_BYTES - 2 * NP * 4;
     static constexpr int S_RAW = BUDGET / STAGE_BYTES;
-    static constexpr int STAGES = S_RAW > 8 ? 8 : S_RAW;
+    // A multiple of the three MMA issuers: stage s then always belongs to issuer s % 3, which observes EVERY phase of its
+    // barrier.  (With a depth of 5, 7 or 8 a warp would look at a barrier only every third use, and a parity wait cannot
+    // tell "two phases behind" from "done")
+    static constexpr int STAGES = S_RAW >= 9 ? 9 : (S_RAW >= 6 ? 6 : S_RAW);
     static constexpr int TX_BYTES = KHS * A_ROWS * ROWB;
     static constexpr int ACC_COLS = R * NP;
     static constexpr int TMEM_COLS = 2 * ACC_COLS;                // 256 (NP=16) or 512 (NP=32)
     static constexpr int SMEM = W_BYTES + STAGES * STAGE_BYTES + 1024 + BAR_BYTES + 2 * NP * 4;
     static constexpr int THREADS = 384;                           // warp 0 TMA, warps 1-3 MMA (kh = 0,1,2), warps 4-11 epilogue
-    static_assert(STAGES >= 4, "activation ring too shallow");
+    static_assert(STAGES >= 4 && STAGES % 3 == 0, "activation ring: at least 4 stages, a multiple of the issuer count");
     static_assert((W_TILE % 1024) == 0 && ((NP * ROWB) % 1024) == 0, "weight sub-tiles must keep the swizzle phase");
 };
 
@@ -1788,8 +1791,8 @@ extern "C" int dsm_conv2d_fwd(const void* x, const void* w_packed, const float* 
                               int B, int Cin, int Cout, int H, int W, int ksize, int stride, int dilation, int relu,
                               int rim_in, int rim_out, int ldx, int ldy, int ldr, int y_mode, int variant, void* stream) {
     DsmDeviceGuard dsm_guard_(x);
-    // stride-1 3x3 layers with 32 / 64 channels: the row-sharing kernel (conv2d_rs.cu) unless variant bit 2 asks for the per-tile one
-    if (!(variant & 4) && ksize == 3 && stride == 1 && y_mode == 0 && relu <= 1 && (Cin == 32 || Cin == 64) && (Cout == 32 || Cout == 64) &&
+    // stride-1 3x3 layers with 32 / 64 / 128 channels: the row-sharing kernel (conv2d_rs.cu) unless variant bit 2 asks for the per-tile one
+    if (!(variant & 4) && ksize == 3 && stride == 1 && y_mode == 0 && relu <= 1 && (Cin == 32 || Cin == 64 || Cin == 128) && (Cout == 32 || Cout == 64 || Cout == 128) && !(Cin == 128 && Cout == 32) &&
         !(ldy & 15) && !(ldr & 15) && dsm_aligned32(y) && (!residual || dsm_aligned32(residual)))
         return dsm_conv2d_rs_fwd(x, w_packed, scale, shift, residual, y, B, Cin, Cout, H, W, dilation, relu, rim_in, rim_out,
                                  ldx, ldy, ldr, variant, stream);

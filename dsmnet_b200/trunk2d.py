@@ -82,7 +82,7 @@ class FusedConv2d:
 
     def __init__(self, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d], relu: int, device, variant: Optional[int] = None):
         if variant is None:
-            variant = PDL | (8 if DETERMINISTIC else 0)
+            variant = PDL | (8 if DETERMINISTIC else 0) | int(os.environ.get("DSM_CONV2D_VARIANT", "0"))   # experiments: 4 = per-tile kernels
         w = conv.weight.detach().float()
         self.cout, self.cin, k, k2 = w.shape
         if k != k2 or k not in (1, 3):

@@ -79,7 +79,7 @@ if "--layers" in sys.argv:
             return t(lambda: gl.replay(), 10) / 20
         ms = once()
         rows.append((name, ms * 1e3, fl / ms / 1e9))
-        if conv is not None and conv.k == 3 and conv.stride == 1 and conv.cin <= 64 and conv.cout <= 64:
+        if conv is not None and conv.k == 3 and conv.stride == 1 and conv.cin <= 128 and conv.cout <= 128:
             v0 = conv.variant
             for tag, v in (("  .. per-tile kernel (variant 4)", v0 | 4), ("  .. row-sharing, one MMA issuer (variant 8)", v0 | 8)):
                 conv.variant = v
@@ -96,15 +96,15 @@ if "--layers" in sys.argv:
     layer("64->64 k3 @96x312", lambda: c1(q64[0], q64[1]), 2 * 9 * 64 * 64 * px4, c1)
     layer("64->64 k3 + residual", lambda: c2(q64[0], q64[1], residual=q64[2]), 2 * 9 * 64 * 64 * px4, c2)
     c1, c2, ds = plan.layers[2][0]
-    layer("64->128 k3 (from cat slice)", lambda: c1(cat, q128[0]), 2 * 9 * 64 * 128 * px4)
+    layer("64->128 k3 (from cat slice)", lambda: c1(cat, q128[0]), 2 * 9 * 64 * 128 * px4, c1)
     layer("64->128 k1", lambda: ds(cat, q128[1]), 2 * 64 * 128 * px4)
     c1, c2, ds = plan.layers[2][1]
-    layer("128->128 k3", lambda: c1(q128[0], q128[1]), 2 * 9 * 128 * 128 * px4)
+    layer("128->128 k3", lambda: c1(q128[0], q128[1]), 2 * 9 * 128 * 128 * px4, c1)
     c1, c2, ds = plan.layers[3][1]
-    layer("128->128 k3 dilation 2", lambda: c1(q128[0], q128[1]), 2 * 9 * 128 * 128 * px4)
+    layer("128->128 k3 dilation 2", lambda: c1(q128[0], q128[1]), 2 * 9 * 128 * 128 * px4, c1)
     layer("320->128 k3 (lastconv.0)", lambda: plan.last0(cat, q128[0]), 2 * 9 * 320 * 128 * px4)
     o = torch.empty(2, 32, 96, 312, device=dev)
     layer("128->32 k1 -> fp32 NCHW", lambda: plan.last2(q128[0], o), 2 * 128 * 32 * px4)
-    print("%-44s %10s %10s" % ("trunk layer (batch 2)", "us", "TFLOP/s"))
+    print("%-52s %10s %10s" % ("trunk layer (batch 2)", "us", "TFLOP/s"))
     for name, us, tf in rows:
-        print("%-44s %10.1f %10.1f" % (name, us, tf))
+        print("%-52s %10.1f %10.1f" % (name, us, tf))
