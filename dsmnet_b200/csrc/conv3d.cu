@@ -115,7 +115,9 @@ __device__ __forceinline__ bool wait_bar(uint32_t bar, uint32_t parity) {
     }
 }
 
-template <int KC, int NP, int MODE>
+// WRES (MODE_BOX, one K chunk, 27 taps): all weight tiles stay resident in shared memory and only activation boxes stream
+// through the ring — a third less TMA traffic per tile for the stride-2 32 -> 64 layer (hourglass conv1).
+template <int KC, int NP, int MODE, int WRES = 0>
 struct Cfg {
     static constexpr int ROWB = KC * 2;
     static constexpr int A_ROWS = (MODE == MODE_SHIFT) ? 130 : 128;
@@ -123,18 +125,22 @@ struct Cfg {
     static constexpr int NB = (MODE == MODE_SHIFT) ? 3 : 1;
     static constexpr int B_TILE = NP * ROWB;
     static constexpr int B_BYTES = ((NB * B_TILE + 1023) / 1024) * 1024;
-    static constexpr int STAGE = A_BYTES + B_BYTES;
+    static constexpr int W_RES = WRES ? 27 * B_TILE : 0;
+    static constexpr int TPS = WRES ? 3 : 1;                  // taps per pipeline stage (WRES: the three kw taps of one (kd, kh))
+    static constexpr int STAGE = WRES ? TPS * A_BYTES : A_BYTES + B_BYTES;
     // two CTAs per SM when a useful ring (>= 4 stages) fits in ~100 KB, otherwise one CTA with up to 200 KB
-    static constexpr int CTAS_PER_SM = (3 * STAGE <= 100 * 1024) ? 2 : 1;
-    static constexpr int BUDGET = (CTAS_PER_SM == 2 ? 100 : 200) * 1024;
+    static constexpr int CTAS_PER_SM = (!WRES && 3 * STAGE <= 100 * 1024) ? 2 : 1;
+    static constexpr int BUDGET = WRES ? 224 * 1024 - W_RES : (CTAS_PER_SM == 2 ? 100 : 200) * 1024;
     static constexpr int S_RAW = BUDGET / STAGE;
-    static constexpr int STAGES = S_RAW > 8 ? 8 : (S_RAW < 2 ? 2 : S_RAW);
+    static constexpr int S_CAP = 8;
+    static constexpr int STAGES = S_RAW > S_CAP ? S_CAP : (S_RAW < 2 ? 2 : S_RAW);
     static constexpr int ACC_COLS = NP < 32 ? 32 : NP;        // TMEM columns of one accumulator
     static constexpr int NUM_ACC = 2;                         // double-buffered: MMA of tile i+1 overlaps epilogue of tile i
     static constexpr int TMEM_COLS = NUM_ACC * ACC_COLS;      // 64 / 128 / 256: a power of two
     static constexpr int BAR_BYTES = 512;
-    static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + BAR_BYTES + 2 * NP * 4;
+    static constexpr int SMEM = W_RES + STAGES * STAGE + 1024 /*align slack*/ + BAR_BYTES + 2 * NP * 4;
     static constexpr int THREADS = 192;                       // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+    static_assert(!WRES || (MODE == MODE_BOX && (B_TILE % 1024) == 0), "resident weights: box mode, swizzle-aligned tiles");
 };
 
 // Which tile is it, and does it produce anything?
@@ -193,12 +199,12 @@ __device__ __forceinline__ TileInfo decode_tile(const ConvGeom& g, int t, long l
 //   warps 2..5        : epilogue — tcgen05.ld the finished buffer (lane quadrant = warp % 4),
 //                       hand it back, then affine + residual + ReLU + store while the next tile's
 //                       MMAs already run into the other buffer.
-template <int KC, int NP, int MODE>
+template <int KC, int NP, int MODE, int WRES>
 __global__ void __launch_bounds__(192)
 conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvGeom g,
                     const float* __restrict__ scale, const float* __restrict__ shift,
                     const void* __restrict__ residual, void* __restrict__ y) {
-    using C = Cfg<KC, NP, MODE>;
+    using C = Cfg<KC, NP, MODE, WRES>;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Dp = g.Di + 2 * g.dpad, Hp = g.Hi + 2 * g.ri, Wp = g.Wi + 2 * g.ri;
     const long long plane = (long long)Hp * Wp, vol = plane * Dp;
@@ -206,14 +212,16 @@ conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
     // ---- shared memory carve-up ---------------------------------------------------------
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = ptx::smem_u32(smem_raw);
-    const uint32_t base = (raw + 1023u) & ~1023u;
+    const uint32_t wres = (raw + 1023u) & ~1023u;          // WRES: the 27 resident weight tiles, then the ring
+    const uint32_t base = wres + C::W_RES;
     uint8_t* base_ptr = smem_raw + (base - raw);
-    const uint32_t bars = base + C::STAGES * C::STAGE;     // full[S], empty[S], tmem_full[2], tmem_empty[2], slot, scratch
+    const uint32_t bars = base + C::STAGES * C::STAGE;     // full[S], empty[S], tmem_full[2], tmem_empty[2], [wfull], slot, scratch
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
     auto tfull_bar = [&](int a) { return bars + 8u * (2 * C::STAGES + a); };
     auto tempty_bar = [&](int a) { return bars + 8u * (2 * C::STAGES + C::NUM_ACC + a); };
-    constexpr int NBARS = 2 * C::STAGES + 2 * C::NUM_ACC;
+    const uint32_t wfull_bar = bars + 8u * (2 * C::STAGES + 2 * C::NUM_ACC);
+    constexpr int NBARS = 2 * C::STAGES + 2 * C::NUM_ACC + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + C::STAGES * C::STAGE + 8 * NBARS);
     const uint32_t scratch_smem = bars + 8u * NBARS + 8u;
     float* s_scale = reinterpret_cast<float*>(base_ptr + C::STAGES * C::STAGE + C::BAR_BYTES);
@@ -228,6 +236,7 @@ conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
         ptx::prefetch_tensormap(&maps.a[0]);
         for (int s = 0; s < C::STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
         for (int a = 0; a < C::NUM_ACC; ++a) { ptx::mbar_init(tfull_bar(a), 1); ptx::mbar_init(tempty_bar(a), 4); }
+        ptx::mbar_init(wfull_bar, 1);
         ptx::fence_mbar_init();
     }
     if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), C::TMEM_COLS);
@@ -239,6 +248,15 @@ conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
     ptx::griddep_launch_dependents();
     if (warp == 0) {
         // ================= TMA producer (whole warp walks the loop, one elected lane issues) =================
+        if (WRES) {                                    // the weights are parameters: before the dependency wait
+            if (ptx::elect_one_sync()) {
+                const int nt = g.cls_begin[1] - g.cls_begin[0];
+                ptx::mbar_arrive_expect_tx(wfull_bar, (uint32_t)(nt * C::B_TILE));
+                for (int tp = 0; tp < nt; ++tp)
+                    ptx::tma_load_2d(wres + tp * C::B_TILE, &maps.w, wfull_bar, 0, g.w_row[g.cls_begin[0] + tp]);
+            }
+            __syncwarp();
+        }
         ptx::griddep_wait();                           // the activations are the previous kernel's output
         int it = 0;                                    // ring position, runs on across tiles
         for (int t = blockIdx.x; t < g.ntiles; t += gridDim.x) {
@@ -246,6 +264,26 @@ conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
             if (ti.skip) continue;
             const int tap0 = g.cls_begin[ti.cls];
             const int ntaps = g.cls_begin[ti.cls + 1] - tap0;
+            if (WRES) {
+                // one stage = the three kw taps of a (kd, kh): one barrier round trip per three boxes
+                for (int grp = 0; grp < ntaps / 3; ++grp, ++it) {
+                    const int s = it % C::STAGES;
+                    const uint32_t ph = (uint32_t)(it / C::STAGES) & 1u;
+                    wait_bar(empty_bar(s), ph ^ 1u);
+                    if (ptx::elect_one_sync()) {
+                        ptx::mbar_arrive_expect_tx(full_bar(s), (uint32_t)(3 * 128 * C::ROWB));
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            const int code = g.a_off[tap0 + 3 * grp + j];
+                            ptx::tma_load_5d(base + s * C::STAGE + j * C::A_BYTES, &maps.a[code & 7], full_bar(s), 0,
+                                             ti.w * 16 + ((code >> 4) & 1), ti.h * 8 + ((code >> 5) & 1),
+                                             ti.d + ((code >> 6) & 1), ti.b);
+                        }
+                    }
+                    __syncwarp();
+                }
+                continue;
+            }
             const int ngroups = (MODE == MODE_SHIFT) ? ntaps / 3 : ntaps;
             for (int grp = 0; grp < ngroups; ++grp) {
                 const int tp = tap0 + ((MODE == MODE_SHIFT) ? 3 * grp : grp);
@@ -276,11 +314,12 @@ conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
         // ================= MMA issuer (whole warp walks the loop, one elected lane issues) =================
         constexpr uint32_t idesc = ptx::make_idesc_bf16(NP);
         int it = 0, tcount = 0;
+        if (WRES) { wait_bar(wfull_bar, 0); ptx::tc_fence_after(); }
         for (int t = blockIdx.x; t < g.ntiles; t += gridDim.x) {
             const TileInfo ti = decode_tile<MODE>(g, t, plane, vol, Dp);
             if (ti.skip) continue;
             const int ntaps = g.cls_begin[ti.cls + 1] - g.cls_begin[ti.cls];
-            const int n_it = ((MODE == MODE_SHIFT) ? ntaps / 3 : ntaps) * g.nchunks;
+            const int n_it = ((MODE == MODE_SHIFT || WRES) ? ntaps / 3 : ntaps) * g.nchunks;
             const int acc = tcount & 1;
             const uint32_t acc_ph = (uint32_t)(tcount >> 1) & 1u;
             wait_bar(tempty_bar(acc), acc_ph ^ 1u);        // epilogue has drained this buffer
@@ -291,10 +330,19 @@ conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
                 const uint32_t ph = (uint32_t)(it / C::STAGES) & 1u;
                 wait_bar(full_bar(s), ph);
                 ptx::tc_fence_after();
-                const uint32_t sa = base + s * C::STAGE, sb = sa + C::A_BYTES;
+                const uint32_t sa = base + s * C::STAGE, sb = WRES ? wres + (uint32_t)(3 * i) * C::B_TILE : sa + C::A_BYTES;
                 if (ptx::elect_one_sync()) {
                     const uint64_t ad0 = ptx::make_kmajor_desc(sa, C::ROWB, 0u);
                     const uint64_t bd0 = ptx::make_kmajor_desc(sb, C::ROWB, 0u);
+                    if (WRES) {
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+#pragma unroll
+                            for (int k = 0; k < KC / 16; ++k)
+                                ptx::umma_bf16(d_tmem, ptx::desc_advance(ad0, j * C::A_BYTES + k * 32),
+                                               ptx::desc_advance(bd0, j * C::B_TILE + k * 32), idesc, (i | j | k) ? 1u : 0u);
+                        }
+                    } else
 #pragma unroll
                     for (int j = 0; j < C::NB; ++j) {
 #pragma unroll
@@ -1325,11 +1373,11 @@ void launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, c
     cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
-template <int KC, int NP, int MODE>
+template <int KC, int NP, int MODE, int WRES = 0>
 int launch_cfg(const ConvMaps& maps, const ConvGeom& g, dim3 grid, const float* scale, const float* shift,
                const void* residual, void* y, cudaStream_t st) {
-    using C = Cfg<KC, NP, MODE>;
-    auto kern = conv3d_igemm_kernel<KC, NP, MODE>;
+    using C = Cfg<KC, NP, MODE, WRES>;
+    auto kern = conv3d_igemm_kernel<KC, NP, MODE, WRES>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) return (int)e;
     int nsm = DSM_NUM_SMS_B200, dev = 0;
@@ -1606,6 +1654,11 @@ int conv3d_dispatch(const void* x, const void* w, const float* scale, const floa
     }
     cudaStream_t st = (cudaStream_t)stream;
     g.tx_bytes = (mode == MODE_SHIFT ? 130 : 128) * row_bytes + (mode == MODE_SHIFT ? 3 : 1) * NP * row_bytes;
+    if (mode == MODE_BOX && KC == 32 && NP == 64 && g.nchunks == 1 && !(variant & 512)) {
+        // hourglass conv1 (32 -> 64, stride 2): the 27 weight tiles (110 KB) stay resident, only activation boxes stream
+        g.tx_bytes = 128 * row_bytes;
+        return launch_cfg<32, 64, MODE_BOX, 1>(maps, g, grid, scale, shift, residual, y, st);
+    }
     if (mode == MODE_BOX)   return launch_mode<MODE_BOX>(KC, NP, maps, g, grid, scale, shift, residual, y, st);
     if (mode == MODE_SHIFT) return launch_mode<MODE_SHIFT>(KC, NP, maps, g, grid, scale, shift, residual, y, st);
     return launch_mode<MODE_FLAT>(KC, NP, maps, g, grid, scale, shift, residual, y, st);
