@@ -273,6 +273,8 @@ int main(int argc, char** argv) {
             {1, 32, 32, 48, 96, 312, 1, 0, 1, 1, 1, 0, 8, "32->32 per-tile shift"},
             {1, 32, 1, 48, 96, 312, 1, 0, 0, 1, 0, 1, 8, "classif 32->1 per-tile shift"},
             {1, 64, 32, 24, 48, 156, 2, 1, 0, 1, 1, 0, 8, "conv6 deconv 64->32 per-class"},
+            {1, 64, 64, 12, 24, 78, 1, 0, 1, 0, 1, 0, 4, "conv4 64->64 @12x24x78 per-tile shift"},
+            {1, 64, 64, 12, 24, 78, 1, 0, 1, 0, 1, 0, 0, "conv4 64->64 @12x24x78 default"},
         };
         { int idx = 0; for (auto& c : cases) { if (g_only < 0 || g_only == idx) { Case cc = c; cc.variant |= g_level << 8; fails += run_case(cc, true, 10); } ++idx; } }
     }
