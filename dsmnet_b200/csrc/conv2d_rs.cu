@@ -16,6 +16,7 @@
 // Activations: bf16 [B][H+2r][W+2r][ld] with a zero rim of r >= dil pixels (trunk2d.PaddedImage); ld >= C (channel slices).
 #include "common.cuh"
 #include "ptx.cuh"
+#include "epilogue.cuh"
 #include "tma_host.cuh"
 #include <string.h>
 
@@ -260,6 +261,7 @@ conv2d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
         }
         const float4* sc4 = reinterpret_cast<const float4*>(s_scale);
+        const int emode = epi_mode(g.relu, residual != nullptr);
         const float4* sh4 = reinterpret_cast<const float4*>(s_shift);
         const int Hop = g.H + 2 * g.ro, Wop = g.W + 2 * g.ro;
         int tcount = 0;
@@ -311,30 +313,7 @@ conv2d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         if constexpr (C::CW == 32) ptx::tmem_zero32(taddr0 + j * NP + c0); else ptx::tmem_zero16(taddr0 + j * NP + c0);
                         if (j == my_last && c0 + C::CW >= NP) release();
                         if (valid) {
-                            uint4 ovp = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-                            for (int c = 0; c < NV; ++c) {
-                                const float4 s0 = sc4[(c0 >> 2) + 2 * c], s1 = sc4[(c0 >> 2) + 2 * c + 1];
-                                const float4 h0 = sh4[(c0 >> 2) + 2 * c], h1 = sh4[(c0 >> 2) + 2 * c + 1];
-                                const uint4 rr = rv[c];
-                                float f[8];
-                                f[0] = fmaf(__uint_as_float(v[8 * c + 0]), s0.x, h0.x) + bf16_lo(rr.x);
-                                f[1] = fmaf(__uint_as_float(v[8 * c + 1]), s0.y, h0.y) + bf16_hi(rr.x);
-                                f[2] = fmaf(__uint_as_float(v[8 * c + 2]), s0.z, h0.z) + bf16_lo(rr.y);
-                                f[3] = fmaf(__uint_as_float(v[8 * c + 3]), s0.w, h0.w) + bf16_hi(rr.y);
-                                f[4] = fmaf(__uint_as_float(v[8 * c + 4]), s1.x, h1.x) + bf16_lo(rr.z);
-                                f[5] = fmaf(__uint_as_float(v[8 * c + 5]), s1.y, h1.y) + bf16_hi(rr.z);
-                                f[6] = fmaf(__uint_as_float(v[8 * c + 6]), s1.z, h1.z) + bf16_lo(rr.w);
-                                f[7] = fmaf(__uint_as_float(v[8 * c + 7]), s1.w, h1.w) + bf16_hi(rr.w);
-                                if (g.relu) {
-#pragma unroll
-                                    for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
-                                }
-                                uint4 ov;
-                                ov.x = pack_bf16x2(f[0], f[1]); ov.y = pack_bf16x2(f[2], f[3]);
-                                ov.z = pack_bf16x2(f[4], f[5]); ov.w = pack_bf16x2(f[6], f[7]);
-                                if (c & 1) st_v8(out + (c0 >> 3) + c - 1, ovp, ov); else ovp = ov;   // one 256-bit store per 16 channels
-                            }
+                            DSM_EPI_DISPATCH(emode, epi_store256, 4, v, sc4 + (c0 >> 2), sh4 + (c0 >> 2), rv, out + (c0 >> 3))   // 256-bit stores
                         }
                     }
                 }

@@ -21,6 +21,7 @@
 // Roofline: tensor pipe; algorithmic flops = 2*27*Cin*Cout*voxels (transposed: input voxels).
 #include "common.cuh"
 #include "ptx.cuh"
+#include "epilogue.cuh"
 #include "tma_host.cuh"
 #include <string.h>
 
@@ -364,6 +365,7 @@ conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
         const int q = warp & 3;                            // TMEM lane quadrant this warp may read
         const int r = q * 32 + lane;                       // row of the tile
         int tcount = 0;
+        const int emode = epi_mode(g.relu, residual != nullptr);
         for (int t = blockIdx.x; t < g.ntiles; t += gridDim.x) {
             const TileInfo ti = decode_tile<MODE>(g, t, plane, vol, Dp);
             if (ti.skip) continue;
@@ -456,22 +458,7 @@ conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant
                         if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
                     }
                     if (valid) {
-#pragma unroll
-                        for (int qq = 0; qq < CH / 8; ++qq) {
-                            float f[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                f[i] = fmaf(__uint_as_float(v[qq * 8 + i]), s_scale[c0 + qq * 8 + i], s_shift[c0 + qq * 8 + i]);
-                            const uint4 rv = res ? __ldg(res + (c0 / 8) + qq) : make_uint4(0u, 0u, 0u, 0u);
-                            const float rr[8] = {bf16_lo(rv.x), bf16_hi(rv.x), bf16_lo(rv.y), bf16_hi(rv.y),
-                                                 bf16_lo(rv.z), bf16_hi(rv.z), bf16_lo(rv.w), bf16_hi(rv.w)};
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) f[i] = fuse_act(f[i], rr[i], g.relu);
-                            uint4 ov;
-                            ov.x = pack_bf16x2(f[0], f[1]); ov.y = pack_bf16x2(f[2], f[3]);
-                            ov.z = pack_bf16x2(f[4], f[5]); ov.w = pack_bf16x2(f[6], f[7]);
-                            out[(c0 / 8) + qq] = ov;
-                        }
+                        DSM_EPI_DISPATCH(emode, epi_store128, CH / 8, v, s_scale + c0, s_shift + c0, res ? res + c0 / 8 : nullptr, out + c0 / 8)
                     }
                 }
             }
@@ -882,6 +869,7 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
         constexpr int NV = NP / 8;                                // uint4 per bf16 output row
         const float4* sc4 = reinterpret_cast<const float4*>(s_scale);
+        const int emode = epi_mode(g.relu, residual != nullptr);
         const float4* sh4 = reinterpret_cast<const float4*>(s_shift);
         int tcount = 0;
         for (int t = item0; t < g.nitems; t += item_step) {
@@ -978,25 +966,7 @@ conv3d_rs_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         if (j == my_last) release();
                         if (valid) {
                             uint4* out = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y) + o0 + j * ostep);
-                            uint4 ovp = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-                            for (int c = 0; c < NV; ++c) {
-                                const float4 s0 = sc4[2 * c], s1 = sc4[2 * c + 1], h0 = sh4[2 * c], h1 = sh4[2 * c + 1];
-                                const uint4 rr = rv[jj][c];
-                                float f[8];
-                                f[0] = fuse_act(fmaf(__uint_as_float(v[8 * c + 0]), s0.x, h0.x), bf16_lo(rr.x), g.relu);
-                                f[1] = fuse_act(fmaf(__uint_as_float(v[8 * c + 1]), s0.y, h0.y), bf16_hi(rr.x), g.relu);
-                                f[2] = fuse_act(fmaf(__uint_as_float(v[8 * c + 2]), s0.z, h0.z), bf16_lo(rr.y), g.relu);
-                                f[3] = fuse_act(fmaf(__uint_as_float(v[8 * c + 3]), s0.w, h0.w), bf16_hi(rr.y), g.relu);
-                                f[4] = fuse_act(fmaf(__uint_as_float(v[8 * c + 4]), s1.x, h1.x), bf16_lo(rr.z), g.relu);
-                                f[5] = fuse_act(fmaf(__uint_as_float(v[8 * c + 5]), s1.y, h1.y), bf16_hi(rr.z), g.relu);
-                                f[6] = fuse_act(fmaf(__uint_as_float(v[8 * c + 6]), s1.z, h1.z), bf16_lo(rr.w), g.relu);
-                                f[7] = fuse_act(fmaf(__uint_as_float(v[8 * c + 7]), s1.w, h1.w), bf16_hi(rr.w), g.relu);
-                                uint4 ov;
-                                ov.x = pack_bf16x2(f[0], f[1]); ov.y = pack_bf16x2(f[2], f[3]);
-                                ov.z = pack_bf16x2(f[4], f[5]); ov.w = pack_bf16x2(f[6], f[7]);
-                                if (c & 1) st_v8(out + c - 1, ovp, ov); else ovp = ov;      // one 256-bit store per 16 channels
-                            }
+                            DSM_EPI_DISPATCH(emode, epi_store256, NV, v, sc4, sh4, rv[jj], out)   // one 256-bit store per 16 channels
                         }
                     }
                 }
@@ -1260,6 +1230,7 @@ conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
         } else {
         const float4* sc4 = reinterpret_cast<const float4*>(s_scale);
+        const int emode = epi_mode(g.relu, residual != nullptr);
         const float4* sh4 = reinterpret_cast<const float4*>(s_shift);
         int tcount = 0;
         for (int t = tile0; t < g.ntiles; t += tile_step) {
@@ -1317,25 +1288,7 @@ conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     if (jj == 1) release();
                     if (valid[jj]) {
                         uint4* out = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y) + off[jj]);
-                        uint4 ovp = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-                        for (int c = 0; c < NV; ++c) {
-                            const float4 s0 = sc4[2 * c], s1 = sc4[2 * c + 1], h0 = sh4[2 * c], h1 = sh4[2 * c + 1];
-                            const uint4 rr = rv[jj][c];
-                            float f[8];
-                            f[0] = fuse_act(fmaf(__uint_as_float(v[8 * c + 0]), s0.x, h0.x), bf16_lo(rr.x), g.relu);
-                            f[1] = fuse_act(fmaf(__uint_as_float(v[8 * c + 1]), s0.y, h0.y), bf16_hi(rr.x), g.relu);
-                            f[2] = fuse_act(fmaf(__uint_as_float(v[8 * c + 2]), s0.z, h0.z), bf16_lo(rr.y), g.relu);
-                            f[3] = fuse_act(fmaf(__uint_as_float(v[8 * c + 3]), s0.w, h0.w), bf16_hi(rr.y), g.relu);
-                            f[4] = fuse_act(fmaf(__uint_as_float(v[8 * c + 4]), s1.x, h1.x), bf16_lo(rr.z), g.relu);
-                            f[5] = fuse_act(fmaf(__uint_as_float(v[8 * c + 5]), s1.y, h1.y), bf16_hi(rr.z), g.relu);
-                            f[6] = fuse_act(fmaf(__uint_as_float(v[8 * c + 6]), s1.z, h1.z), bf16_lo(rr.w), g.relu);
-                            f[7] = fuse_act(fmaf(__uint_as_float(v[8 * c + 7]), s1.w, h1.w), bf16_hi(rr.w), g.relu);
-                            uint4 ov;
-                            ov.x = pack_bf16x2(f[0], f[1]); ov.y = pack_bf16x2(f[2], f[3]);
-                            ov.z = pack_bf16x2(f[4], f[5]); ov.w = pack_bf16x2(f[6], f[7]);
-                            if (c & 1) st_v8(out + c - 1, ovp, ov); else ovp = ov;      // one 256-bit store per 16 channels
-                        }
+                        DSM_EPI_DISPATCH(emode, epi_store256, NV, v, sc4, sh4, rv[jj], out)   // one 256-bit store per 16 channels
                     }
                 }
             }

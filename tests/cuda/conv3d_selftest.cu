@@ -284,6 +284,15 @@ int main(int argc, char** argv) {
         Case c2 = {1, 32, 32, 48, 96, 312, 1, 0, 1, 1, 1, 0, 32, "32->32 dbg32 (no TMA)"};
         run_case(c2, true, 10);
     }
+    if (!strcmp(what, "dbgdc2")) {
+        // is the class-sharing kernel's epilogue bound by its residual loads or by its stores?
+        for (int v : {0, 96}) {
+            Case c = {1, 64, 32, 24, 48, 156, 2, 1, 0, 1, 1, 0, v, "conv6 deconv 64->32 +res"};
+            run_case(c, true, 10);
+            Case c2 = {1, 64, 32, 24, 48, 156, 2, 1, 0, 0, 1, 0, v, "conv6 deconv 64->32 no res"};
+            run_case(c2, true, 10);
+        }
+    }
     if (!strcmp(what, "dbgdc")) {
         // timing experiments on the class-sharing transposed-conv kernel (results are garbage for v != 0)
         for (int v : {0, 16, 32, 64, 48, 80, 96, 112}) {
