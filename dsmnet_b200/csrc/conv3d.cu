@@ -1233,10 +1233,9 @@ conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int emode = epi_mode(g.relu, residual != nullptr);
         const float4* sh4 = reinterpret_cast<const float4*>(s_shift);
         int tcount = 0;
-        for (int t = tile0; t < g.ntiles; t += tile_step) {
-            const long long p0 = (long long)t * 128;
-            if (dc_skip(p0, g.P, plane, vol, Dp)) continue;
-            const long long p = p0 + r;
+        // where this thread's two output voxels (its two classes) of tile t live; false when neither exists
+        auto locate = [&](int t, bool* valid, size_t* off) -> bool {
+            const long long p = (long long)t * 128 + r;
             bool interior = false;
             int ob = 0, dz = 0, hy = 0, wx = 0;
             if (p < g.P) {
@@ -1246,11 +1245,6 @@ conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 interior = dp >= 1 && dp <= g.D && hp >= 1 && hp <= g.H && wp >= 1 && wp <= g.W;
                 ob = fp.b; dz = 2 * (dp - 1); hy = 2 * (hp - 1); wx = 2 * (wp - 1);
             }
-            const int acc = tcount & 1;
-            const uint32_t acc_ph = (uint32_t)(tcount >> 1) & 1u;
-            ++tcount;
-            const uint32_t taddr0 = tmem + ((uint32_t)(q * 32) << 16) + acc * C::ACC_COLS;
-            bool valid[2]; size_t off[2];
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
                 const int c = kDcPosClass[2 * half + jj];
@@ -1259,6 +1253,17 @@ conv3d_dc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 off[jj] = g.y_f32 ? (((size_t)ob * g.Do + od) * g.Ho + oh) * g.Wo + ow
                                   : ((((size_t)ob * (g.Do + 2) + od + 1) * (g.Ho + 2) + oh + 1) * (g.Wo + 2) + ow + 1) * (size_t)g.Cout + ch0;
             }
+            return interior;
+        };
+        for (int t = tile0; t < g.ntiles; t += tile_step) {
+            const long long p0 = (long long)t * 128;
+            if (dc_skip(p0, g.P, plane, vol, Dp)) continue;
+            const int acc = tcount & 1;
+            const uint32_t acc_ph = (uint32_t)(tcount >> 1) & 1u;
+            ++tcount;
+            const uint32_t taddr0 = tmem + ((uint32_t)(q * 32) << 16) + acc * C::ACC_COLS;
+            bool valid[2]; size_t off[2];
+            locate(t, valid, off);
             auto release = [&]() {
                 ptx::tc_fence_before();
                 __syncwarp();
