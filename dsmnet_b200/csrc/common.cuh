@@ -74,5 +74,11 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);   // .x = lo (low 16 bits)
     return *reinterpret_cast<uint32_t*>(&v);
 }
+// the same with ReLU folded into the conversion (F2FP.RELU): bf16(max(x, 0)) == max(bf16(x), 0), rounding is monotonic
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));   // first source -> upper half
+    return r;
+}
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }

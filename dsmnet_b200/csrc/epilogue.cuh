@@ -20,22 +20,41 @@ __device__ __forceinline__ float epi_act(float a, float r) {
     return a;
 }
 
+// sm_100 packed fp32 arithmetic: two IEEE fp32 FMAs / adds per instruction (bit-identical to the scalar forms)
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "add.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
+// two channels: acc (fp32 bits) * scale + shift, residual pair packed as bf16x2 -> one packed bf16x2
+template <int MODE>
+__device__ __forceinline__ uint32_t epi_pack2(uint32_t v0, uint32_t v1, float s0, float s1, float h0, float h1, uint32_t rr) {
+    float a0, a1;
+    ffma2(a0, a1, __uint_as_float(v0), __uint_as_float(v1), s0, s1, h0, h1);
+    if (MODE == 4) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+    if (MODE >= 2) fadd2(a0, a1, a0, a1, bf16_lo(rr), bf16_hi(rr));
+    return (MODE == 1 || MODE == 3) ? pack_bf16x2_relu(a0, a1) : pack_bf16x2(a0, a1);   // a final ReLU rides on the conversion
+}
+
 // 8 accumulators v[0..7] (fp32 bits), their scale / shift (two float4 each) and 8 bf16 residuals (one uint4) -> 8 bf16 (one uint4)
 template <int MODE>
 __device__ __forceinline__ uint4 epi_pack8(const uint32_t* v, const float4& s0, const float4& s1, const float4& h0, const float4& h1,
                                            const uint4& rr) {
-    float f[8];
-    f[0] = epi_act<MODE>(fmaf(__uint_as_float(v[0]), s0.x, h0.x), bf16_lo(rr.x));
-    f[1] = epi_act<MODE>(fmaf(__uint_as_float(v[1]), s0.y, h0.y), bf16_hi(rr.x));
-    f[2] = epi_act<MODE>(fmaf(__uint_as_float(v[2]), s0.z, h0.z), bf16_lo(rr.y));
-    f[3] = epi_act<MODE>(fmaf(__uint_as_float(v[3]), s0.w, h0.w), bf16_hi(rr.y));
-    f[4] = epi_act<MODE>(fmaf(__uint_as_float(v[4]), s1.x, h1.x), bf16_lo(rr.z));
-    f[5] = epi_act<MODE>(fmaf(__uint_as_float(v[5]), s1.y, h1.y), bf16_hi(rr.z));
-    f[6] = epi_act<MODE>(fmaf(__uint_as_float(v[6]), s1.z, h1.z), bf16_lo(rr.w));
-    f[7] = epi_act<MODE>(fmaf(__uint_as_float(v[7]), s1.w, h1.w), bf16_hi(rr.w));
     uint4 ov;
-    ov.x = pack_bf16x2(f[0], f[1]); ov.y = pack_bf16x2(f[2], f[3]);
-    ov.z = pack_bf16x2(f[4], f[5]); ov.w = pack_bf16x2(f[6], f[7]);
+    ov.x = epi_pack2<MODE>(v[0], v[1], s0.x, s0.y, h0.x, h0.y, rr.x);
+    ov.y = epi_pack2<MODE>(v[2], v[3], s0.z, s0.w, h0.z, h0.w, rr.y);
+    ov.z = epi_pack2<MODE>(v[4], v[5], s1.x, s1.y, h1.x, h1.y, rr.z);
+    ov.w = epi_pack2<MODE>(v[6], v[7], s1.z, s1.w, h1.z, h1.w, rr.w);
     return ov;
 }
 
