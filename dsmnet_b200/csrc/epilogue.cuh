@@ -20,22 +20,6 @@ __device__ __forceinline__ float epi_act(float a, float r) {
     return a;
 }
 
-// sm_100 packed fp32 arithmetic: two IEEE fp32 FMAs / adds per instruction (bit-identical to the scalar forms)
-__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
-    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
-        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
-        "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
-        "mov.b64 {%0, %1}, rd;\n\t}"
-        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
-}
-__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
-    asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
-        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
-        "add.rn.f32x2 rd, ra, rb;\n\t"
-        "mov.b64 {%0, %1}, rd;\n\t}"
-        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
-}
-
 // two channels: acc (fp32 bits) * scale + shift, residual pair packed as bf16x2 -> one packed bf16x2
 template <int MODE>
 __device__ __forceinline__ uint32_t epi_pack2(uint32_t v0, uint32_t v1, float s0, float s1, float h0, float h1, uint32_t rr) {

@@ -286,11 +286,13 @@ upsample_softargmin_kernel(const float* __restrict__ cost, float* __restrict__ d
         const float da = a1 - a0, db = b1 - b0;
         const int n = s_cnt[dl];
         for (int k = 0; k < n; ++k, ++d) {
+            // the two pixels of the thread as packed fp32 pairs (FFMA2 / FADD2: same results, 7 instead of 10 instructions)
             const float l = s_l1[d];
-            const float ea = ex2_approx(fmaf(l, da, a0));
-            const float eb = ex2_approx(fmaf(l, db, b0));
-            sa += ea; ta = fmaf(fd, ea, ta);
-            sb += eb; tb = fmaf(fd, eb, tb);
+            float xa, xb;
+            ffma2(xa, xb, l, l, da, db, a0, b0);
+            const float ea = ex2_approx(xa), eb = ex2_approx(xb);
+            fadd2(sa, sb, sa, sb, ea, eb);
+            ffma2(ta, tb, fd, fd, ea, eb, ta, tb);
             fd += 1.f;
         }
         a0 = a1; b0 = b1;
