@@ -300,31 +300,36 @@ unpack_ndhwc_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, 
 }
 
 // NCHW fp32 -> NHWC bf16 with a zero rim of `rim` pixels, [B][H+2r][W+2r][C] (the feature-map layout of the fused volume
-// convolution and of the 2-D trunk); CTA = one padded image row, rim included
+// convolution and of the 2-D trunk).  One thread per PADDED pixel: a warp's 32 neighbouring pixels make every per-channel load
+// a coalesced 128-byte run, and the thread's C channels leave as consecutive 16-byte stores (a warp fills a contiguous
+// 32 * 2C-byte span) — no shared-memory transpose, all of a thread's loads in flight at once.  (The first version staged a row
+// through shared memory with a division per element and 16-way conflicted stores: 24.6 us for 11.5 MB at PSMNet's size.)
 __global__ void __launch_bounds__(256)
 pack_nhwc_kernel(const float* __restrict__ x, uint4* __restrict__ y, const float* __restrict__ x2, uint4* __restrict__ y2,
-                 int C, int H, int W, int rim) {
+                 int C, int H, int W, int rim, long long npix) {
     if (blockIdx.z == 1) { x = x2; y = y2; }                                  // the second map of a pair (one launch for both)
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __nv_bfloat16* s = reinterpret_cast<__nv_bfloat16*>(smem_raw);            // [W][C]
-    const int yp = blockIdx.x, b = blockIdx.y;
-    const int yy = yp - rim, Wp = W + 2 * rim, cpv = C / 8;
-    const bool row_ok = yy >= 0 && yy < H;
-    if (row_ok) {
-        const float* src = x + ((size_t)b * C * H + yy) * W;
-        const size_t cstride = (size_t)H * W;
-        for (int i = threadIdx.x; i < C * W; i += blockDim.x) {
-            const int c = i / W, xx = i - c * W;
-            s[xx * C + c] = __float2bfloat16_rn(__ldg(src + c * cstride + xx));
-        }
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;            // padded pixel index over [B][H+2r][W+2r]
+    if (i >= npix) return;
+    const int Hp = H + 2 * rim, Wp = W + 2 * rim, cpv = C / 8;
+    const int xp = (int)(i % Wp);
+    const long long t = i / Wp;
+    const int yp = (int)(t % Hp), b = (int)(t / Hp);
+    const int xx = xp - rim, yy = yp - rim;
+    uint4* o = y + (size_t)i * cpv;
+    if (xx < 0 || xx >= W || yy < 0 || yy >= H) {
+        for (int k = 0; k < cpv; ++k) o[k] = make_uint4(0u, 0u, 0u, 0u);
+        return;
     }
-    __syncthreads();
-    const uint4* v = reinterpret_cast<const uint4*>(s);
-    uint4* orow = y + ((size_t)b * (H + 2 * rim) + yp) * (size_t)(Wp * cpv);
-    for (int i = threadIdx.x; i < Wp * cpv; i += blockDim.x) {
-        const int xp = i / cpv, k = i - xp * cpv;
-        const int xx = xp - rim;
-        orow[i] = (row_ok && xx >= 0 && xx < W) ? v[xx * cpv + k] : make_uint4(0u, 0u, 0u, 0u);
+    const size_t cstride = (size_t)H * W;
+    const float* src = x + ((size_t)b * C * H + yy) * W + xx;
+#pragma unroll 4
+    for (int k = 0; k < cpv; ++k) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = __ldg(src + (size_t)(8 * k + e) * cstride);
+        uint4 v;
+        v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]); v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
+        o[k] = v;
     }
 }
 
@@ -335,11 +340,10 @@ extern "C" int dsm_pack_nhwc_bf16(const float* x, void* y, int B, int C, int H, 
     if (!x || !y || B <= 0 || C <= 0 || H <= 0 || W <= 0 || rim < 0 || rim > 8) return DSM_EINVAL;
     if (C % 8 != 0 || H > 65535 * 32 || B > 65535) return DSM_EUNSUPPORTED;
     if (!dsm_aligned16(y)) return DSM_EALIGN;
-    const size_t smem = (size_t)W * C * sizeof(__nv_bfloat16);
-    if (smem > 200 * 1024) return DSM_EUNSUPPORTED;
-    cudaError_t e = cudaFuncSetAttribute(pack_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    pack_nhwc_kernel<<<dim3(H + 2 * rim, B), 256, smem, (cudaStream_t)stream>>>(x, (uint4*)y, nullptr, nullptr, C, H, W, rim);
+    const long long npix = (long long)B * (H + 2 * rim) * (W + 2 * rim);
+    const long long blocks = dsm_ceil_div_ll(npix, 256);
+    if (blocks > 0x7fffffffLL) return DSM_EUNSUPPORTED;
+    pack_nhwc_kernel<<<dim3((unsigned)blocks, 1, 1), 256, 0, (cudaStream_t)stream>>>(x, (uint4*)y, nullptr, nullptr, C, H, W, rim, npix);
     return dsm_launch_status();
 }
 
@@ -348,11 +352,10 @@ extern "C" int dsm_pack_nhwc_bf16_pair(const float* xL, const float* xR, void* y
     if (!xL || !xR || !yL || !yR || B <= 0 || C <= 0 || H <= 0 || W <= 0 || rim < 0 || rim > 8) return DSM_EINVAL;
     if (C % 8 != 0 || H > 65535 * 32 || B > 65535) return DSM_EUNSUPPORTED;
     if (!dsm_aligned16(yL) || !dsm_aligned16(yR)) return DSM_EALIGN;
-    const size_t smem = (size_t)W * C * sizeof(__nv_bfloat16);
-    if (smem > 200 * 1024) return DSM_EUNSUPPORTED;
-    cudaError_t e = cudaFuncSetAttribute(pack_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    pack_nhwc_kernel<<<dim3(H + 2 * rim, B, 2), 256, smem, (cudaStream_t)stream>>>(xL, (uint4*)yL, xR, (uint4*)yR, C, H, W, rim);
+    const long long npix = (long long)B * (H + 2 * rim) * (W + 2 * rim);
+    const long long blocks = dsm_ceil_div_ll(npix, 256);
+    if (blocks > 0x7fffffffLL) return DSM_EUNSUPPORTED;
+    pack_nhwc_kernel<<<dim3((unsigned)blocks, 1, 2), 256, 0, (cudaStream_t)stream>>>(xL, (uint4*)yL, xR, (uint4*)yR, C, H, W, rim, npix);
     return dsm_launch_status();
 }
 

@@ -420,3 +420,21 @@ def test_fused_ssim_vs_reference_formula(B, C, H, W):
     assert s.shape == (B, 1, H, W)
     assert e_mine <= max(2.0 * e_torch, 2e-4)
     assert rel_err(gb, gb64) < 2e-3
+
+
+@pytest.mark.parametrize("B,C,H,W,rim", [(1, 32, 96, 312, 1), (2, 64, 7, 13, 2), (3, 8, 5, 33, 0), (1, 128, 11, 70, 2)])
+def test_pack_nhwc_bf16_bit_exact(B, C, H, W, rim):
+    """dsm_pack_nhwc_bf16 / _pair: NCHW fp32 -> zero-rimmed NHWC bf16, bit-identical to torch's RNE conversion; the rim is written (zero)"""
+    from dsmnet_b200.conv3d import pack_features_nhwc, pack_feature_pair_nhwc
+    torch.manual_seed(3)
+    a = torch.randn(B, C, H, W, device="cuda") * 3
+    b = torch.randn(B, C, H, W, device="cuda")
+    def ref(x):
+        out = torch.zeros(B, H + 2 * rim, W + 2 * rim, C, device="cuda", dtype=torch.bfloat16)
+        out[:, rim:rim + H, rim:rim + W, :] = x.permute(0, 2, 3, 1).to(torch.bfloat16)
+        return out
+    one = pack_features_nhwc(a, rim)
+    pa, pb = pack_feature_pair_nhwc(a, b, rim)
+    torch.cuda.synchronize()
+    assert torch.equal(one.view(torch.int16), ref(a).view(torch.int16))
+    assert torch.equal(pa.view(torch.int16), ref(a).view(torch.int16)) and torch.equal(pb.view(torch.int16), ref(b).view(torch.int16))
