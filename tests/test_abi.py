@@ -96,3 +96,18 @@ def test_training_wrappers_have_no_cpu_fallback():
         upsample_softargmin(torch.zeros(1, 2, 3, 4, requires_grad=True), (8, 12, 16), True)
     with pytest.raises(_lib.DsmError):
         T.conv_c1(PaddedVolume(y, 1, 32, 2, 2, 2), nn.Conv3d(32, 1, 3, padding=1))
+
+
+def test_trunk_entry_points_validate_arguments():
+    """the 2-D trunk entry points reject bad pointers / shapes / alignment before any CUDA call
+    (x, w, scale, shift, residual, y, B, Cin, Cout, H, W, dilation, relu, rim_in, rim_out, ldx, ldy, ldr, variant, stream)"""
+    L = _lib.lib()
+    ok = (64, 64, 0, 0, 0, 64)
+    assert L.dsm_conv2d_rs_fwd(0, 0, 0, 0, 0, 0, 1, 64, 64, 8, 8, 1, 1, 1, 1, 64, 64, 64, 0, 0) == -1      # null pointers
+    assert L.dsm_conv2d_rs_fwd(*ok, 1, 48, 64, 8, 8, 1, 1, 1, 1, 64, 64, 64, 0, 0) == -2                  # Cin not in {32, 64, 128}
+    assert L.dsm_conv2d_rs_fwd(*ok, 1, 128, 32, 8, 8, 1, 1, 2, 2, 128, 32, 32, 0, 0) == -2                # 128 -> 32 stays per-tile
+    assert L.dsm_conv2d_rs_fwd(*ok, 1, 64, 64, 8, 8, 2, 1, 1, 1, 64, 64, 64, 0, 0) == -1                  # rim narrower than the dilation
+    assert L.dsm_conv2d_rs_fwd(64, 64, 0, 0, 0, 80, 1, 64, 64, 8, 8, 1, 1, 1, 1, 64, 64, 64, 0, 0) == -3  # y not 32-byte aligned
+    assert L.dsm_conv2d_rs_fwd(*ok, 1, 64, 64, 8, 8, 1, 1, 1, 1, 64, 72, 64, 0, 0) == -1                  # ldy not a multiple of 16
+    assert L.dsm_conv2d_rs_fwd(*ok, 1, 64, 64, 8, 8, 1, 2, 1, 1, 64, 64, 64, 0, 0) == -1                  # relu mode 2 is 3-D only
+    assert L.dsm_spp_workspace_bytes(1, 63, 200) == 0 and L.dsm_spp_workspace_bytes(1, 96, 312) > 0       # AvgPool2d(64) needs 64 x 64
