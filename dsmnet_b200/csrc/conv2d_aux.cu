@@ -65,62 +65,100 @@ conv_first_kernel(const float* __restrict__ img, const float* __restrict__ w, co
 }
 
 // ---- SPP ------------------------------------------------------------------------------------------------------
-// cells: [B][ch][cw][128] fp32 sums over 8x8 pixel cells (ch = H/8, cw = W/8, floor)
+// cells: [B][ch][cw][128] fp32 sums over 8x8 pixel cells (ch = H/8, cw = W/8, floor).  CTA = one cell: thread (dx = t / 16,
+// cg = t % 16) reads the 8 channels [8 cg, 8 cg + 8) of the cell's column dx for all 8 rows as 16-byte loads (all in flight),
+// then the 8 columns are added through shared memory.
 __global__ void __launch_bounds__(128)
 spp_cells_kernel(const __nv_bfloat16* __restrict__ skip, float* __restrict__ cells, int H, int W, int rim, int ld, int ch, int cw) {
-    const int cx = blockIdx.x, cy = blockIdx.y, b = blockIdx.z, c = threadIdx.x;
+    const int cx = blockIdx.x, cy = blockIdx.y, b = blockIdx.z, t = threadIdx.x;
+    const int dx = t >> 4, cg = t & 15;
     const int Wp = W + 2 * rim, Hp = H + 2 * rim;
-    float s = 0.f;
-    for (int dy = 0; dy < 8; ++dy) {
-        const __nv_bfloat16* row = skip + (((size_t)b * Hp + cy * 8 + dy + rim) * Wp + cx * 8 + rim) * ld + c;
+    __shared__ float part[8][128];
+    const __nv_bfloat16* p0 = skip + (((size_t)b * Hp + cy * 8 + rim) * Wp + cx * 8 + dx + rim) * ld + cg * 8;
+    uint4 v[8];
 #pragma unroll
-        for (int dx = 0; dx < 8; ++dx) s += __bfloat162float(row[(size_t)dx * ld]);
+    for (int dy = 0; dy < 8; ++dy) v[dy] = __ldg(reinterpret_cast<const uint4*>(p0 + (size_t)dy * Wp * ld));
+    float s[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s[e] = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 8; ++dy) {                             // rows in order, as the reference's pooling window is summed
+        s[0] += bf16_lo(v[dy].x); s[1] += bf16_hi(v[dy].x); s[2] += bf16_lo(v[dy].y); s[3] += bf16_hi(v[dy].y);
+        s[4] += bf16_lo(v[dy].z); s[5] += bf16_hi(v[dy].z); s[6] += bf16_lo(v[dy].w); s[7] += bf16_hi(v[dy].w);
     }
-    cells[(((size_t)b * ch + cy) * cw + cx) * 128 + c] = s;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) part[dx][cg * 8 + e] = s[e];
+    __syncthreads();
+    float a = 0.f;
+#pragma unroll
+    for (int x = 0; x < 8; ++x) a += part[x][t];
+    cells[(((size_t)b * ch + cy) * cw + cx) * 128 + t] = a;
 }
 
 struct SppLevel { int k8, ph, pw, off; };        // window = k8 x k8 cells; pooled map ph x pw; `off` = first element of this level in `br`
 struct SppGeom { int B, H, W, ch, cw; SppLevel lv[4]; };
 
-// br: for level l, [B][ph+2][pw+2][32] fp32 = relu(BN(conv1x1(avgpool))) with the ring of relu(shift); one CTA per output pixel
-__global__ void __launch_bounds__(32)
+// br: for level l, [B][ph+2][pw+2][32] fp32 = relu(BN(conv1x1(avgpool))) with the ring of relu(shift); one CTA of 128 threads
+// per output pixel: thread = channel for the pooling (up to 64 cells, four independent partial sums so that the loads overlap)
+// and for its share of the 128 -> 32 dot products (see below).
+__global__ void __launch_bounds__(128)
 spp_branch_kernel(const float* __restrict__ cells, const float* __restrict__ w /*[4][32][128]*/, const float* __restrict__ scale /*[4][32]*/,
                   const float* __restrict__ shift, float* __restrict__ br, SppGeom g) {
     const int l = blockIdx.z & 3, b = blockIdx.z >> 2;
     const SppLevel L = g.lv[l];
     const int px = blockIdx.x, py = blockIdx.y;
     if (px >= L.pw + 2 || py >= L.ph + 2) return;
-    const int co = threadIdx.x;
+    const int t = threadIdx.x, co = t & 31, q = t >> 5;
+    __shared__ float part[4][32];
     float acc = 0.f;
-    if (px >= 1 && px <= L.pw && py >= 1 && py <= L.ph) {
-        __shared__ float pooled[128];
+    if (px >= 1 && px <= L.pw && py >= 1 && py <= L.ph) {          // uniform over the CTA
         const float inv = 1.f / (float)(L.k8 * L.k8 * 64);
-        for (int c = co; c < 128; c += 32) {
-            float s = 0.f;
+        const float* cb = cells + (((size_t)b * g.ch + (py - 1) * L.k8) * g.cw + (px - 1) * L.k8) * 128 + t;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        if (L.k8 >= 4) {
+            for (int yy = 0; yy < L.k8; ++yy) {
+                const float* r = cb + (size_t)yy * g.cw * 128;
+                for (int xx = 0; xx < L.k8; xx += 4) {
+                    s0 += r[(xx + 0) * 128]; s1 += r[(xx + 1) * 128]; s2 += r[(xx + 2) * 128]; s3 += r[(xx + 3) * 128];
+                }
+            }
+        } else {
             for (int yy = 0; yy < L.k8; ++yy)
-                for (int xx = 0; xx < L.k8; ++xx)
-                    s += cells[(((size_t)b * g.ch + (py - 1) * L.k8 + yy) * g.cw + (px - 1) * L.k8 + xx) * 128 + c];
-            pooled[c] = s * inv;
+                for (int xx = 0; xx < L.k8; ++xx) s0 += cb[((size_t)yy * g.cw + xx) * 128];
         }
-        __syncwarp();
-        const float* wr = w + ((size_t)l * 32 + co) * 128;
-        for (int c = 0; c < 128; ++c) acc = fmaf(pooled[c], wr[c], acc);
+        // 128 -> 32 dot products with the thread still owning channel t: lanes read 32 consecutive weights of output co (the
+        // PyTorch layout [co][c]; one lane per OUTPUT read 32 different 128-byte lines per load), a warp reduces its 32
+        // channels with shuffles, the four warps' partial sums meet in shared memory
+        const float pc = ((s0 + s1) + (s2 + s3)) * inv;
+        const float* wl = w + (size_t)l * 32 * 128 + t;
+#pragma unroll 4
+        for (int o = 0; o < 32; ++o) {
+            float p = pc * __ldg(wl + o * 128);
+            p += __shfl_xor_sync(0xffffffffu, p, 16); p += __shfl_xor_sync(0xffffffffu, p, 8);
+            p += __shfl_xor_sync(0xffffffffu, p, 4);  p += __shfl_xor_sync(0xffffffffu, p, 2);
+            p += __shfl_xor_sync(0xffffffffu, p, 1);
+            if (co == 0) part[q][o] = p;
+        }
+        __syncthreads();
+        acc = (part[0][co] + part[1][co]) + (part[2][co] + part[3][co]);
     }
-    const float v = fmaxf(fmaf(acc, scale[l * 32 + co], shift[l * 32 + co]), 0.f);
-    br[L.off + (((size_t)b * (L.ph + 2) + py) * (L.pw + 2) + px) * 32 + co] = v;
+    if (t < 32) {
+        const float v = fmaxf(fmaf(acc, scale[l * 32 + co], shift[l * 32 + co]), 0.f);
+        br[L.off + (((size_t)b * (L.ph + 2) + py) * (L.pw + 2) + px) * 32 + co] = v;
+    }
 }
 
 // bilinear upsampling of the four branch maps to H x W, bf16 into channels [coff + 32*slot, +32) of the concat buffer;
 // slot order in the concatenation is (branch4, branch3, branch2, branch1) = levels (3, 2, 1, 0) (submodule.py:138)
 __global__ void __launch_bounds__(256)
 spp_upsample_kernel(const float* __restrict__ br, __nv_bfloat16* __restrict__ cat, SppGeom g, int rim, int ld, int coff, int align_corners) {
-    const long long n = (long long)g.B * g.H * g.W * 16;                 // (pixel, level, 8-channel group)
-    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (i >= n) return;
-    const int grp = (int)(i & 3), l = (int)((i >> 2) & 3);
-    long long t = i >> 4;
-    const int x = (int)(t % g.W); t /= g.W;
-    const int y = (int)(t % g.H); const int b = (int)(t / g.H);
+    // grid = (ceil(16 W / 256), B * H): a thread is (pixel x of row blockIdx.y, level, 8-channel group).  (The first version
+    // decoded a flat 64-bit index with four 64-bit divisions per thread: most of the SPP's 48 us.)
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= g.W * 16) return;
+    const int grp = i & 3, l = (i >> 2) & 3;
+    const int x = i >> 4;
+    const int b = (int)blockIdx.y / g.H, y = (int)blockIdx.y - b * g.H;
     const SppLevel L = g.lv[l];
     const int ih = L.ph + 2, iw = L.pw + 2;
     float sy, sx;
@@ -201,14 +239,13 @@ extern "C" int dsm_spp_fwd(const void* skip, const float* w, const float* scale,
     SppGeom g;
     if (!spp_geom(g, B, H, W)) return DSM_EINVAL;                   // the skip tensor must be at least 64 x 64 (AvgPool2d(64))
     if (ws_bytes < dsm_spp_workspace_bytes(B, H, W)) return DSM_EINVAL;
-    if (!dsm_aligned16(cat) || !dsm_aligned16(ws)) return DSM_EALIGN;
-    if (B > 16383 || g.ch > 65535) return DSM_EUNSUPPORTED;
+    if (!dsm_aligned16(cat) || !dsm_aligned16(ws) || !dsm_aligned16(skip)) return DSM_EALIGN;
+    if (B > 16383 || g.ch > 65535 || (long long)B * H > 65535 || W > (1 << 24)) return DSM_EUNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     float* cells = static_cast<float*>(ws);
     float* br = cells + (size_t)B * g.ch * g.cw * 128;
     spp_cells_kernel<<<dim3(g.cw, g.ch, B), 128, 0, st>>>(static_cast<const __nv_bfloat16*>(skip), cells, H, W, rim, ld, g.ch, g.cw);
-    spp_branch_kernel<<<dim3(g.lv[3].pw + 2, g.lv[3].ph + 2, B * 4), 32, 0, st>>>(cells, w, scale, shift, br, g);
-    const long long n = (long long)B * H * W * 16;
-    spp_upsample_kernel<<<(unsigned)dsm_ceil_div_ll(n, 256), 256, 0, st>>>(br, static_cast<__nv_bfloat16*>(cat), g, rim, ld, coff, align_corners);
+    spp_branch_kernel<<<dim3(g.lv[3].pw + 2, g.lv[3].ph + 2, B * 4), 128, 0, st>>>(cells, w, scale, shift, br, g);
+    spp_upsample_kernel<<<dim3((unsigned)dsm_ceil_div(W * 16, 256), (unsigned)(B * H)), 256, 0, st>>>(br, static_cast<__nv_bfloat16*>(cat), g, rim, ld, coff, align_corners);
     return dsm_launch_status();
 }
